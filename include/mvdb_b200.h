@@ -1,0 +1,180 @@
+/*
+ * mvdb_b200.h -- C ABI of the B200-native flat inner-product engine that
+ * replaces the faiss-cpu boundary of cnmoro/MiniVectorDB.
+ *
+ * The reference reaches its hot path through exactly four faiss SWIG calls
+ * (reference paths relative to /root/reference):
+ *
+ *   faiss.IndexFlatIP(d)        minivectordb/vector_database.py:43, 511
+ *                               minivectordb/sharded_vector_database.py:80, 639
+ *   faiss.normalize_L2(x)       vector_database.py:45, 475 ; sharded_...py:82, 604
+ *   index.add(x)                vector_database.py:46, 512 ; sharded_...py:83, 640
+ *   index.search(q, k)          vector_database.py:497, 514 ; sharded_...py:626, 642
+ *
+ * and owns the matrix on the host through np.vstack / np.delete
+ * (vector_database.py:72, 107, 126).  Every entry point below names the
+ * reference interface it stands in for.  All functions are plain C: opaque
+ * handle, raw pointers and sizes, int return code (0 = ok, <0 = error, text
+ * from mvdb_last_error()).  No torch / C++ types cross this boundary.
+ *
+ * There is NO CPU fallback: every compute entry point needs a CUDA device and
+ * fails with MVDB_ERR_CUDA when none is present.
+ *
+ * Thread-safety: any number of host threads may call mvdb_index_search*
+ * concurrently on one index (each call runs on its own stream/workspace);
+ * mutating calls (add / remove / compact / reset) are serialised internally
+ * and never move rows under a running search (mvdb_index_compact waits for
+ * running searches to drain).
+ */
+#ifndef MVDB_B200_H
+#define MVDB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVDB_ABI_VERSION 1
+
+enum {
+    MVDB_OK = 0,
+    MVDB_ERR_ARG = -1,    /* bad argument (dimension mismatch, k <= 0, NULL, row out of range) */
+    MVDB_ERR_CUDA = -2,   /* CUDA runtime / driver failure, or no device */
+    MVDB_ERR_OOM = -3,    /* device or pinned-host allocation failed */
+    MVDB_ERR_STATE = -4   /* operation not valid in the index's current state */
+};
+
+/* scan kernel selection (mvdb_index_set_option "scan_variant") */
+enum {
+    MVDB_SCAN_AUTO = 0,
+    MVDB_SCAN_TMA = 1,    /* cp.async.bulk + mbarrier ring, warp-specialised producer */
+    MVDB_SCAN_LDG = 2     /* direct 128-bit ld.global.nc loads */
+};
+
+typedef struct mvdb_index mvdb_index; /* opaque; one HBM-resident matrix on one device */
+
+/* ---- library ---------------------------------------------------------- */
+
+int mvdb_abi_version(void);
+/* Thread-local text of the last error returned to this thread. */
+const char* mvdb_last_error(void);
+/* Number of visible CUDA devices (0 and MVDB_OK when there is none). */
+int mvdb_device_count(int* count);
+
+/* ---- index lifetime ---------------------------------------------------
+ * Replaces faiss.IndexFlatIP(d) (vector_database.py:43).  `capacity_hint`
+ * rows of address space are reserved up front; physical HBM is mapped in
+ * chunks as rows arrive, so row addresses never move while the index grows
+ * (0 = default reservation). */
+int mvdb_index_create(int d, int device, uint64_t capacity_hint, mvdb_index** out);
+int mvdb_index_destroy(mvdb_index* ix);
+/* Drop every row (fresh IndexFlatIP, as _build_index does at vector_database.py:43). */
+int mvdb_index_reset(mvdb_index* ix);
+
+/* Tunables; unknown names -> MVDB_ERR_ARG.
+ *   "scan_variant"  MVDB_SCAN_*          "fused_k_max"  largest k served by the fused select
+ *   "grid_ctas"     CTAs of the scan kernel (0 = one per SM)
+ *   "consumer_warps" consumer warps per CTA of the TMA scan (0 = auto) */
+int mvdb_index_set_option(mvdb_index* ix, const char* name, int64_t value);
+
+/* ---- ingest -------------------------------------------------------------
+ * Replaces index.add(x) (vector_database.py:46) and the np.vstack append
+ * (vector_database.py:72, 107).  x: n x d float32, row-major, HOST memory.
+ * normalize != 0 additionally applies faiss.normalize_L2 semantics to every
+ * row on the device while it is written (vector_database.py:45): rows with
+ * zero norm are stored unchanged.  *first_row receives the row number of
+ * x[0]; rows are numbered densely in arrival order, as faiss does. */
+int mvdb_index_add(mvdb_index* ix, const float* x, uint64_t n, int normalize, int64_t* first_row);
+/* Same with x in DEVICE memory of the index's device. */
+int mvdb_index_add_device(mvdb_index* ix, const float* x_dev, uint64_t n, int normalize,
+                          int64_t* first_row);
+/* Append n rows of the counter-based synthetic generator (bench / tests;
+ * bit-identical to oracle/faiss_flat_ip.c:orc_synth_rows), generated and
+ * normalised on the device.  dist: 0 bell, 1 uniform[0,1). */
+int mvdb_index_add_synthetic(mvdb_index* ix, uint64_t seed, int64_t row0, uint64_t n, int dist,
+                             int normalize, int64_t* first_row);
+
+/* ---- delete -------------------------------------------------------------
+ * Replaces np.delete (vector_database.py:126; sharded_...py:229-232).  Rows
+ * are tombstoned (never returned again); numbering of the other rows is
+ * unchanged until mvdb_index_compact.  Unknown / already deleted rows ->
+ * MVDB_ERR_ARG and nothing is changed. */
+int mvdb_index_remove_rows(mvdb_index* ix, const int64_t* rows, uint64_t n);
+/* Squeeze tombstoned rows out, PRESERVING the order of live rows (so that
+ * exact-tie order, which follows row numbers, matches a reference that
+ * renumbers on every delete: vector_database.py:138-152).  After it, live
+ * row i of the old numbering is row rank(i).  *ntotal_out = new row count. */
+int mvdb_index_compact(mvdb_index* ix, int64_t* ntotal_out);
+
+/* ---- introspection ------------------------------------------------------ */
+int mvdb_index_dim(const mvdb_index* ix, int* d);
+/* ntotal = rows incl. tombstones (faiss Index.ntotal); nlive = rows a search can return. */
+int mvdb_index_ntotal(const mvdb_index* ix, int64_t* ntotal, int64_t* nlive);
+/* Copy row `row` (as stored, i.e. normalised if it was added so) into out[d]
+ * (host).  Stands in for self.embeddings[row] (vector_database.py:55). */
+int mvdb_index_reconstruct(mvdb_index* ix, int64_t row, float* out);
+/* Copy rows [row0, row0+n) into out[n*d] (host). */
+int mvdb_index_reconstruct_n(mvdb_index* ix, int64_t row0, uint64_t n, float* out);
+/* Device address / leading dimension (floats) of the resident matrix, and
+ * of the live-row bitmask (bit r&31 of word r>>5 set = row r live). */
+int mvdb_index_device_view(mvdb_index* ix, const float** matrix_dev, int64_t* ld,
+                           const uint32_t** live_dev);
+
+/* ---- search -------------------------------------------------------------
+ * Replaces index.search(q, k) (vector_database.py:497) and, with `mask`, the
+ * reference's gather-into-a-temporary-index branch (vector_database.py:
+ * 508-523): instead of copying admissible rows, the scan applies the filter
+ * as a bitmask in its epilogue.
+ *
+ *   q     nq x d float32 row-major (host)
+ *   mask  NULL, or ceil(mask_rows/8) bytes (host): bit (r & 7) of byte (r >> 3)
+ *         set = row r admissible (numpy.packbits(..., bitorder="little")).
+ *         Rows >= mask_rows (appended after the caller built the mask) are
+ *         not admissible.  mask_rows is ignored when mask is NULL.
+ *   normalize_queries != 0: apply faiss.normalize_L2 to each query first
+ *         (vector_database.py:475)
+ *   D     nq x k float32 (host): inner products, best first
+ *   I     nq x k int64  (host): row numbers; when fewer than k rows are
+ *         admissible the tail is (-FLT_MAX, -1), exactly as faiss pads
+ *         (consumed at vector_database.py:500).
+ * Order: score descending; exact ties by ascending row number. */
+int mvdb_index_search(mvdb_index* ix, const float* q, int64_t nq, int64_t k, const uint8_t* mask,
+                      uint64_t mask_rows, int normalize_queries, float* D, int64_t* I);
+
+/* Device-buffer flavour for callers that keep queries/results in HBM (the
+ * sharded path and the bench's device-resident leg).  All pointers are device
+ * pointers on the index's device; `stream` is a cudaStream_t (NULL = default
+ * stream); the call only enqueues work.  mask_dev: ceil(mask_rows/32) uint32
+ * words (bits past mask_rows clear) or NULL.  label_offset is added to every returned row number (global
+ * numbering of a row shard).  `workspace` must come from
+ * mvdb_index_workspace_create and must not be shared by concurrent calls. */
+typedef struct mvdb_workspace mvdb_workspace;
+int mvdb_index_workspace_create(mvdb_index* ix, mvdb_workspace** out);
+int mvdb_index_workspace_destroy(mvdb_workspace* ws);
+int mvdb_index_search_device(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, int64_t nq,
+                             int64_t k, const uint32_t* mask_dev, uint64_t mask_rows,
+                             int normalize_queries, int64_t label_offset, float* D_dev,
+                             int64_t* I_dev, void* stream);
+
+/* ---- helpers ------------------------------------------------------------ */
+/* faiss.normalize_L2(x) on host data, in place (vector_database.py:475):
+ * copies to `device`, normalises with the ingest kernel, copies back. */
+int mvdb_normalize_L2(float* x, uint64_t n, int d, int device);
+
+/* Merge `nparts` per-shard result lists (each nq x k, best first, labels
+ * already global, padding (-FLT_MAX,-1)) into the global best-first top-k.
+ * D_parts / I_parts are laid out [part][nq][k] in DEVICE memory -- the shape
+ * an all-gather of per-GPU results produces.  Enqueues on `stream`. */
+int mvdb_merge_topk_device(int device, const float* D_parts, const int64_t* I_parts, int nparts,
+                           int64_t nq, int64_t k, float* D_out, int64_t* I_out, void* stream);
+
+/* Number of kernel launches issued by this library since load (bench.py's
+ * "gpu_launches" claim is read from here). */
+uint64_t mvdb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVDB_B200_H */

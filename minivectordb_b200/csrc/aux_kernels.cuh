@@ -1,0 +1,264 @@
+// aux_kernels.cuh -- ingest, tombstones, large-k selection, shard merge.
+#pragma once
+#include <cfloat>
+
+#include "select.cuh"
+
+namespace mvdb {
+
+// ---------------------------------------------------------------------------
+// K1 ingest: one warp per row; optional faiss.normalize_L2 semantics
+// (ref vector_database.py:45 -- nr = sum x^2 in fp32, scale by
+// (float)(1.0/sqrtf(nr)) when nr > 0); the row is written with zero padding
+// up to the leading dimension.  kSynth generates the row instead of reading it.
+// ---------------------------------------------------------------------------
+template <bool kSynth>
+__global__ void __launch_bounds__(256) append_rows_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                          uint64_t n, int d, int64_t ld, int normalize,
+                                                          uint64_t seed, uint64_t synth_row0, int dist) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+    for (uint64_t r = warp; r < n; r += nwarps) {
+        float* out = dst + r * ld;
+        const float* in = kSynth ? nullptr : src + r * uint64_t(d);
+        float nr = 0.f;
+        for (int c = lane; c < d; c += kWarp) {
+            float v = kSynth ? synth_value(seed, synth_row0 + r, uint32_t(c), dist) : in[c];
+            nr = fmaf(v, v, nr);
+        }
+        float inv = 1.f;
+        bool scale = false;
+        if (normalize) {
+            nr = warp_allsum(nr);
+            if (nr > 0.f) {
+                inv = renorm_scale(nr);
+                scale = true;
+            }
+        }
+        for (int c = lane; c < ld; c += kWarp) {
+            float v = 0.f;
+            if (c < d) {
+                v = kSynth ? synth_value(seed, synth_row0 + r, uint32_t(c), dist) : in[c];
+                if (scale) v *= inv;
+            }
+            out[c] = v;
+        }
+    }
+}
+
+// in-place normalisation of a dense [n][d] buffer (mvdb_normalize_L2)
+__global__ void __launch_bounds__(256) normalize_dense_kernel(float* x, uint64_t n, int d) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+    for (uint64_t r = warp; r < n; r += nwarps) {
+        float* row = x + r * uint64_t(d);
+        float nr = 0.f;
+        for (int c = lane; c < d; c += kWarp) nr = fmaf(row[c], row[c], nr);
+        nr = warp_allsum(nr);
+        if (nr > 0.f) {
+            float inv = renorm_scale(nr);
+            for (int c = lane; c < d; c += kWarp) row[c] *= inv;
+        }
+    }
+}
+
+// live bitmask maintenance ---------------------------------------------------
+__global__ void set_live_range_kernel(uint32_t* live, uint64_t row0, uint64_t n) {
+    // one thread per 32-row word touched by [row0, row0+n)
+    uint64_t w0 = row0 >> 5, w1 = (row0 + n + 31) >> 5;
+    uint64_t w = w0 + uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (w >= w1) return;
+    uint64_t lo = max(row0, w << 5), hi = min(row0 + n, (w + 1) << 5);
+    if (hi <= lo) return;
+    uint32_t nb = uint32_t(hi - lo);
+    uint32_t bits = (nb == 32 ? 0xFFFFFFFFu : ((1u << nb) - 1u)) << uint32_t(lo & 31);
+    atomicOr(live + w, bits);
+}
+__global__ void clear_live_rows_kernel(uint32_t* live, const int64_t* rows, uint64_t n) {
+    uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t r = uint64_t(rows[i]);
+    atomicAnd(live + (r >> 5), ~(1u << uint32_t(r & 31)));
+}
+
+// order-preserving compaction: scratch[i] = x[src_rows[i]] (whole padded rows)
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float4* __restrict__ x, float4* __restrict__ out,
+                                                          const uint32_t* __restrict__ src_rows, uint64_t m,
+                                                          int ld4) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+    for (uint64_t i = warp; i < m; i += nwarps) {
+        const float4* s = x + uint64_t(src_rows[i]) * ld4;
+        float4* o = out + i * ld4;
+        for (int c = lane; c < ld4; c += kWarp) o[c] = s[c];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K5 large-k selection over the score images written by the scan in
+// all_ord mode.  Keys are unique 64-bit (ord << 32 | ~row), so an 8-round
+// MSB-first radix select finds the k-th largest key exactly with no tie
+// handling; survivors are appended unordered and then bitonic-sorted.
+// ---------------------------------------------------------------------------
+struct RadixState {
+    uint64_t prefix;      // bits decided so far (high to low)
+    uint64_t mask;        // which bits are decided
+    uint64_t remaining;   // rank still to resolve inside the current prefix (1-based)
+    unsigned int hist[256];
+    unsigned int out_count;
+};
+
+__device__ __forceinline__ uint64_t ord_key(uint32_t ord, uint32_t row) {
+    return ord ? ((uint64_t(ord) << 32) | uint64_t(0xFFFFFFFFu - row)) : kEmptyKey;
+}
+
+__global__ void radix_init_kernel(RadixState* st, uint64_t k) {
+    if (threadIdx.x == 0) {
+        st->prefix = 0;
+        st->mask = 0;
+        st->remaining = k;
+        st->out_count = 0;
+    }
+    if (threadIdx.x < 256) st->hist[threadIdx.x] = 0;
+}
+
+__global__ void __launch_bounds__(512) radix_hist_kernel(const uint32_t* __restrict__ ord, uint32_t n,
+                                                         RadixState* st, int shift) {
+    __shared__ unsigned int h[256];
+    if (threadIdx.x < 256) h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t prefix = st->prefix, mask = st->mask;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint64_t key = ord_key(ord[i], i);
+        if ((key & mask) == prefix) atomicAdd(&h[(key >> shift) & 0xFF], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 256 && h[threadIdx.x]) atomicAdd(&st->hist[threadIdx.x], h[threadIdx.x]);
+}
+
+__global__ void radix_pick_kernel(RadixState* st, int shift) {
+    // single thread: walk the digits from the largest down
+    if (threadIdx.x == 0) {
+        uint64_t rem = st->remaining;
+        int b = 255;
+        for (; b > 0; b--) {
+            unsigned int c = st->hist[b];
+            if (rem <= c) break;
+            rem -= c;
+        }
+        // if even digit 0 does not hold the rank (fewer than k keys match), the
+        // k-th key is the empty key: digit 0, rank clamps
+        st->remaining = rem;
+        st->prefix |= uint64_t(b) << shift;
+        st->mask |= uint64_t(0xFF) << shift;
+    }
+    __syncthreads();
+    if (threadIdx.x < 256) st->hist[threadIdx.x] = 0;
+}
+
+// append every non-empty key >= the selected threshold (st->prefix)
+__global__ void __launch_bounds__(512) radix_collect_kernel(const uint32_t* __restrict__ ord, uint32_t n,
+                                                            RadixState* st, uint64_t* out, uint32_t out_cap) {
+    const uint64_t thr = st->prefix;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint64_t key = ord_key(ord[i], i);
+        if (key != kEmptyKey && key >= thr) {
+            unsigned int pos = atomicAdd(&st->out_count, 1u);
+            if (pos < out_cap) out[pos] = key;
+        }
+    }
+}
+
+// fill keys[count .. npad) with the empty key (count read from the device)
+__global__ void pad_keys_kernel(uint64_t* keys, const RadixState* st, uint32_t npad) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t cnt = min(st->out_count, npad);
+    if (i >= cnt && i < npad) keys[i] = kEmptyKey;
+}
+
+struct BlockSyncer {
+    __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+
+// single-CTA bitonic sort (descending) of npad <= 16384 keys through shared memory
+__global__ void __launch_bounds__(1024) sort_keys_smem_kernel(uint64_t* keys, uint32_t npad) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint64_t* a = reinterpret_cast<uint64_t*>(smem);
+    for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x) a[i] = keys[i];
+    __syncthreads();
+    bitonic_sort_desc(a, int(npad), int(threadIdx.x), int(blockDim.x), BlockSyncer());
+    for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x) keys[i] = a[i];
+}
+
+// one compare-exchange stage of a global-memory bitonic sort (any npad)
+__global__ void __launch_bounds__(256) sort_keys_global_step_kernel(uint64_t* a, uint64_t npad, uint64_t size,
+                                                                    uint64_t stride) {
+    uint64_t t = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= (npad >> 1)) return;
+    uint64_t i = 2 * t - (t & (stride - 1));
+    uint64_t j = i + stride;
+    bool desc = (i & size) == 0;
+    uint64_t x = a[i], y = a[j];
+    if ((x < y) == desc) {
+        a[i] = y;
+        a[j] = x;
+    }
+}
+
+__global__ void keys_to_results_kernel(const uint64_t* keys, uint32_t navail, int64_t k, float* D, int64_t* I,
+                                       int64_t label_offset) {
+    int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= k) return;
+    uint64_t key = (i < int64_t(navail)) ? keys[i] : kEmptyKey;
+    if (key == kEmptyKey) {
+        D[i] = -FLT_MAX;
+        I[i] = -1;
+    } else {
+        D[i] = key_score(key);
+        I[i] = int64_t(key_row(key)) + label_offset;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// shard merge (sharded path): per query, merge nparts best-first lists.
+// Key = (score image, ~position) with position = part * k + i, so equal scores
+// keep shard order then in-shard order (= ascending global row when shards
+// are contiguous row blocks).  One CTA per query; npad keys in shared memory.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) merge_topk_kernel(const float* __restrict__ Dp, const int64_t* __restrict__ Ip,
+                                                         int nparts, int64_t nq, int64_t k, uint32_t npad,
+                                                         float* D, int64_t* I) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint64_t* a = reinterpret_cast<uint64_t*>(smem);
+    const int64_t qi = blockIdx.x;
+    const uint32_t total = uint32_t(nparts * k);
+    for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x) {
+        uint64_t key = kEmptyKey;
+        if (i < total) {
+            uint32_t part = i / uint32_t(k), j = i % uint32_t(k);
+            size_t off = (size_t(part) * nq + qi) * k + j;
+            if (Ip[off] >= 0) key = make_key(Dp[off], i);
+        }
+        a[i] = key;
+    }
+    __syncthreads();
+    bitonic_sort_desc(a, int(npad), int(threadIdx.x), int(blockDim.x), BlockSyncer());
+    for (int64_t i = threadIdx.x; i < k; i += blockDim.x) {
+        uint64_t key = a[i];
+        if (key == kEmptyKey) {
+            D[qi * k + i] = -FLT_MAX;
+            I[qi * k + i] = -1;
+        } else {
+            uint32_t pos = key_row(key);
+            uint32_t part = pos / uint32_t(k), j = pos % uint32_t(k);
+            size_t off = (size_t(part) * nq + qi) * k + j;
+            D[qi * k + i] = Dp[off];
+            I[qi * k + i] = Ip[off];
+        }
+    }
+}
+
+}  // namespace mvdb

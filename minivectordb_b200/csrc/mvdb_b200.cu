@@ -1,0 +1,1073 @@
+// mvdb_b200.cu -- host side of the C ABI declared in include/mvdb_b200.h.
+//
+// One mvdb_index = one HBM-resident, growable, row-major fp32 matrix on one
+// B200 plus a live-row bitmask (tombstones).  It stands in for the faiss
+// IndexFlatIP object and the numpy `embeddings` matrix that the reference's
+// VectorDatabase owns (ref minivectordb/vector_database.py:12, 17, 43-46).
+//
+// Memory: the matrix lives in a virtual-address reservation sized for the
+// whole device (cuMemAddressReserve); physical HBM is mapped behind it chunk
+// by chunk (cuMemCreate/cuMemMap) as rows arrive.  Appending therefore never
+// moves a row and never copies the matrix (the reference pays an O(N*d)
+// np.vstack per insert, vector_database.py:72), and a search running
+// concurrently with an append keeps valid pointers.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <shared_mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/mvdb_b200.h"
+#include "aux_kernels.cuh"
+#include "scan.cuh"
+
+using namespace mvdb;
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU_OK(expr)                                                                        \
+    do {                                                                                   \
+        cudaError_t e__ = (expr);                                                          \
+        if (e__ != cudaSuccess)                                                            \
+            return fail(e__ == cudaErrorMemoryAllocation ? MVDB_ERR_OOM : MVDB_ERR_CUDA,   \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
+                        __LINE__);                                                         \
+    } while (0)
+#define RC_OK(expr)             \
+    do {                        \
+        int rc__ = (expr);      \
+        if (rc__ != MVDB_OK) return rc__; \
+    } while (0)
+#define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------
+// driver entry points for virtual memory management, resolved at run time so
+// that the library has no link-time dependency on libcuda (it must dlopen on
+// a GPU-less build box for the symbol-export test).
+// ---------------------------------------------------------------------------
+struct DriverVmm {
+    CUresult (*AddressReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+    CUresult (*AddressFree)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*Create)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+    CUresult (*Release)(CUmemGenericAllocationHandle) = nullptr;
+    CUresult (*Map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+    CUresult (*Unmap)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*SetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+    CUresult (*GetGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+    bool ok = false;
+};
+
+static DriverVmm* driver_vmm() {
+    static DriverVmm api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        if (getenv("MVDB_NO_VMM")) return;
+        auto get = [](const char* name, void** fn) {
+            cudaDriverEntryPointQueryResult st;
+            return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &st) == cudaSuccess &&
+                   st == cudaDriverEntryPointSuccess && *fn != nullptr;
+        };
+        bool ok = true;
+        ok &= get("cuMemAddressReserve", (void**)&api.AddressReserve);
+        ok &= get("cuMemAddressFree", (void**)&api.AddressFree);
+        ok &= get("cuMemCreate", (void**)&api.Create);
+        ok &= get("cuMemRelease", (void**)&api.Release);
+        ok &= get("cuMemMap", (void**)&api.Map);
+        ok &= get("cuMemUnmap", (void**)&api.Unmap);
+        ok &= get("cuMemSetAccess", (void**)&api.SetAccess);
+        ok &= get("cuMemGetAllocationGranularity", (void**)&api.GetGranularity);
+        (void)cudaGetLastError();
+        api.ok = ok;
+    });
+    return &api;
+}
+
+// Growable device buffer.  VMM flavour: stable base address.  Fallback
+// (MVDB_NO_VMM=1 or driver without VMM): cudaMalloc + copy, address may move
+// (callers take the exclusive move lock around ensure()).
+class GrowBuf {
+  public:
+    int init(int device, size_t reserve_bytes) {
+        device_ = device;
+        DriverVmm* v = driver_vmm();
+        if (v->ok) {
+            CUmemAllocationProp prop = {};
+            prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+            prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+            prop.location.id = device;
+            size_t gran = 0;
+            if (v->GetGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) == CUDA_SUCCESS && gran) {
+                gran_ = gran;
+                reserved_ = align_up(std::max(reserve_bytes, gran), gran);
+                if (v->AddressReserve(&base_, reserved_, 0, 0, 0) == CUDA_SUCCESS) {
+                    vmm_ = true;
+                    return MVDB_OK;
+                }
+            }
+        }
+        vmm_ = false;
+        return MVDB_OK;
+    }
+    bool stable() const { return vmm_; }
+    void* ptr() const { return vmm_ ? reinterpret_cast<void*>(base_) : plain_; }
+    size_t mapped() const { return mapped_; }
+
+    // Make at least `bytes` usable.  New bytes are zero-filled on `stream`.
+    int ensure(size_t bytes, cudaStream_t stream) {
+        if (bytes <= mapped_) return MVDB_OK;
+        if (vmm_) {
+            DriverVmm* v = driver_vmm();
+            while (mapped_ < bytes) {
+                // chunk doubles with the buffer, capped at 1 GiB, so handle
+                // count stays small from kilobyte test indexes to 180 GB shards
+                size_t want = std::min<size_t>(std::max(mapped_, gran_), size_t(1) << 30);
+                want = std::max(want, std::min(bytes - mapped_, size_t(1) << 30));
+                size_t chunk = align_up(want, gran_);
+                if (mapped_ + chunk > reserved_ && bytes <= reserved_) chunk = reserved_ - mapped_;
+                if (mapped_ + chunk > reserved_)
+                    return fail(MVDB_ERR_OOM, "index capacity reservation (%zu bytes) exhausted", reserved_);
+                CUmemAllocationProp prop = {};
+                prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+                prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+                prop.location.id = device_;
+                CUmemGenericAllocationHandle h;
+                CUresult r = v->Create(&h, chunk, &prop, 0);
+                if (r != CUDA_SUCCESS)
+                    return fail(r == CUDA_ERROR_OUT_OF_MEMORY ? MVDB_ERR_OOM : MVDB_ERR_CUDA,
+                                "cuMemCreate(%zu) failed: %d", chunk, int(r));
+                r = v->Map(base_ + mapped_, chunk, 0, h, 0);
+                if (r != CUDA_SUCCESS) {
+                    v->Release(h);
+                    return fail(MVDB_ERR_CUDA, "cuMemMap failed: %d", int(r));
+                }
+                CUmemAccessDesc acc = {};
+                acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+                acc.location.id = device_;
+                acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+                r = v->SetAccess(base_ + mapped_, chunk, &acc, 1);
+                if (r != CUDA_SUCCESS) {
+                    v->Unmap(base_ + mapped_, chunk);
+                    v->Release(h);
+                    return fail(MVDB_ERR_CUDA, "cuMemSetAccess failed: %d", int(r));
+                }
+                CU_OK(cudaMemsetAsync(reinterpret_cast<void*>(base_ + mapped_), 0, chunk, stream));
+                chunks_.push_back({h, chunk});
+                mapped_ += chunk;
+            }
+            return MVDB_OK;
+        }
+        size_t cap = std::max(bytes, mapped_ * 2);
+        cap = align_up(std::max<size_t>(cap, 1 << 16), 256);
+        void* np = nullptr;
+        CU_OK(cudaMalloc(&np, cap));
+        CU_OK(cudaMemsetAsync(np, 0, cap, stream));
+        if (plain_) {
+            CU_OK(cudaMemcpyAsync(np, plain_, mapped_, cudaMemcpyDeviceToDevice, stream));
+            CU_OK(cudaStreamSynchronize(stream));
+            cudaFree(plain_);
+        }
+        plain_ = np;
+        mapped_ = cap;
+        return MVDB_OK;
+    }
+    void destroy() {
+        if (vmm_) {
+            DriverVmm* v = driver_vmm();
+            size_t off = 0;
+            for (auto& c : chunks_) {
+                v->Unmap(base_ + off, c.bytes);
+                v->Release(c.h);
+                off += c.bytes;
+            }
+            chunks_.clear();
+            if (base_) v->AddressFree(base_, reserved_);
+            base_ = 0;
+        } else if (plain_) {
+            cudaFree(plain_);
+            plain_ = nullptr;
+        }
+        mapped_ = 0;
+    }
+
+  private:
+    struct Chunk {
+        CUmemGenericAllocationHandle h;
+        size_t bytes;
+    };
+    int device_ = 0;
+    bool vmm_ = false;
+    CUdeviceptr base_ = 0;
+    size_t reserved_ = 0, mapped_ = 0, gran_ = 0;
+    std::vector<Chunk> chunks_;
+    void* plain_ = nullptr;
+};
+
+// simple grow-only device / pinned scratch
+template <class T>
+static int grow_dev(T** p, size_t* cap, size_t need) {
+    if (need <= *cap) return MVDB_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    size_t nc = std::max(need, *cap * 2);
+    CU_OK(cudaMalloc(reinterpret_cast<void**>(p), nc * sizeof(T)));
+    *cap = nc;
+    return MVDB_OK;
+}
+template <class T>
+static int grow_pin(T** p, size_t* cap, size_t need) {
+    if (need <= *cap) return MVDB_OK;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr;
+    size_t nc = std::max(need, *cap * 2);
+    CU_OK(cudaMallocHost(reinterpret_cast<void**>(p), nc * sizeof(T)));
+    *cap = nc;
+    return MVDB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// objects
+// ---------------------------------------------------------------------------
+struct mvdb_workspace {
+    mvdb_index* ix = nullptr;
+    cudaStream_t stream = nullptr;  // owned (host-buffer searches run here)
+    bool pooled = false;
+    // device scratch
+    uint64_t* partials = nullptr;
+    size_t partials_cap = 0;
+    unsigned int* ticket = nullptr;
+    uint32_t* all_ord = nullptr;
+    size_t all_ord_cap = 0;
+    RadixState* radix = nullptr;
+    uint64_t* keys = nullptr;
+    size_t keys_cap = 0;
+    // host-buffer path
+    float* q_dev = nullptr;
+    size_t q_cap = 0;
+    uint32_t* mask_dev = nullptr;
+    size_t mask_cap = 0;
+    float* D_dev = nullptr;
+    size_t D_cap = 0;
+    int64_t* I_dev = nullptr;
+    size_t I_cap = 0;
+    float* q_pin = nullptr;
+    size_t q_pin_cap = 0;
+    uint32_t* mask_pin = nullptr;
+    size_t mask_pin_cap = 0;
+    float* D_pin = nullptr;
+    size_t D_pin_cap = 0;
+    int64_t* I_pin = nullptr;
+    size_t I_pin_cap = 0;
+};
+
+struct mvdb_index {
+    int d = 0, device = 0;
+    int64_t ld = 0;  // floats, multiple of 4
+    int ld4 = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    GrowBuf mat, live;
+    std::vector<uint32_t> live_host;  // mirror of the device bitmask
+    std::atomic<uint64_t> ntotal{0};
+    std::atomic<uint64_t> ndead{0};
+    std::mutex mut_mu;            // serialises mutations
+    std::shared_mutex move_mu;    // shared: searches / reads; exclusive: anything that moves rows
+    cudaStream_t mut_stream = nullptr;
+    float* stage_dev[2] = {nullptr, nullptr};
+    size_t stage_cap[2] = {0, 0};
+    int64_t* rows_dev = nullptr;
+    size_t rows_cap = 0;
+    // options
+    int scan_variant = MVDB_SCAN_AUTO;
+    int fused_k_max = 128;
+    int grid_ctas = 0;
+    int consumer_warps = 0;
+    // workspace pool for host-buffer searches
+    std::mutex pool_mu;
+    std::condition_variable pool_cv;
+    std::vector<mvdb_workspace*> pool_free;
+    int pool_created = 0;
+    static constexpr int kPoolMax = 16;
+};
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+#define ENTER(ix)                                                                    \
+    if (!(ix)) return fail(MVDB_ERR_ARG, "null index");                              \
+    DeviceGuard guard__((ix)->device);                                               \
+    if (!guard__.ok) return fail(MVDB_ERR_CUDA, "cudaSetDevice(%d) failed", (ix)->device)
+
+// ---------------------------------------------------------------------------
+// scan dispatch
+// ---------------------------------------------------------------------------
+typedef void (*ScanKernel)(const ScanParams);
+
+template <bool kTma>
+static ScanKernel q1_kernel(int d4) {
+    switch (d4) {
+        case 1: return scan_q1_kernel<1, kTma>;
+        case 2: return scan_q1_kernel<2, kTma>;
+        case 3: return scan_q1_kernel<3, kTma>;
+        case 4: return scan_q1_kernel<4, kTma>;
+        case 5: return scan_q1_kernel<5, kTma>;
+        case 6: return scan_q1_kernel<6, kTma>;
+        case 7: return scan_q1_kernel<7, kTma>;
+        case 8: return scan_q1_kernel<8, kTma>;
+        default: return nullptr;
+    }
+}
+template <bool kTma>
+static ScanKernel multi_kernel(int nq) {
+    switch (nq) {
+        case 1: return scan_multi_kernel<1, kTma>;
+        case 2: return scan_multi_kernel<2, kTma>;
+        case 4: return scan_multi_kernel<4, kTma>;
+        case 8: return scan_multi_kernel<8, kTma>;
+        default: return nullptr;
+    }
+}
+
+struct ScanPlan {
+    ScanKernel fn = nullptr;
+    bool tma = false;
+    int grid = 0, threads = 0;
+    size_t smem = 0;
+};
+
+// Choose kernel, grid and shared-memory layout for one launch of `nq`
+// (1, 2, 4 or 8) queries.  Fills the layout fields of `p`.
+static int plan_scan(mvdb_index* ix, ScanParams& p, int nq, ScanPlan* plan) {
+    const int d4 = (ix->ld4 + 31) / 32;
+    const bool use_q1 = (nq == 1 && d4 <= 8);
+    const uint32_t tiles = (p.n + kRowsPerTile - 1) / kRowsPerTile;
+    p.cap = select_cap(p.k);
+    p.nq = nq;
+    p.stage_bytes = uint32_t(align_up(size_t(kRowsPerTile) * ix->ld * 4, 128));
+
+    auto layout = [&](int ncw, bool tma, int* stages) -> size_t {
+        size_t off = 1024;
+        p.sel_off = uint32_t(off);
+        off += size_t(ncw) * nq * p.cap * 8;
+        off = align_up(off, 16);
+        p.q_off = uint32_t(off);
+        if (!use_q1) off += size_t(nq) * ix->ld * 4;
+        off = align_up(off, 128);
+        p.stage_off = uint32_t(off);
+        if (!tma) {
+            *stages = 0;
+            return off;
+        }
+        if (off + 2 * size_t(p.stage_bytes) > ix->smem_optin) {
+            *stages = 0;
+            return 0;
+        }
+        int s = int((ix->smem_optin - off) / p.stage_bytes);
+        s = std::min(s, 16);
+        *stages = s;
+        return off + size_t(s) * p.stage_bytes;
+    };
+
+    int variant = ix->scan_variant;
+    int ncw_tma = ix->consumer_warps > 0 ? std::min(ix->consumer_warps, 8) : (nq >= 4 ? 8 : 4);
+    int stages = 0;
+    size_t smem = 0;
+    bool tma = (variant != MVDB_SCAN_LDG);
+    if (tma) {
+        smem = layout(ncw_tma, true, &stages);
+        if (stages < 3) {
+            if (variant == MVDB_SCAN_TMA && stages < 2)
+                return fail(MVDB_ERR_ARG, "dimension %d too large for the TMA scan ring", ix->d);
+            if (variant != MVDB_SCAN_TMA) tma = false;
+        }
+    }
+    if (tma) {
+        plan->tma = true;
+        plan->threads = 32 * (1 + ncw_tma);
+        plan->fn = use_q1 ? q1_kernel<true>(d4) : multi_kernel<true>(nq);
+        plan->smem = smem;
+        p.stages = stages;
+        int g = ix->grid_ctas > 0 ? ix->grid_ctas : ix->sm_count;
+        plan->grid = int(std::min<uint32_t>(uint32_t(g), tiles));
+    } else {
+        const int ncw = 8;
+        smem = layout(ncw, false, &stages);
+        if (smem > ix->smem_optin) return fail(MVDB_ERR_ARG, "k=%d / d=%d need too much shared memory", p.k, ix->d);
+        plan->tma = false;
+        plan->threads = 32 * ncw;
+        plan->fn = use_q1 ? q1_kernel<false>(d4) : multi_kernel<false>(nq);
+        plan->smem = smem;
+        p.stages = 0;
+        int per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, plan->fn, plan->threads, smem);
+        per_sm = std::max(1, std::min(per_sm, 4));
+        int g = ix->grid_ctas > 0 ? ix->grid_ctas : ix->sm_count * per_sm;
+        uint32_t per_cta_tiles = uint32_t(ncw);  // at least one tile per warp
+        plan->grid = int(std::max<uint32_t>(1, std::min<uint32_t>(uint32_t(g), (tiles + per_cta_tiles - 1) / per_cta_tiles)));
+    }
+    if (!plan->fn) return fail(MVDB_ERR_STATE, "no scan kernel for nq=%d d4=%d", nq, d4);
+    static std::mutex attr_mu;
+    {
+        // opt in to large dynamic shared memory once per kernel
+        std::lock_guard<std::mutex> g(attr_mu);
+        static std::vector<std::pair<void*, int>> done;
+        bool seen = false;
+        for (auto& e : done) seen |= (e.first == (void*)plan->fn && e.second == ix->device);
+        if (!seen) {
+            CU_OK(cudaFuncSetAttribute(plan->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ix->smem_optin)));
+            done.push_back({(void*)plan->fn, ix->device});
+        }
+    }
+    return MVDB_OK;
+}
+
+__global__ void fill_empty_results_kernel(float* D, int64_t* I, int64_t total) {
+    int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < total) {
+        D[i] = -FLT_MAX;
+        I[i] = -1;
+    }
+}
+
+static int ws_scratch(mvdb_workspace* ws) {
+    if (!ws->ticket) {
+        CU_OK(cudaMalloc(&ws->ticket, sizeof(unsigned int)));
+        CU_OK(cudaMemset(ws->ticket, 0, sizeof(unsigned int)));
+    }
+    return MVDB_OK;
+}
+
+// Core search on device buffers.  Caller holds move_mu shared.
+static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, int64_t nq, int64_t k,
+                      const uint32_t* mask_dev, uint64_t mask_rows, int normalize_q, int64_t label_offset,
+                      float* D_dev, int64_t* I_dev, cudaStream_t stream) {
+    if (nq <= 0) return MVDB_OK;
+    uint64_t n64 = ix->ntotal.load(std::memory_order_acquire);
+    if (mask_dev) n64 = std::min<uint64_t>(n64, mask_rows);
+    if (n64 > 0xFFFFFFF0ull) return fail(MVDB_ERR_ARG, "more than 2^32 rows per index are not supported");
+    const uint32_t n = uint32_t(n64);
+    if (n == 0) {
+        int64_t total = nq * k;
+        fill_empty_results_kernel<<<unsigned((total + 255) / 256), 256, 0, stream>>>(D_dev, I_dev, total);
+        LAUNCHED();
+        CU_OK(cudaGetLastError());
+        return MVDB_OK;
+    }
+    RC_OK(ws_scratch(ws));
+    ScanParams p = {};
+    p.x = static_cast<const float*>(ix->mat.ptr());
+    p.live = ix->ndead.load(std::memory_order_acquire) ? static_cast<const uint32_t*>(ix->live.ptr()) : nullptr;
+    p.mask = mask_dev;
+    p.ticket = ws->ticket;
+    p.label_offset = label_offset;
+    p.n = n;
+    p.d = ix->d;
+    p.ld4 = ix->ld4;
+    p.normalize_q = normalize_q;
+
+    if (k <= ix->fused_k_max) {
+        p.k = int(k);
+        int64_t done = 0;
+        while (done < nq) {
+            int64_t rem = nq - done;
+            int g = rem >= 8 ? 8 : rem >= 4 ? 4 : rem >= 2 ? 2 : 1;
+            ScanPlan plan;
+            RC_OK(plan_scan(ix, p, g, &plan));
+            RC_OK(grow_dev(&ws->partials, &ws->partials_cap, size_t(g) * plan.grid * p.k));
+            p.partials = ws->partials;
+            p.q = q_dev + done * ix->d;
+            p.outD = D_dev + done * k;
+            p.outI = I_dev + done * k;
+            p.all_ord = nullptr;
+            plan.fn<<<plan.grid, plan.threads, plan.smem, stream>>>(p);
+            LAUNCHED();
+            CU_OK(cudaGetLastError());
+            done += g;
+        }
+        return MVDB_OK;
+    }
+
+    // ---- large k: materialise score images, radix-select, sort -------------
+    if (!ws->radix) CU_OK(cudaMalloc(&ws->radix, sizeof(RadixState)));
+    RC_OK(grow_dev(&ws->all_ord, &ws->all_ord_cap, size_t(n)));
+    const uint64_t kk = std::min<uint64_t>(uint64_t(k), n);
+    uint64_t npad = 1;
+    while (npad < kk) npad <<= 1;
+    RC_OK(grow_dev(&ws->keys, &ws->keys_cap, size_t(npad)));
+    p.k = 1;
+    const int hist_grid = int(std::min<uint64_t>(uint64_t(ix->sm_count) * 4, (uint64_t(n) + 511) / 512));
+    for (int64_t qi = 0; qi < nq; qi++) {
+        ScanPlan plan;
+        RC_OK(plan_scan(ix, p, 1, &plan));
+        p.q = q_dev + qi * ix->d;
+        p.all_ord = ws->all_ord;
+        p.partials = nullptr;
+        p.outD = nullptr;
+        p.outI = nullptr;
+        plan.fn<<<plan.grid, plan.threads, plan.smem, stream>>>(p);
+        LAUNCHED();
+        radix_init_kernel<<<1, 256, 0, stream>>>(ws->radix, kk);
+        LAUNCHED();
+        for (int shift = 56; shift >= 0; shift -= 8) {
+            radix_hist_kernel<<<hist_grid, 512, 0, stream>>>(ws->all_ord, n, ws->radix, shift);
+            radix_pick_kernel<<<1, 256, 0, stream>>>(ws->radix, shift);
+            LAUNCHED();
+            LAUNCHED();
+        }
+        radix_collect_kernel<<<hist_grid, 512, 0, stream>>>(ws->all_ord, n, ws->radix, ws->keys, uint32_t(kk));
+        LAUNCHED();
+        pad_keys_kernel<<<unsigned((npad + 255) / 256), 256, 0, stream>>>(ws->keys, ws->radix, uint32_t(npad));
+        LAUNCHED();
+        if (npad <= 16384) {
+            cudaFuncSetAttribute(sort_keys_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
+            sort_keys_smem_kernel<<<1, 1024, npad * 8, stream>>>(ws->keys, uint32_t(npad));
+            LAUNCHED();
+        } else {
+            for (uint64_t size = 2; size <= npad; size <<= 1)
+                for (uint64_t stride = size >> 1; stride > 0; stride >>= 1) {
+                    sort_keys_global_step_kernel<<<unsigned((npad / 2 + 255) / 256), 256, 0, stream>>>(ws->keys, npad, size, stride);
+                    LAUNCHED();
+                }
+        }
+        keys_to_results_kernel<<<unsigned((k + 255) / 256), 256, 0, stream>>>(ws->keys, uint32_t(kk), k, D_dev + qi * k,
+                                                                               I_dev + qi * k, label_offset);
+        LAUNCHED();
+        CU_OK(cudaGetLastError());
+    }
+    return MVDB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// workspace handling
+// ---------------------------------------------------------------------------
+static void ws_free(mvdb_workspace* ws) {
+    if (!ws) return;
+    cudaFree(ws->partials);
+    cudaFree(ws->ticket);
+    cudaFree(ws->all_ord);
+    cudaFree(ws->radix);
+    cudaFree(ws->keys);
+    cudaFree(ws->q_dev);
+    cudaFree(ws->mask_dev);
+    cudaFree(ws->D_dev);
+    cudaFree(ws->I_dev);
+    cudaFreeHost(ws->q_pin);
+    cudaFreeHost(ws->mask_pin);
+    cudaFreeHost(ws->D_pin);
+    cudaFreeHost(ws->I_pin);
+    if (ws->stream) cudaStreamDestroy(ws->stream);
+    delete ws;
+}
+
+static int ws_new(mvdb_index* ix, mvdb_workspace** out) {
+    mvdb_workspace* ws = new mvdb_workspace();
+    ws->ix = ix;
+    cudaError_t e = cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete ws;
+        return fail(MVDB_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
+    }
+    *out = ws;
+    return MVDB_OK;
+}
+
+static int pool_acquire(mvdb_index* ix, mvdb_workspace** out) {
+    std::unique_lock<std::mutex> lk(ix->pool_mu);
+    for (;;) {
+        if (!ix->pool_free.empty()) {
+            *out = ix->pool_free.back();
+            ix->pool_free.pop_back();
+            return MVDB_OK;
+        }
+        if (ix->pool_created < mvdb_index::kPoolMax) {
+            ix->pool_created++;
+            lk.unlock();
+            int rc = ws_new(ix, out);
+            if (rc != MVDB_OK) {
+                lk.lock();
+                ix->pool_created--;
+                return rc;
+            }
+            (*out)->pooled = true;
+            return MVDB_OK;
+        }
+        ix->pool_cv.wait(lk);
+    }
+}
+static void pool_release(mvdb_index* ix, mvdb_workspace* ws) {
+    {
+        std::lock_guard<std::mutex> g(ix->pool_mu);
+        ix->pool_free.push_back(ws);
+    }
+    ix->pool_cv.notify_one();
+}
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int mvdb_abi_version(void) { return MVDB_ABI_VERSION; }
+const char* mvdb_last_error(void) { return g_err.c_str(); }
+uint64_t mvdb_launch_count(void) { return g_launches.load(); }
+
+int mvdb_device_count(int* count) {
+    if (!count) return fail(MVDB_ERR_ARG, "null count");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        n = 0;
+    }
+    *count = n;
+    return MVDB_OK;
+}
+
+int mvdb_index_create(int d, int device, uint64_t capacity_hint, mvdb_index** out) {
+    if (!out) return fail(MVDB_ERR_ARG, "null out");
+    *out = nullptr;
+    if (d <= 0 || d > (1 << 20)) return fail(MVDB_ERR_ARG, "dimension %d out of range", d);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        (void)cudaGetLastError();
+        return fail(MVDB_ERR_CUDA, "no CUDA device: this engine has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(MVDB_ERR_ARG, "device %d out of range (%d visible)", device, ndev);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(MVDB_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    CU_OK(cudaFree(0));
+    cudaDeviceProp prop;
+    CU_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(MVDB_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    mvdb_index* ix = new mvdb_index();
+    ix->d = d;
+    ix->device = device;
+    ix->ld = int64_t(align_up(size_t(d), 4));
+    ix->ld4 = int(ix->ld / 4);
+    ix->sm_count = prop.multiProcessorCount;
+    ix->smem_optin = prop.sharedMemPerBlockOptin;
+    size_t free_b = 0, total_b = 0;
+    CU_OK(cudaMemGetInfo(&free_b, &total_b));
+    size_t reserve = capacity_hint ? size_t(capacity_hint) * ix->ld * 4 : total_b;
+    reserve = std::max(reserve, size_t(1) << 21);
+    int rc = ix->mat.init(device, reserve);
+    if (rc == MVDB_OK) rc = ix->live.init(device, std::max<size_t>(reserve / (size_t(ix->ld) * 4) / 8 + 4096, size_t(1) << 21));
+    cudaError_t e = cudaStreamCreateWithFlags(&ix->mut_stream, cudaStreamNonBlocking);
+    if (rc != MVDB_OK || e != cudaSuccess) {
+        ix->mat.destroy();
+        ix->live.destroy();
+        delete ix;
+        return rc != MVDB_OK ? rc : fail(MVDB_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
+    }
+    *out = ix;
+    return MVDB_OK;
+}
+
+int mvdb_index_destroy(mvdb_index* ix) {
+    if (!ix) return MVDB_OK;
+    DeviceGuard guard(ix->device);
+    cudaDeviceSynchronize();
+    for (auto* ws : ix->pool_free) ws_free(ws);
+    ix->pool_free.clear();
+    ix->mat.destroy();
+    ix->live.destroy();
+    cudaFree(ix->stage_dev[0]);
+    cudaFree(ix->stage_dev[1]);
+    cudaFree(ix->rows_dev);
+    if (ix->mut_stream) cudaStreamDestroy(ix->mut_stream);
+    delete ix;
+    return MVDB_OK;
+}
+
+int mvdb_index_reset(mvdb_index* ix) {
+    ENTER(ix);
+    std::unique_lock<std::shared_mutex> mv(ix->move_mu);
+    std::lock_guard<std::mutex> g(ix->mut_mu);
+    size_t words = (ix->ntotal.load() + 31) / 32;
+    if (words) CU_OK(cudaMemsetAsync(ix->live.ptr(), 0, words * 4, ix->mut_stream));
+    CU_OK(cudaStreamSynchronize(ix->mut_stream));
+    ix->live_host.clear();
+    ix->ntotal.store(0);
+    ix->ndead.store(0);
+    return MVDB_OK;
+}
+
+int mvdb_index_set_option(mvdb_index* ix, const char* name, int64_t value) {
+    if (!ix || !name) return fail(MVDB_ERR_ARG, "null argument");
+    std::string s(name);
+    if (s == "scan_variant") {
+        if (value < 0 || value > 2) return fail(MVDB_ERR_ARG, "scan_variant must be 0..2");
+        ix->scan_variant = int(value);
+    } else if (s == "fused_k_max") {
+        if (value < 0 || value > 1024) return fail(MVDB_ERR_ARG, "fused_k_max must be 0..1024");
+        ix->fused_k_max = int(value);
+    } else if (s == "grid_ctas") {
+        if (value < 0 || value > 65535) return fail(MVDB_ERR_ARG, "grid_ctas out of range");
+        ix->grid_ctas = int(value);
+    } else if (s == "consumer_warps") {
+        if (value < 0 || value > 8) return fail(MVDB_ERR_ARG, "consumer_warps must be 0..8");
+        ix->consumer_warps = int(value);
+    } else {
+        return fail(MVDB_ERR_ARG, "unknown option '%s'", name);
+    }
+    return MVDB_OK;
+}
+
+// shared tail of the three add flavours: capacity, kernels, bookkeeping
+static int add_common(mvdb_index* ix, const float* x_host, const float* x_dev, bool synth, uint64_t seed,
+                      int64_t synth_row0, int dist, uint64_t n, int normalize, int64_t* first_row) {
+    std::unique_lock<std::shared_mutex> mv(ix->move_mu, std::defer_lock);
+    if (!ix->mat.stable()) mv.lock();  // cudaMalloc fallback may move the matrix
+    std::lock_guard<std::mutex> g(ix->mut_mu);
+    const uint64_t n0 = ix->ntotal.load();
+    if (first_row) *first_row = int64_t(n0);
+    if (n == 0) return MVDB_OK;
+    if (n0 + n > 0xFFFFFFF0ull) return fail(MVDB_ERR_ARG, "more than 2^32 rows per index are not supported");
+    cudaStream_t st = ix->mut_stream;
+    RC_OK(ix->mat.ensure(size_t(n0 + n) * ix->ld * 4, st));
+    RC_OK(ix->live.ensure(align_up((n0 + n + 31) / 32 * 4, 256), st));
+    float* base = static_cast<float*>(ix->mat.ptr()) + n0 * ix->ld;
+    const int threads = 256;
+    auto grid_for = [&](uint64_t rows) { return unsigned(std::min<uint64_t>((rows * 32 + threads - 1) / threads, uint64_t(ix->sm_count) * 16)); };
+    if (synth) {
+        append_rows_kernel<true><<<grid_for(n), threads, 0, st>>>(nullptr, base, n, ix->d, ix->ld, normalize, seed,
+                                                                  uint64_t(synth_row0), dist);
+        LAUNCHED();
+    } else if (x_dev) {
+        append_rows_kernel<false><<<grid_for(n), threads, 0, st>>>(x_dev, base, n, ix->d, ix->ld, normalize, 0, 0, 0);
+        LAUNCHED();
+    } else {
+        // host rows: stream through two device staging buffers so the H2D copy
+        // of chunk i+1 overlaps the normalise/append kernel of chunk i
+        const size_t row_bytes = size_t(ix->d) * 4;
+        const uint64_t chunk_rows = std::max<uint64_t>(1, (size_t(64) << 20) / row_bytes);
+        uint64_t done = 0;
+        int b = 0;
+        while (done < n) {
+            uint64_t m = std::min(chunk_rows, n - done);
+            RC_OK(grow_dev(&ix->stage_dev[b], &ix->stage_cap[b], size_t(m) * ix->d));
+            CU_OK(cudaMemcpyAsync(ix->stage_dev[b], x_host + done * ix->d, m * row_bytes, cudaMemcpyHostToDevice, st));
+            append_rows_kernel<false><<<grid_for(m), threads, 0, st>>>(ix->stage_dev[b], base + done * ix->ld, m, ix->d,
+                                                                       ix->ld, normalize, 0, 0, 0);
+            LAUNCHED();
+            done += m;
+            b ^= 1;
+        }
+    }
+    {
+        uint64_t words = ((n0 + n + 31) >> 5) - (n0 >> 5);
+        set_live_range_kernel<<<unsigned((words + 255) / 256), 256, 0, st>>>(static_cast<uint32_t*>(ix->live.ptr()), n0, n);
+        LAUNCHED();
+    }
+    CU_OK(cudaGetLastError());
+    CU_OK(cudaStreamSynchronize(st));
+    ix->live_host.resize((n0 + n + 31) / 32, 0u);
+    for (uint64_t r = n0; r < n0 + n;) {
+        if ((r & 31) == 0 && r + 32 <= n0 + n) {
+            ix->live_host[r >> 5] = 0xFFFFFFFFu;
+            r += 32;
+        } else {
+            ix->live_host[r >> 5] |= 1u << (r & 31);
+            r++;
+        }
+    }
+    ix->ntotal.store(n0 + n, std::memory_order_release);
+    return MVDB_OK;
+}
+
+int mvdb_index_add(mvdb_index* ix, const float* x, uint64_t n, int normalize, int64_t* first_row) {
+    ENTER(ix);
+    if (n && !x) return fail(MVDB_ERR_ARG, "null rows");
+    return add_common(ix, x, nullptr, false, 0, 0, 0, n, normalize, first_row);
+}
+int mvdb_index_add_device(mvdb_index* ix, const float* x_dev, uint64_t n, int normalize, int64_t* first_row) {
+    ENTER(ix);
+    if (n && !x_dev) return fail(MVDB_ERR_ARG, "null rows");
+    return add_common(ix, nullptr, x_dev, false, 0, 0, 0, n, normalize, first_row);
+}
+int mvdb_index_add_synthetic(mvdb_index* ix, uint64_t seed, int64_t row0, uint64_t n, int dist, int normalize,
+                             int64_t* first_row) {
+    ENTER(ix);
+    if (dist < 0 || dist > 1 || row0 < 0) return fail(MVDB_ERR_ARG, "bad synthetic parameters");
+    return add_common(ix, nullptr, nullptr, true, seed, row0, dist, n, normalize, first_row);
+}
+
+int mvdb_index_remove_rows(mvdb_index* ix, const int64_t* rows, uint64_t n) {
+    ENTER(ix);
+    if (n && !rows) return fail(MVDB_ERR_ARG, "null rows");
+    std::lock_guard<std::mutex> g(ix->mut_mu);
+    const uint64_t nt = ix->ntotal.load();
+    // validate everything before changing anything
+    std::vector<int64_t> sorted(rows, rows + n);
+    std::sort(sorted.begin(), sorted.end());
+    for (uint64_t i = 0; i < n; i++) {
+        int64_t r = sorted[i];
+        if (r < 0 || uint64_t(r) >= nt) return fail(MVDB_ERR_ARG, "row %lld out of range", (long long)r);
+        if (i && sorted[i - 1] == r) return fail(MVDB_ERR_ARG, "row %lld listed twice", (long long)r);
+        if (!((ix->live_host[r >> 5] >> (r & 31)) & 1u)) return fail(MVDB_ERR_ARG, "row %lld already deleted", (long long)r);
+    }
+    if (n == 0) return MVDB_OK;
+    cudaStream_t st = ix->mut_stream;
+    RC_OK(grow_dev(&ix->rows_dev, &ix->rows_cap, size_t(n)));
+    CU_OK(cudaMemcpyAsync(ix->rows_dev, rows, n * 8, cudaMemcpyHostToDevice, st));
+    // publish "tombstones exist" before the bits flip so new searches read the bitmask
+    ix->ndead.fetch_add(n, std::memory_order_release);
+    clear_live_rows_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(static_cast<uint32_t*>(ix->live.ptr()), ix->rows_dev, n);
+    LAUNCHED();
+    CU_OK(cudaGetLastError());
+    CU_OK(cudaStreamSynchronize(st));
+    for (uint64_t i = 0; i < n; i++) ix->live_host[rows[i] >> 5] &= ~(1u << (rows[i] & 31));
+    return MVDB_OK;
+}
+
+int mvdb_index_compact(mvdb_index* ix, int64_t* ntotal_out) {
+    ENTER(ix);
+    std::unique_lock<std::shared_mutex> mv(ix->move_mu);  // waits for running searches
+    std::lock_guard<std::mutex> g(ix->mut_mu);
+    const uint64_t nt = ix->ntotal.load();
+    if (ix->ndead.load() == 0) {
+        if (ntotal_out) *ntotal_out = int64_t(nt);
+        return MVDB_OK;
+    }
+    std::vector<uint32_t> src;
+    src.reserve(nt);
+    for (uint64_t r = 0; r < nt; r++)
+        if ((ix->live_host[r >> 5] >> (r & 31)) & 1u) src.push_back(uint32_t(r));
+    const uint64_t nl = src.size();
+    uint64_t first = 0;
+    while (first < nl && src[first] == first) first++;
+    cudaStream_t st = ix->mut_stream;
+    const size_t row_bytes = size_t(ix->ld) * 4;
+    const uint64_t win = std::max<uint64_t>(1, std::min<uint64_t>(nl - first, (size_t(256) << 20) / row_bytes));
+    float* scratch = nullptr;
+    uint32_t* src_dev = nullptr;
+    if (nl > first) {
+        CU_OK(cudaMalloc(&scratch, win * row_bytes));
+        cudaError_t e = cudaMalloc(&src_dev, win * 4);
+        if (e != cudaSuccess) {
+            cudaFree(scratch);
+            return fail(MVDB_ERR_OOM, "cudaMalloc failed: %s", cudaGetErrorString(e));
+        }
+    }
+    float* mat = static_cast<float*>(ix->mat.ptr());
+    int rc = MVDB_OK;
+    for (uint64_t a = first; a < nl && rc == MVDB_OK; a += win) {
+        uint64_t m = std::min(win, nl - a);
+        // destination rows [a, a+m) never overlap the sources of later windows
+        // (src[i] >= i), and the gather of this window completes before its copy.
+        cudaError_t e = cudaMemcpyAsync(src_dev, src.data() + a, m * 4, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) {
+            unsigned grid = unsigned(std::min<uint64_t>((m * 32 + 255) / 256, uint64_t(ix->sm_count) * 16));
+            gather_rows_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(mat), reinterpret_cast<float4*>(scratch),
+                                                     src_dev, m, ix->ld4);
+            LAUNCHED();
+            e = cudaMemcpyAsync(mat + a * ix->ld, scratch, m * row_bytes, cudaMemcpyDeviceToDevice, st);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // src.data() window reuse + error check
+        if (e != cudaSuccess) rc = fail(MVDB_ERR_CUDA, "compaction failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(scratch);
+    cudaFree(src_dev);
+    if (rc != MVDB_OK) return rc;
+    // rebuild the bitmask: rows [0, nl) live, the rest clear
+    size_t old_words = (nt + 31) / 32, new_words = (nl + 31) / 32;
+    ix->live_host.assign(old_words, 0u);
+    for (uint64_t w = 0; w < nl / 32; w++) ix->live_host[w] = 0xFFFFFFFFu;
+    if (nl & 31) ix->live_host[nl / 32] = (1u << (nl & 31)) - 1u;
+    if (old_words) CU_OK(cudaMemcpyAsync(ix->live.ptr(), ix->live_host.data(), old_words * 4, cudaMemcpyHostToDevice, st));
+    CU_OK(cudaStreamSynchronize(st));
+    ix->live_host.resize(new_words);
+    ix->ntotal.store(nl, std::memory_order_release);
+    ix->ndead.store(0, std::memory_order_release);
+    if (ntotal_out) *ntotal_out = int64_t(nl);
+    return MVDB_OK;
+}
+
+int mvdb_index_dim(const mvdb_index* ix, int* d) {
+    if (!ix || !d) return fail(MVDB_ERR_ARG, "null argument");
+    *d = ix->d;
+    return MVDB_OK;
+}
+
+int mvdb_index_ntotal(const mvdb_index* ix, int64_t* ntotal, int64_t* nlive) {
+    if (!ix) return fail(MVDB_ERR_ARG, "null index");
+    uint64_t nt = ix->ntotal.load(), nd = ix->ndead.load();
+    if (ntotal) *ntotal = int64_t(nt);
+    if (nlive) *nlive = int64_t(nt - std::min(nd, nt));
+    return MVDB_OK;
+}
+
+int mvdb_index_reconstruct_n(mvdb_index* ix, int64_t row0, uint64_t n, float* out) {
+    ENTER(ix);
+    if (!out) return fail(MVDB_ERR_ARG, "null out");
+    std::shared_lock<std::shared_mutex> mv(ix->move_mu);
+    const uint64_t nt = ix->ntotal.load(std::memory_order_acquire);
+    if (row0 < 0 || uint64_t(row0) + n > nt) return fail(MVDB_ERR_ARG, "rows [%lld, +%llu) out of range", (long long)row0, (unsigned long long)n);
+    if (n == 0) return MVDB_OK;
+    const float* src = static_cast<const float*>(ix->mat.ptr()) + uint64_t(row0) * ix->ld;
+    CU_OK(cudaMemcpy2D(out, size_t(ix->d) * 4, src, size_t(ix->ld) * 4, size_t(ix->d) * 4, n, cudaMemcpyDeviceToHost));
+    return MVDB_OK;
+}
+int mvdb_index_reconstruct(mvdb_index* ix, int64_t row, float* out) { return mvdb_index_reconstruct_n(ix, row, 1, out); }
+
+int mvdb_index_device_view(mvdb_index* ix, const float** matrix_dev, int64_t* ld, const uint32_t** live_dev) {
+    if (!ix) return fail(MVDB_ERR_ARG, "null index");
+    if (matrix_dev) *matrix_dev = static_cast<const float*>(ix->mat.ptr());
+    if (ld) *ld = ix->ld;
+    if (live_dev) *live_dev = static_cast<const uint32_t*>(ix->live.ptr());
+    return MVDB_OK;
+}
+
+int mvdb_index_workspace_create(mvdb_index* ix, mvdb_workspace** out) {
+    ENTER(ix);
+    if (!out) return fail(MVDB_ERR_ARG, "null out");
+    return ws_new(ix, out);
+}
+int mvdb_index_workspace_destroy(mvdb_workspace* ws) {
+    if (!ws) return MVDB_OK;
+    DeviceGuard guard(ws->ix->device);
+    if (ws->stream) cudaStreamSynchronize(ws->stream);
+    ws_free(ws);
+    return MVDB_OK;
+}
+
+int mvdb_index_search_device(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, int64_t nq, int64_t k,
+                             const uint32_t* mask_dev, uint64_t mask_rows, int normalize_queries,
+                             int64_t label_offset, float* D_dev, int64_t* I_dev, void* stream) {
+    ENTER(ix);
+    if (!ws || ws->ix != ix) return fail(MVDB_ERR_ARG, "workspace does not belong to this index");
+    if (nq < 0 || k <= 0) return fail(MVDB_ERR_ARG, "need nq >= 0 and k > 0 (got nq=%lld k=%lld)", (long long)nq, (long long)k);
+    if (nq && (!q_dev || !D_dev || !I_dev)) return fail(MVDB_ERR_ARG, "null buffer");
+    std::shared_lock<std::shared_mutex> mv(ix->move_mu);
+    return run_search(ix, ws, q_dev, nq, k, mask_dev, mask_rows, normalize_queries, label_offset, D_dev, I_dev,
+                      static_cast<cudaStream_t>(stream));
+}
+
+int mvdb_index_search(mvdb_index* ix, const float* q, int64_t nq, int64_t k, const uint8_t* mask, uint64_t mask_rows,
+                      int normalize_queries, float* D, int64_t* I) {
+    ENTER(ix);
+    if (nq < 0 || k <= 0) return fail(MVDB_ERR_ARG, "need nq >= 0 and k > 0 (got nq=%lld k=%lld)", (long long)nq, (long long)k);
+    if (nq == 0) return MVDB_OK;
+    if (!q || !D || !I) return fail(MVDB_ERR_ARG, "null buffer");
+    mvdb_workspace* ws = nullptr;
+    RC_OK(pool_acquire(ix, &ws));
+    struct Release {
+        mvdb_index* ix;
+        mvdb_workspace* ws;
+        ~Release() { pool_release(ix, ws); }
+    } rel{ix, ws};
+    std::shared_lock<std::shared_mutex> mv(ix->move_mu);
+    cudaStream_t st = ws->stream;
+    const size_t qn = size_t(nq) * ix->d, on = size_t(nq) * k;
+    RC_OK(grow_dev(&ws->q_dev, &ws->q_cap, qn));
+    RC_OK(grow_pin(&ws->q_pin, &ws->q_pin_cap, qn));
+    RC_OK(grow_dev(&ws->D_dev, &ws->D_cap, on));
+    RC_OK(grow_dev(&ws->I_dev, &ws->I_cap, on));
+    RC_OK(grow_pin(&ws->D_pin, &ws->D_pin_cap, on));
+    RC_OK(grow_pin(&ws->I_pin, &ws->I_pin_cap, on));
+    memcpy(ws->q_pin, q, qn * 4);
+    CU_OK(cudaMemcpyAsync(ws->q_dev, ws->q_pin, qn * 4, cudaMemcpyHostToDevice, st));
+    const uint32_t* mask_dev = nullptr;
+    if (mask) {
+        const uint64_t rows = std::min<uint64_t>(mask_rows, ix->ntotal.load(std::memory_order_acquire));
+        mask_rows = rows;
+        const size_t words = (rows + 31) / 32, bytes = (rows + 7) / 8;
+        RC_OK(grow_dev(&ws->mask_dev, &ws->mask_cap, std::max<size_t>(words, 1)));
+        RC_OK(grow_pin(&ws->mask_pin, &ws->mask_pin_cap, std::max<size_t>(words, 1)));
+        if (words) {
+            ws->mask_pin[words - 1] = 0;
+            memcpy(ws->mask_pin, mask, bytes);
+            if (rows & 7) reinterpret_cast<uint8_t*>(ws->mask_pin)[bytes - 1] &= uint8_t((1u << (rows & 7)) - 1u);
+            CU_OK(cudaMemcpyAsync(ws->mask_dev, ws->mask_pin, words * 4, cudaMemcpyHostToDevice, st));
+        }
+        mask_dev = ws->mask_dev;
+    }
+    RC_OK(run_search(ix, ws, ws->q_dev, nq, k, mask_dev, mask_rows, normalize_queries, 0, ws->D_dev, ws->I_dev, st));
+    CU_OK(cudaMemcpyAsync(ws->D_pin, ws->D_dev, on * 4, cudaMemcpyDeviceToHost, st));
+    CU_OK(cudaMemcpyAsync(ws->I_pin, ws->I_dev, on * 8, cudaMemcpyDeviceToHost, st));
+    CU_OK(cudaStreamSynchronize(st));
+    memcpy(D, ws->D_pin, on * 4);
+    memcpy(I, ws->I_pin, on * 8);
+    return MVDB_OK;
+}
+
+int mvdb_normalize_L2(float* x, uint64_t n, int d, int device) {
+    if (d <= 0) return fail(MVDB_ERR_ARG, "dimension %d out of range", d);
+    if (n == 0) return MVDB_OK;
+    if (!x) return fail(MVDB_ERR_ARG, "null rows");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        (void)cudaGetLastError();
+        return fail(MVDB_ERR_CUDA, "no CUDA device: this engine has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(MVDB_ERR_ARG, "device %d out of range", device);
+    DeviceGuard guard(device);
+    float* dev = nullptr;
+    const size_t bytes = size_t(n) * d * 4;
+    CU_OK(cudaMalloc(&dev, bytes));
+    cudaError_t e = cudaMemcpy(dev, x, bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        unsigned grid = unsigned(std::min<uint64_t>((n * 32 + 255) / 256, 148ull * 16));
+        normalize_dense_kernel<<<grid, 256>>>(dev, n, d);
+        LAUNCHED();
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(x, dev, bytes, cudaMemcpyDeviceToHost);
+    cudaFree(dev);
+    if (e != cudaSuccess) return fail(MVDB_ERR_CUDA, "normalize_L2 failed: %s", cudaGetErrorString(e));
+    return MVDB_OK;
+}
+
+int mvdb_merge_topk_device(int device, const float* D_parts, const int64_t* I_parts, int nparts, int64_t nq, int64_t k,
+                           float* D_out, int64_t* I_out, void* stream) {
+    if (nparts <= 0 || nq < 0 || k <= 0) return fail(MVDB_ERR_ARG, "bad merge shape");
+    if (nq == 0) return MVDB_OK;
+    if (!D_parts || !I_parts || !D_out || !I_out) return fail(MVDB_ERR_ARG, "null buffer");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(MVDB_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    uint64_t total = uint64_t(nparts) * uint64_t(k);
+    uint64_t npad = 64;
+    while (npad < total) npad <<= 1;
+    if (npad > 16384) return fail(MVDB_ERR_ARG, "merge of %d x k=%lld exceeds 16384 candidates per query", nparts, (long long)k);
+    if (npad * 8 > 48 * 1024)
+        CU_OK(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(npad * 8)));
+    merge_topk_kernel<<<unsigned(nq), 256, npad * 8, static_cast<cudaStream_t>(stream)>>>(D_parts, I_parts, nparts, nq, k,
+                                                                                         uint32_t(npad), D_out, I_out);
+    LAUNCHED();
+    CU_OK(cudaGetLastError());
+    return MVDB_OK;
+}
+
+}  // extern "C"

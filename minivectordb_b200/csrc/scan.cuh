@@ -1,0 +1,456 @@
+// scan.cuh -- the hot path: flat inner-product scan with fused top-k.
+//
+// Replaces faiss IndexFlatIP.search for small query batches
+// (exhaustive_inner_product_seq + HeapBlockResultHandler; call sites
+// ref minivectordb/vector_database.py:497, 514 and
+// minivectordb/sharded_vector_database.py:626, 642) and, through the
+// admissible-row bitmask applied in the epilogue, the reference's
+// gather-into-a-temporary-index filtered branch (vector_database.py:508-523).
+//
+// Work decomposition (HBM-bound: N*ld*4 bytes streamed once per query group):
+//   * the matrix is cut into tiles of 8 consecutive rows (= one byte of the
+//     admissible/live bitmasks); tile t belongs to CTA t % gridDim.x;
+//   * TMA variant: warp 0 is the producer -- one lane issues one
+//     cp.async.bulk (global -> shared, L2 evict_first) per tile into a ring of
+//     S stages guarded by full/empty mbarriers; consumer warp w owns every
+//     ncw-th tile of the CTA, so no CTA-wide barrier exists in steady state;
+//   * LDG variant: every warp is a consumer and loads its tile straight from
+//     global memory with 128-bit non-allocating loads;
+//   * a consumer lane owns float4 chunk `lane + 32 j` of each row, accumulates
+//     8 rows x NQ queries, reduce8() folds the 8 partials across the warp in 9
+//     shuffles, and quad leaders push (score,row) keys into the WarpSelect;
+//   * epilogue: warps merge inside the CTA, the CTA writes its k best keys,
+//     the LAST CTA to finish (ticket counter) merges all partial lists and
+//     writes (D, I) -- one launch per search.
+#pragma once
+#include <cfloat>
+
+#include "select.cuh"
+
+namespace mvdb {
+
+struct ScanParams {
+    const float* x;        // matrix, row-major, leading dimension ld (floats, multiple of 4)
+    const float* q;        // queries, dense [nq][d]
+    const uint32_t* live;  // live-row bitmask or nullptr (no tombstones)
+    const uint32_t* mask;  // admissible-row bitmask or nullptr (no filter)
+    uint64_t* partials;    // [nq][gridDim.x][k] keys
+    unsigned int* ticket;  // zero before launch; reset by the last CTA
+    float* outD;           // [nq][k]
+    int64_t* outI;         // [nq][k]
+    uint32_t* all_ord;     // large-k mode: [nq][n] score images (0 = not admissible); else nullptr
+    int64_t label_offset;
+    uint32_t n;            // rows to scan (snapshot of ntotal)
+    int d;                 // logical dimension
+    int ld4;               // ld / 4
+    int nq;                // queries in this launch (== NQ template for the multi kernel)
+    int k;
+    int cap;               // WarpSelect capacity (select_cap(k))
+    int normalize_q;
+    int stages;            // TMA ring depth
+    uint32_t stage_bytes;  // 8 * ld * 4 rounded to 128
+    uint32_t sel_off, q_off, stage_off;  // byte offsets into dynamic shared memory
+};
+
+// shared-memory header (first 1024 bytes)
+struct SmemHeader {
+    uint64_t full[16];
+    uint64_t empty[16];
+    int cnts[64];      // [warp][query] list lengths for the CTA merge
+    int last_flag;
+};
+static_assert(sizeof(SmemHeader) <= 1024, "header too large");
+
+// ---------------------------------------------------------------------------
+// epilogue shared by all scan kernels
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void write_results(const uint64_t* keys, int cnt, int k, float* D,
+                                              int64_t* I, int64_t label_offset, int lane) {
+    for (int i = lane; i < k; i += kWarp) {
+        uint64_t key = (i < cnt) ? keys[i] : kEmptyKey;
+        if (key == kEmptyKey) {
+            D[i] = -FLT_MAX;  // faiss pads IP results with the lowest float and id -1
+            I[i] = -1;
+        } else {
+            D[i] = key_score(key);
+            I[i] = int64_t(key_row(key)) + label_offset;
+        }
+    }
+}
+
+// Merge the per-warp lists of query qi (already compacted, lengths in
+// hdr->cnts) into warp `cw`'s list.  Returns the merged select state.
+__device__ __forceinline__ WarpSelect merge_cta_lists(SmemHeader* hdr, uint64_t* selbuf, int nq,
+                                                      int qi, int cw, int ncw, int cap, int k,
+                                                      int lane) {
+    WarpSelect m;
+    m.init(selbuf + size_t(cw * nq + qi) * cap, cap, k);
+    m.cnt = hdr->cnts[cw * nq + qi];
+    m.thr = (m.cnt == k) ? m.buf[k - 1] : kEmptyKey;
+    for (int w = 0; w < ncw; w++) {
+        if (w == cw) continue;
+        m.push_array(selbuf + size_t(w * nq + qi) * cap, hdr->cnts[w * nq + qi], lane);
+    }
+    m.compact(lane);
+    return m;
+}
+
+// Called by all consumer warps once their tiles are done.  `sel_cnt[qi]` must
+// already be compacted lists in selbuf[(cw*nq+qi)*cap ..].
+// bar_id/bar_threads: named barrier covering exactly the consumer warps.
+__device__ __forceinline__ void finish_scan(const ScanParams& p, SmemHeader* hdr, uint64_t* selbuf,
+                                            int cw, int ncw, int lane, int bar_id, int bar_threads) {
+    const int nq = p.nq, k = p.k, cap = p.cap;
+    const int G = gridDim.x;
+    named_bar_sync(bar_id, bar_threads);
+    // ---- CTA merge: warp (qi % ncw) owns query qi -------------------------
+    for (int qi = cw; qi < nq; qi += ncw) {
+        WarpSelect m = merge_cta_lists(hdr, selbuf, nq, qi, cw, ncw, cap, k, lane);
+        uint64_t* dst = p.partials + (size_t(qi) * G + blockIdx.x) * k;
+        for (int i = lane; i < k; i += kWarp) dst[i] = (i < m.cnt) ? m.buf[i] : kEmptyKey;
+    }
+    __threadfence();
+    named_bar_sync(bar_id, bar_threads);
+    if (cw == 0 && lane == 0) {
+        unsigned t = atomicAdd(p.ticket, 1u);
+        hdr->last_flag = (t == unsigned(G - 1));
+    }
+    named_bar_sync(bar_id, bar_threads);
+    if (!hdr->last_flag) return;
+    // ---- last CTA: merge the G partial lists of every query ---------------
+    __threadfence();
+    const int total = G * k;
+    const int chunk = (total + ncw - 1) / ncw;
+    for (int qi = 0; qi < nq; qi++) {
+        WarpSelect f;
+        f.init(selbuf + size_t(cw * nq + qi) * cap, cap, k);
+        const uint64_t* src = p.partials + size_t(qi) * total;
+        int lo = cw * chunk, hi = min(total, lo + chunk);
+        for (int i = lo; i < hi; i += kWarp) {
+            int j = i + lane;
+            uint64_t key = (j < hi) ? __ldcg(src + j) : kEmptyKey;
+            f.push(j < hi, key, lane);
+        }
+        f.compact(lane);
+        if (lane == 0) hdr->cnts[cw * nq + qi] = f.cnt;
+    }
+    named_bar_sync(bar_id, bar_threads);
+    for (int qi = cw; qi < nq; qi += ncw) {
+        WarpSelect m = merge_cta_lists(hdr, selbuf, nq, qi, cw, ncw, cap, k, lane);
+        __syncwarp();
+        write_results(m.buf, m.cnt, k, p.outD + size_t(qi) * k, p.outI + size_t(qi) * k,
+                      p.label_offset, lane);
+    }
+    if (cw == 0 && lane == 0) *p.ticket = 0u;  // ready for the next launch on this workspace
+}
+
+// Load (and optionally L2-normalise) this lane's float4 chunks of one query.
+template <int D4>
+__device__ __forceinline__ void load_query_regs(const float* q, int d, int ld4, int normalize,
+                                                int lane, float4 (&qr)[D4]) {
+    float nr = 0.f;
+#pragma unroll
+    for (int j = 0; j < D4; j++) {
+        int c = lane + 32 * j;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < ld4) {
+            int b = 4 * c;
+            if (b + 0 < d) v.x = q[b + 0];
+            if (b + 1 < d) v.y = q[b + 1];
+            if (b + 2 < d) v.z = q[b + 2];
+            if (b + 3 < d) v.w = q[b + 3];
+        }
+        qr[j] = v;
+        nr = dot4(v, v, nr);
+    }
+    if (normalize) {
+        nr = warp_allsum(nr);
+        if (nr > 0.f) {
+            float inv = renorm_scale(nr);
+#pragma unroll
+            for (int j = 0; j < D4; j++) {
+                qr[j].x *= inv;
+                qr[j].y *= inv;
+                qr[j].z *= inv;
+                qr[j].w *= inv;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t admissible_byte(const ScanParams& p, uint32_t tile) {
+    uint32_t adm = 0xFFu;
+    if (p.mask) adm &= reinterpret_cast<const uint8_t*>(p.mask)[tile];
+    if (p.live) adm &= reinterpret_cast<const uint8_t*>(p.live)[tile];
+    return adm;
+}
+
+// ---------------------------------------------------------------------------
+// Kernel A: one query, query chunks in registers, D4 = ceil(ld4 / 32) known at
+// compile time.  kTma selects the producer/consumer ring or direct loads.
+// ---------------------------------------------------------------------------
+template <int D4, bool kTma>
+__global__ void __launch_bounds__(kTma ? 288 : 256, kTma ? 1 : 2) scan_q1_kernel(const ScanParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem);
+    uint64_t* selbuf = reinterpret_cast<uint64_t*>(smem + p.sel_off);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ncw = (blockDim.x >> 5) - (kTma ? 1 : 0);
+    const int cw = warp - (kTma ? 1 : 0);
+    const uint32_t G = gridDim.x;
+    const uint32_t T = (p.n + kRowsPerTile - 1) / kRowsPerTile;
+    const uint32_t iters = (T > blockIdx.x) ? (T - blockIdx.x + G - 1) / G : 0;
+    const int S = p.stages;
+
+    if (kTma) {
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < S; s++) {
+                mbar_init(&hdr->full[s], 1);
+                mbar_init(&hdr->empty[s], 1);
+            }
+            mbar_fence_init();
+        }
+        __syncthreads();
+        if (warp == 0) {
+            if (lane == 0) {
+                const uint64_t pol = policy_evict_first();
+                const uint32_t row_bytes = uint32_t(p.ld4) * 16u;
+                int s = 0;
+                uint32_t ph = 0;
+                for (uint32_t it = 0; it < iters; it++) {
+                    mbar_wait(&hdr->empty[s], ph ^ 1u);
+                    uint32_t tile = blockIdx.x + it * G;
+                    uint32_t row0 = tile * kRowsPerTile;
+                    uint32_t rows = min(uint32_t(kRowsPerTile), p.n - row0);
+                    uint32_t bytes = rows * row_bytes;
+                    mbar_arrive_expect_tx(&hdr->full[s], bytes);
+                    bulk_g2s(smem + p.stage_off + size_t(s) * p.stage_bytes,
+                             p.x + size_t(row0) * size_t(p.ld4) * 4, bytes, &hdr->full[s], pol);
+                    if (++s == S) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                }
+            }
+            return;
+        }
+    }
+
+    float4 qr[D4];
+    load_query_regs<D4>(p.q, p.d, p.ld4, p.normalize_q, lane, qr);
+
+    WarpSelect sel;
+    sel.init(selbuf + size_t(cw) * p.cap, p.cap, p.k);
+    const int my_row = tile_row_of_lane(lane);
+    const bool leader = (lane & 3) == 0;
+    const int ld4 = p.ld4;
+
+    for (uint32_t it = cw; it < iters; it += ncw) {
+        const uint32_t tile = blockIdx.x + it * G;
+        const uint32_t row0 = tile * kRowsPerTile;
+        const uint32_t adm = admissible_byte(p, tile);  // issued before the data wait
+        float acc[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) acc[r] = 0.f;
+        if (kTma) {
+            const int s = it % S;
+            const uint32_t ph = (it / S) & 1u;
+            mbar_wait(&hdr->full[s], ph);
+            const float4* st = reinterpret_cast<const float4*>(smem + p.stage_off + size_t(s) * p.stage_bytes);
+#pragma unroll
+            for (int j = 0; j < D4; j++) {
+                const int c = lane + 32 * j;
+                if (c < ld4) {
+#pragma unroll
+                    for (int r = 0; r < 8; r++) acc[r] = dot4(st[r * ld4 + c], qr[j], acc[r]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&hdr->empty[s]);
+        } else {
+            const float4* xt = reinterpret_cast<const float4*>(p.x) + size_t(row0) * ld4;
+            const uint32_t rows = min(uint32_t(kRowsPerTile), p.n - row0);
+#pragma unroll
+            for (int j = 0; j < D4; j++) {
+                const int c = lane + 32 * j;
+                if (c < ld4) {
+                    float4 v[8];
+#pragma unroll
+                    for (int r = 0; r < 8; r++)
+                        v[r] = (uint32_t(r) < rows) ? ldg_stream(xt + size_t(r) * ld4 + c)
+                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int r = 0; r < 8; r++) acc[r] = dot4(v[r], qr[j], acc[r]);
+                }
+            }
+        }
+        const float score = reduce8(acc, lane);
+        const uint32_t row = row0 + my_row;
+        const bool ok = leader && row < p.n && ((adm >> my_row) & 1u);
+        if (p.all_ord) {
+            if (leader && row < p.n) {
+                uint32_t o = (ok && score == score) ? score_to_ord(score) : 0u;
+                p.all_ord[row] = o;
+            }
+        } else {
+            sel.push(ok, make_key(score, row), lane);
+        }
+    }
+    if (p.all_ord) return;
+    sel.compact(lane);
+    if (lane == 0) hdr->cnts[cw] = sel.cnt;
+    finish_scan(p, hdr, selbuf, cw, ncw, lane, 1, ncw * 32);
+}
+
+// ---------------------------------------------------------------------------
+// Kernel B: NQ queries per pass (NQ in {1,2,4,8}), queries staged in shared
+// memory, arbitrary dimension (runtime chunk loop).  Used for small batches
+// and for dimensions whose chunk count exceeds kernel A's templates.
+// ---------------------------------------------------------------------------
+template <int NQ, bool kTma>
+__global__ void __launch_bounds__(kTma ? 288 : 256, (kTma || NQ >= 8) ? 1 : 2) scan_multi_kernel(const ScanParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem);
+    uint64_t* selbuf = reinterpret_cast<uint64_t*>(smem + p.sel_off);
+    float4* qs = reinterpret_cast<float4*>(smem + p.q_off);  // [NQ][ld4]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ncw = (blockDim.x >> 5) - (kTma ? 1 : 0);
+    const int cw = warp - (kTma ? 1 : 0);
+    const uint32_t G = gridDim.x;
+    const uint32_t T = (p.n + kRowsPerTile - 1) / kRowsPerTile;
+    const uint32_t iters = (T > blockIdx.x) ? (T - blockIdx.x + G - 1) / G : 0;
+    const int S = p.stages;
+    const int ld4 = p.ld4;
+
+    if (kTma) {
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < S; s++) {
+                mbar_init(&hdr->full[s], 1);
+                mbar_init(&hdr->empty[s], 1);
+            }
+            mbar_fence_init();
+        }
+        __syncthreads();
+        if (warp == 0) {
+            if (lane == 0) {
+                const uint64_t pol = policy_evict_first();
+                const uint32_t row_bytes = uint32_t(ld4) * 16u;
+                int s = 0;
+                uint32_t ph = 0;
+                for (uint32_t it = 0; it < iters; it++) {
+                    mbar_wait(&hdr->empty[s], ph ^ 1u);
+                    uint32_t tile = blockIdx.x + it * G;
+                    uint32_t row0 = tile * kRowsPerTile;
+                    uint32_t rows = min(uint32_t(kRowsPerTile), p.n - row0);
+                    uint32_t bytes = rows * row_bytes;
+                    mbar_arrive_expect_tx(&hdr->full[s], bytes);
+                    bulk_g2s(smem + p.stage_off + size_t(s) * p.stage_bytes,
+                             p.x + size_t(row0) * size_t(ld4) * 4, bytes, &hdr->full[s], pol);
+                    if (++s == S) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                }
+            }
+            return;
+        }
+    }
+
+    // stage (and normalise) the queries: warp cw handles queries cw, cw+ncw, ...
+    for (int qi = cw; qi < NQ; qi += ncw) {
+        const float* q = p.q + size_t(qi) * p.d;
+        float nr = 0.f;
+        for (int c = lane; c < ld4; c += kWarp) {
+            int b = 4 * c;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (b + 0 < p.d) v.x = q[b + 0];
+            if (b + 1 < p.d) v.y = q[b + 1];
+            if (b + 2 < p.d) v.z = q[b + 2];
+            if (b + 3 < p.d) v.w = q[b + 3];
+            qs[qi * ld4 + c] = v;
+            nr = dot4(v, v, nr);
+        }
+        if (p.normalize_q) {
+            nr = warp_allsum(nr);
+            if (nr > 0.f) {
+                float inv = renorm_scale(nr);
+                for (int c = lane; c < ld4; c += kWarp) {
+                    float4 v = qs[qi * ld4 + c];
+                    v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+                    qs[qi * ld4 + c] = v;
+                }
+            }
+        }
+    }
+    named_bar_sync(1, ncw * 32);
+
+    WarpSelect sel[NQ];
+#pragma unroll
+    for (int qi = 0; qi < NQ; qi++) sel[qi].init(selbuf + size_t(cw * NQ + qi) * p.cap, p.cap, p.k);
+    const int my_row = tile_row_of_lane(lane);
+    const bool leader = (lane & 3) == 0;
+
+    for (uint32_t it = cw; it < iters; it += ncw) {
+        const uint32_t tile = blockIdx.x + it * G;
+        const uint32_t row0 = tile * kRowsPerTile;
+        const uint32_t adm = admissible_byte(p, tile);
+        float acc[NQ][8];
+#pragma unroll
+        for (int qi = 0; qi < NQ; qi++)
+#pragma unroll
+            for (int r = 0; r < 8; r++) acc[qi][r] = 0.f;
+
+        const float4* st;
+        uint32_t rows = 8;
+        int s = 0;
+        if (kTma) {
+            s = it % S;
+            const uint32_t ph = (it / S) & 1u;
+            mbar_wait(&hdr->full[s], ph);
+            st = reinterpret_cast<const float4*>(smem + p.stage_off + size_t(s) * p.stage_bytes);
+        } else {
+            st = reinterpret_cast<const float4*>(p.x) + size_t(row0) * ld4;
+            rows = min(uint32_t(kRowsPerTile), p.n - row0);
+        }
+        for (int c = lane; c < ld4; c += kWarp) {
+            float4 v[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                if (kTma) v[r] = st[r * ld4 + c];
+                else v[r] = (uint32_t(r) < rows) ? ldg_stream(st + size_t(r) * ld4 + c)
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int qi = 0; qi < NQ; qi++) {
+                const float4 qv = qs[qi * ld4 + c];
+#pragma unroll
+                for (int r = 0; r < 8; r++) acc[qi][r] = dot4(v[r], qv, acc[qi][r]);
+            }
+        }
+        if (kTma) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&hdr->empty[s]);
+        }
+        const uint32_t row = row0 + my_row;
+        const bool ok = leader && row < p.n && ((adm >> my_row) & 1u);
+#pragma unroll
+        for (int qi = 0; qi < NQ; qi++) {
+            const float score = reduce8(acc[qi], lane);
+            if (p.all_ord) {
+                if (leader && row < p.n)
+                    p.all_ord[size_t(qi) * p.n + row] = (ok && score == score) ? score_to_ord(score) : 0u;
+            } else {
+                sel[qi].push(ok, make_key(score, row), lane);
+            }
+        }
+    }
+    if (p.all_ord) return;
+#pragma unroll
+    for (int qi = 0; qi < NQ; qi++) {
+        sel[qi].compact(lane);
+        if (lane == 0) hdr->cnts[cw * NQ + qi] = sel[qi].cnt;
+    }
+    finish_scan(p, hdr, selbuf, cw, ncw, lane, 1, ncw * 32);
+}
+
+}  // namespace mvdb

@@ -1,0 +1,209 @@
+"""FlatIPEngine -- Python handle on one HBM-resident flat inner-product index.
+
+Host-side mirror of the interface the reference binds from faiss
+(ref minivectordb/vector_database.py:43-46, 475, 497, 511-514):
+
+    faiss.IndexFlatIP(d)   -> FlatIPEngine(d)            / faiss_shim.IndexFlatIP(d)
+    index.add(x)           -> engine.add(x)
+    index.search(q, k)     -> engine.search(q, k)        (+ mask=, the filtered branch)
+    faiss.normalize_L2(x)  -> normalize_L2(x)
+
+plus what the numpy matrix gave the reference for free: row fetch
+(`self.embeddings[row]`, VDB:55 -> reconstruct), row deletion (np.delete,
+VDB:126 -> remove_rows + compact).  All arithmetic happens in libmvdb_b200.so
+on the GPU; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _native as N
+
+
+def _as_f32_2d(a, d: Optional[int] = None, what: str = "array") -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if a.ndim == 1:
+        a = a[None, :]
+    if a.ndim != 2:
+        raise ValueError(f"{what} must be 2-D (rows x d)")
+    if d is not None and a.shape[1] != d:
+        # faiss's SWIG wrapper asserts `d == self.d`; surface it as ValueError
+        raise ValueError(f"{what} has dimension {a.shape[1]}, index has {d}")
+    return a
+
+
+def pack_mask(admissible: np.ndarray) -> np.ndarray:
+    """bool[n] -> bytes for the engine (bit r&7 of byte r>>3 = row r admissible)."""
+    return np.packbits(np.asarray(admissible, dtype=bool), bitorder="little")
+
+
+class FlatIPEngine:
+    def __init__(self, d: int, device: int = 0, capacity_hint: int = 0):
+        self._h = ctypes.c_void_p()
+        self.d = int(d)
+        self.device = int(device)
+        N.check(N.lib().mvdb_index_create(self.d, self.device, int(capacity_hint), ctypes.byref(self._h)))
+
+    # -- lifetime ----------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            N.lib().mvdb_index_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def reset(self) -> None:
+        N.check(N.lib().mvdb_index_reset(self._h))
+
+    def set_option(self, name: str, value: int) -> None:
+        N.check(N.lib().mvdb_index_set_option(self._h, name.encode(), int(value)))
+
+    # -- size ----------------------------------------------------------------
+    def _counts(self) -> Tuple[int, int]:
+        nt, nl = ctypes.c_int64(), ctypes.c_int64()
+        N.check(N.lib().mvdb_index_ntotal(self._h, ctypes.byref(nt), ctypes.byref(nl)))
+        return nt.value, nl.value
+
+    @property
+    def ntotal(self) -> int:
+        return self._counts()[0]
+
+    @property
+    def nlive(self) -> int:
+        return self._counts()[1]
+
+    # -- ingest ---------------------------------------------------------------
+    def add(self, x, normalize: bool = False) -> int:
+        """index.add(x) (VDB:46); normalize=True fuses faiss.normalize_L2 (VDB:45).
+        Returns the row number of x[0]."""
+        x = _as_f32_2d(x, self.d, "rows")
+        first = ctypes.c_int64()
+        N.check(N.lib().mvdb_index_add(self._h, x.ctypes.data, x.shape[0], int(bool(normalize)),
+                                       ctypes.byref(first)))
+        return first.value
+
+    def add_device(self, ptr: int, n: int, normalize: bool = False) -> int:
+        first = ctypes.c_int64()
+        N.check(N.lib().mvdb_index_add_device(self._h, ctypes.c_void_p(ptr), int(n), int(bool(normalize)),
+                                              ctypes.byref(first)))
+        return first.value
+
+    def add_synthetic(self, seed: int, row0: int, n: int, dist: int = 0, normalize: bool = True) -> int:
+        first = ctypes.c_int64()
+        N.check(N.lib().mvdb_index_add_synthetic(self._h, int(seed), int(row0), int(n), int(dist),
+                                                 int(bool(normalize)), ctypes.byref(first)))
+        return first.value
+
+    # -- delete ---------------------------------------------------------------
+    def remove_rows(self, rows) -> None:
+        rows = np.ascontiguousarray(rows, dtype=np.int64).ravel()
+        N.check(N.lib().mvdb_index_remove_rows(self._h, rows.ctypes.data, rows.shape[0]))
+
+    def compact(self) -> int:
+        nt = ctypes.c_int64()
+        N.check(N.lib().mvdb_index_compact(self._h, ctypes.byref(nt)))
+        return nt.value
+
+    # -- read back --------------------------------------------------------------
+    def reconstruct(self, row: int) -> np.ndarray:
+        out = np.empty(self.d, dtype=np.float32)
+        N.check(N.lib().mvdb_index_reconstruct(self._h, int(row), out.ctypes.data))
+        return out
+
+    def reconstruct_n(self, row0: int, n: int) -> np.ndarray:
+        out = np.empty((int(n), self.d), dtype=np.float32)
+        N.check(N.lib().mvdb_index_reconstruct_n(self._h, int(row0), int(n), out.ctypes.data))
+        return out
+
+    def device_view(self):
+        """(matrix device pointer, leading dimension in floats, live-mask device pointer)."""
+        m, l = ctypes.c_void_p(), ctypes.c_void_p()
+        ld = ctypes.c_int64()
+        N.check(N.lib().mvdb_index_device_view(self._h, ctypes.byref(m), ctypes.byref(ld), ctypes.byref(l)))
+        return m.value, ld.value, l.value
+
+    # -- search ---------------------------------------------------------------
+    def search(self, q, k: int, mask: Optional[np.ndarray] = None, mask_rows: Optional[int] = None,
+               normalize: bool = False):
+        """index.search(q, k) (VDB:497).  `mask` is either a bool[n] array of
+        admissible rows or already-packed bytes (then pass mask_rows).
+        Returns (D float32[nq,k], I int64[nq,k]) with faiss padding."""
+        q = _as_f32_2d(q, self.d, "queries")
+        k = int(k)
+        if k <= 0:
+            raise ValueError("k must be positive")
+        nq = q.shape[0]
+        D = np.empty((nq, k), dtype=np.float32)
+        I = np.empty((nq, k), dtype=np.int64)
+        mptr, mrows = None, 0
+        if mask is not None:
+            mask = np.asarray(mask)
+            if mask.dtype == np.bool_:
+                mrows = mask.shape[0]
+                mask = pack_mask(mask)
+            else:
+                mask = np.ascontiguousarray(mask, dtype=np.uint8)
+                mrows = int(mask_rows) if mask_rows is not None else mask.shape[0] * 8
+                if mrows > mask.shape[0] * 8:
+                    raise ValueError("mask_rows exceeds the mask length")
+            mptr = mask.ctypes.data
+        N.check(N.lib().mvdb_index_search(self._h, q.ctypes.data, nq, k, mptr, mrows,
+                                          int(bool(normalize)), D.ctypes.data, I.ctypes.data))
+        return D, I
+
+    # -- device-buffer flavour (sharded path, bench) -----------------------------
+    def workspace(self) -> "Workspace":
+        return Workspace(self)
+
+    def search_device(self, ws: "Workspace", q_ptr: int, nq: int, k: int, D_ptr: int, I_ptr: int,
+                      mask_ptr: int = 0, mask_rows: int = 0, normalize: bool = False,
+                      label_offset: int = 0, stream: int = 0) -> None:
+        N.check(N.lib().mvdb_index_search_device(
+            self._h, ws._h, ctypes.c_void_p(q_ptr), int(nq), int(k),
+            ctypes.c_void_p(mask_ptr) if mask_ptr else None, int(mask_rows), int(bool(normalize)),
+            int(label_offset), ctypes.c_void_p(D_ptr), ctypes.c_void_p(I_ptr),
+            ctypes.c_void_p(stream) if stream else None))
+
+
+class Workspace:
+    def __init__(self, engine: FlatIPEngine):
+        self._h = ctypes.c_void_p()
+        self._engine = engine  # keep the index alive
+        N.check(N.lib().mvdb_index_workspace_create(engine.handle, ctypes.byref(self._h)))
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            N.lib().mvdb_index_workspace_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def normalize_L2(x: np.ndarray, device: int = 0) -> None:
+    """faiss.normalize_L2 (VDB:475): in place on a C-contiguous float32 [n, d] array."""
+    if not (isinstance(x, np.ndarray) and x.dtype == np.float32 and x.ndim == 2 and x.flags.c_contiguous):
+        raise TypeError("normalize_L2 needs a C-contiguous float32 [n, d] array")
+    N.check(N.lib().mvdb_normalize_L2(x.ctypes.data, x.shape[0], x.shape[1], int(device)))
+
+
+def merge_topk_device(device: int, D_parts_ptr: int, I_parts_ptr: int, nparts: int, nq: int, k: int,
+                      D_out_ptr: int, I_out_ptr: int, stream: int = 0) -> None:
+    N.check(N.lib().mvdb_merge_topk_device(int(device), ctypes.c_void_p(D_parts_ptr), ctypes.c_void_p(I_parts_ptr),
+                                           int(nparts), int(nq), int(k), ctypes.c_void_p(D_out_ptr),
+                                           ctypes.c_void_p(I_out_ptr),
+                                           ctypes.c_void_p(stream) if stream else None))

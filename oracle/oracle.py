@@ -1,0 +1,284 @@
+"""oracle/oracle.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Python face of the CPU checker for MiniVectorDB's flat inner-product hot path.
+PARITY UNPINNED (see the header of oracle/faiss_flat_ip.c): faiss-cpu, the
+library the reference delegates this path to (ref: minivectordb/
+vector_database.py:43-46, 475, 497, 511-514), is an un-vendored, un-pinned
+dependency that cannot be installed in this image, and the reference's tests
+hold no numeric golden vector for the scan.
+
+Three layers, each usable on its own:
+
+* ``IndexFlatIP`` / ``normalize_L2`` -- faiss-shaped objects backed by the C
+  restatement (liboracle.so).  With ``install_as_faiss()`` the reference's own
+  Python modules can be imported on top of them (used by
+  tests/golden/make_golden.py to generate fixtures from the reference code).
+* ``gold_scores`` / ``gold_topk`` -- float64 numpy scorer with a deterministic
+  order (score descending, row ascending); the arbiter of near-ties.
+* ``classify_parity`` -- the parity rule of SURVEY.md section 8c: ids equal
+  position-wise, a mismatch excused only when the float64 scores of the two
+  ids are closer than the fp32 accumulation bound; distances within 1e-5
+  relative.
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU legs import this.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import sys
+import types
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+FLT_LOWEST = float(np.finfo(np.float32).min)
+
+
+def build(force: bool = False) -> str:
+    """Compile liboracle.so with oracle/Makefile (gcc is in the image)."""
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "faiss_flat_ip.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "-s", "-B", "liboracle.so"], check=True,
+                       env={**os.environ, "CC": "/usr/bin/gcc"})
+    return so
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        so = build()
+        try:
+            lib = ctypes.CDLL(so)
+        except OSError:
+            lib = ctypes.CDLL(build(force=True))
+        f32p = ctypes.POINTER(ctypes.c_float)
+        i64p = ctypes.POINTER(ctypes.c_int64)
+        i64 = ctypes.c_int64
+        lib.orc_renorm_L2.argtypes = [i64, i64, f32p]
+        lib.orc_renorm_L2.restype = None
+        lib.orc_search_flat_ip.argtypes = [f32p, i64, i64, f32p, i64, i64, f32p, i64p, ctypes.c_int]
+        lib.orc_search_flat_ip.restype = ctypes.c_int
+        lib.orc_search_gathered.argtypes = [f32p, i64, i64, i64p, i64, f32p, i64, i64, f32p, i64p,
+                                            f32p, ctypes.c_int]
+        lib.orc_search_gathered.restype = ctypes.c_int
+        lib.orc_synth_rows.argtypes = [ctypes.c_uint64, i64, i64, i64, ctypes.c_int, f32p]
+        lib.orc_synth_rows.restype = None
+        lib.orc_num_threads.restype = ctypes.c_int
+        _LIB = lib
+    return _LIB
+
+
+def _f32p(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+
+def _i64p(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))
+
+
+def num_threads() -> int:
+    return int(_lib().orc_num_threads())
+
+
+# ---------------------------------------------------------------------------
+# faiss-shaped layer
+# ---------------------------------------------------------------------------
+
+def normalize_L2(x: np.ndarray) -> None:
+    """faiss.normalize_L2: in place, float32 C-contiguous [n, d]."""
+    if not (isinstance(x, np.ndarray) and x.dtype == np.float32 and x.ndim == 2
+            and x.flags.c_contiguous):
+        raise TypeError("normalize_L2 needs a C-contiguous float32 [n, d] array")
+    n, d = x.shape
+    _lib().orc_renorm_L2(d, n, _f32p(x))
+
+
+def search_flat_ip(x: np.ndarray, q: np.ndarray, k: int, nthreads: int = 0):
+    """IndexFlatIP.search on an explicit matrix: returns (D[nq,k], I[nq,k])."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    q = np.ascontiguousarray(q, dtype=np.float32)
+    assert x.ndim == 2 and q.ndim == 2 and x.shape[1] == q.shape[1]
+    assert k > 0
+    nq = q.shape[0]
+    D = np.empty((nq, k), dtype=np.float32)
+    I = np.empty((nq, k), dtype=np.int64)
+    rc = _lib().orc_search_flat_ip(_f32p(x), x.shape[0], x.shape[1], _f32p(q), nq, k,
+                                   _f32p(D), _i64p(I), nthreads)
+    if rc != 0:
+        raise RuntimeError(f"orc_search_flat_ip rc={rc}")
+    return D, I
+
+
+def search_gathered(x: np.ndarray, rows: np.ndarray, q: np.ndarray, k: int, nthreads: int = 0):
+    """The reference's filtered branch (VDB:508-523): gather `rows` (in the
+    order given) into a temporary index and search it.  Returns (D, P) with P
+    positions into `rows`."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    q = np.ascontiguousarray(q, dtype=np.float32)
+    rows = np.ascontiguousarray(rows, dtype=np.int64)
+    nq = q.shape[0]
+    D = np.empty((nq, k), dtype=np.float32)
+    P = np.empty((nq, k), dtype=np.int64)
+    scratch = np.empty((max(len(rows), 1), x.shape[1]), dtype=np.float32)
+    rc = _lib().orc_search_gathered(_f32p(x), x.shape[0], x.shape[1], _i64p(rows), len(rows),
+                                    _f32p(q), nq, k, _f32p(D), _i64p(P), _f32p(scratch), nthreads)
+    if rc != 0:
+        raise RuntimeError(f"orc_search_gathered rc={rc}")
+    return D, P
+
+
+def search_masked(x: np.ndarray, admissible: np.ndarray, q: np.ndarray, k: int, nthreads: int = 0):
+    """Bit-mask flavour of the filtered branch: admissible rows gathered in
+    ascending row order, results mapped back to row numbers (-1 padded)."""
+    rows = np.flatnonzero(np.asarray(admissible, dtype=bool)).astype(np.int64)
+    D, P = search_gathered(x, rows, q, k, nthreads)
+    I = np.where(P >= 0, rows[np.clip(P, 0, max(len(rows) - 1, 0))] if len(rows) else -1, -1)
+    return D, I.astype(np.int64)
+
+
+class IndexFlatIP:
+    """faiss.IndexFlatIP restated: keeps a private copy of the rows it is given
+    (faiss copies on add; ref VDB:46) and scans them on search (VDB:497)."""
+
+    def __init__(self, d: int):
+        self.d = int(d)
+        self._chunks = []
+        self._x = np.zeros((0, self.d), dtype=np.float32)
+        self.ntotal = 0
+
+    def add(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        assert x.ndim == 2 and x.shape[1] == self.d
+        self._chunks.append(x.copy())
+        self.ntotal += x.shape[0]
+
+    def _matrix(self):
+        if self._chunks:
+            self._x = np.vstack([self._x] + self._chunks)
+            self._chunks = []
+        return self._x
+
+    def search(self, q, k, nthreads: int = 0):
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        assert q.ndim == 2 and q.shape[1] == self.d
+        assert k > 0
+        return search_flat_ip(self._matrix(), q, int(k), nthreads)
+
+
+def install_as_faiss() -> types.ModuleType:
+    """Register a module named ``faiss`` backed by this oracle so that the
+    reference's Python files (which do ``import faiss``) run unmodified.
+    Used only by tests/golden/make_golden.py inside the build container."""
+    m = types.ModuleType("faiss")
+    m.IndexFlatIP = IndexFlatIP
+    m.normalize_L2 = normalize_L2
+    m.__oracle__ = True
+    sys.modules["faiss"] = m
+    return m
+
+
+# ---------------------------------------------------------------------------
+# synthetic data (bit-identical to the CUDA generator in csrc/)
+# ---------------------------------------------------------------------------
+
+DIST_BELL, DIST_UNIFORM = 0, 1
+
+
+def synth_rows(seed: int, row0: int, n: int, d: int, dist: int = DIST_BELL) -> np.ndarray:
+    out = np.empty((n, d), dtype=np.float32)
+    _lib().orc_synth_rows(seed, row0, n, d, dist, _f32p(out))
+    return out
+
+
+def synth_rows_numpy(seed: int, row0: int, n: int, d: int, dist: int = DIST_BELL) -> np.ndarray:
+    """Same generator in pure numpy (cross-check of the C and CUDA versions)."""
+    M = np.uint64
+    with np.errstate(over="ignore"):
+        rows = (np.arange(row0, row0 + n, dtype=np.uint64)[:, None] << M(20))
+        z = rows + np.arange(d, dtype=np.uint64)[None, :] + M(seed) * M(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> M(30))) * M(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> M(27))) * M(0x94D049BB133111EB)
+        z = z ^ (z >> M(31))
+    if dist == DIST_BELL:
+        s = ((z & M(0xFFFF)) + ((z >> M(16)) & M(0xFFFF)) + ((z >> M(32)) & M(0xFFFF))
+             + (z >> M(48))).astype(np.int64)
+        return ((s - 131070).astype(np.float32) * np.float32(1.0 / 65536.0)).astype(np.float32)
+    return ((z >> M(40)).astype(np.float32) * np.float32(1.0 / 16777216.0)).astype(np.float32)
+
+
+# ---------------------------------------------------------------------------
+# float64 gold + parity rule
+# ---------------------------------------------------------------------------
+
+def gold_scores(x: np.ndarray, q: np.ndarray) -> np.ndarray:
+    """float64 inner products [nq, n] of the float32 inputs."""
+    return np.asarray(q, dtype=np.float64) @ np.asarray(x, dtype=np.float64).T
+
+
+def gold_topk(x: np.ndarray, q: np.ndarray, k: int, admissible=None):
+    """Deterministic float64 top-k: score descending, row ascending; -1 padded."""
+    S = gold_scores(x, q)
+    nq, n = S.shape
+    if admissible is not None:
+        S = np.where(np.asarray(admissible, dtype=bool)[None, :], S, -np.inf)
+    D = np.full((nq, k), FLT_LOWEST, dtype=np.float64)
+    I = np.full((nq, k), -1, dtype=np.int64)
+    for i in range(nq):
+        order = np.lexsort((np.arange(n), -S[i]))[:k]
+        order = order[np.isfinite(S[i][order])]
+        D[i, :len(order)] = S[i][order]
+        I[i, :len(order)] = order
+    return D, I
+
+
+def classify_parity(x, q, I_test, D_test, I_ref, D_ref, rel_tol=1e-5, admissible=None):
+    """Apply the parity rule.  Returns a dict with counts of position-wise id
+    matches, mismatches excused as exact ties / fp near-ties (judged in
+    float64), real errors, and the worst relative distance error.
+
+    The fp32 accumulation bound used for a near-tie is
+    |s_a - s_b| <= 4 * d * 2^-24 * ||q|| * max||x||  (loose, order-independent)."""
+    x = np.asarray(x, dtype=np.float32)
+    q = np.asarray(q, dtype=np.float32)
+    nq, k = I_ref.shape
+    d = x.shape[1]
+    xn = float(np.sqrt((x.astype(np.float64) ** 2).sum(1)).max()) if len(x) else 0.0
+    out = dict(positions=int(nq * k), id_equal=0, exact_tie=0, near_tie=0, real_error=0,
+               max_rel_err=0.0, set_equal_queries=0)
+    for i in range(nq):
+        qi = q[i].astype(np.float64)
+        bound = 4.0 * d * 2.0 ** -24 * float(np.linalg.norm(qi)) * xn
+        if set(I_test[i].tolist()) == set(I_ref[i].tolist()):
+            out["set_equal_queries"] += 1
+        for j in range(k):
+            a, b = int(I_test[i, j]), int(I_ref[i, j])
+            if a == b:
+                out["id_equal"] += 1
+            elif a < 0 or b < 0:
+                out["real_error"] += 1
+                continue
+            else:
+                sa = float(x[a].astype(np.float64) @ qi)
+                sb = float(x[b].astype(np.float64) @ qi)
+                if admissible is not None and not (admissible[a] and admissible[b]):
+                    out["real_error"] += 1
+                elif sa == sb:
+                    out["exact_tie"] += 1
+                elif abs(sa - sb) <= bound:
+                    out["near_tie"] += 1
+                else:
+                    out["real_error"] += 1
+            if b >= 0 and a >= 0:
+                ref = float(D_ref[i, j])
+                # relative error; scores are cosines, so |ref| is floored at 1 % of
+                # ||q||*max||x|| to keep the rule meaningful for near-zero scores
+                floor = 0.01 * float(np.linalg.norm(qi)) * xn
+                err = abs(float(D_test[i, j]) - ref) / max(abs(ref), floor, 1e-30)
+                out["max_rel_err"] = max(out["max_rel_err"], err)
+    out["ok"] = out["real_error"] == 0 and out["max_rel_err"] <= rel_tol
+    return out
