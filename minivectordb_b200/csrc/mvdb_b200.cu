@@ -400,17 +400,40 @@ static int plan_scan(mvdb_index* ix, ScanParams& p, int nq, ScanPlan* plan) {
         return off + size_t(s) * p.stage_bytes;
     };
 
+    // TMA ring: stage s of the ring must always be consumed by the same warp
+    // (consumer of iteration `it` is warp it % ncw, its stage is it % S), else a
+    // warp that runs ahead could pass a full-barrier wait on the parity of an
+    // OLDER phase.  So S is rounded down to a multiple of ncw, and ncw is
+    // chosen to keep the ring deep for wide rows (e.g. d=1024: 7 stages x 7 warps).
     int variant = ix->scan_variant;
-    int ncw_tma = ix->consumer_warps > 0 ? std::min(ix->consumer_warps, 8) : (nq >= 4 ? 8 : 4);
-    int stages = 0;
+    int ncw_tma = 0, stages = 0;
     size_t smem = 0;
     bool tma = (variant != MVDB_SCAN_LDG);
     if (tma) {
-        smem = layout(ncw_tma, true, &stages);
-        if (stages < 3) {
-            if (variant == MVDB_SCAN_TMA && stages < 2)
-                return fail(MVDB_ERR_ARG, "dimension %d too large for the TMA scan ring", ix->d);
-            if (variant != MVDB_SCAN_TMA) tma = false;
+        const int pref = nq >= 4 ? 8 : 4;
+        int cand[9] = {pref, 8, 7, 6, 5, 4, 3, 2, 0};
+        if (ix->consumer_warps > 0) {
+            cand[0] = std::min(ix->consumer_warps, 8);
+            cand[1] = 0;
+        }
+        int best_score = 0;
+        for (int i = 0; cand[i]; i++) {
+            int s_raw = 0;
+            layout(cand[i], true, &s_raw);
+            int s_ok = s_raw / cand[i] * cand[i];
+            int score = std::min(s_ok, 8);
+            if (score > best_score) {
+                best_score = score;
+                ncw_tma = cand[i];
+                stages = s_ok;
+            }
+        }
+        // the ring needs >= 2 stages to overlap at all; AUTO wants >= 3
+        if (stages < 2 || (stages < 3 && variant != MVDB_SCAN_TMA)) tma = false;
+        if (tma) {
+            int s_raw = 0;
+            layout(ncw_tma, true, &s_raw);  // re-derive the offsets for the chosen ncw
+            smem = size_t(p.stage_off) + size_t(stages) * p.stage_bytes;
         }
     }
     if (tma) {
@@ -678,6 +701,7 @@ int mvdb_index_create(int d, int device, uint64_t capacity_hint, mvdb_index** ou
     ix->ld4 = int(ix->ld / 4);
     ix->sm_count = prop.multiProcessorCount;
     ix->smem_optin = prop.sharedMemPerBlockOptin;
+    if (const char* sl = getenv("MVDB_SMEM_SLACK")) ix->smem_optin -= size_t(atoi(sl));
     size_t free_b = 0, total_b = 0;
     CU_OK(cudaMemGetInfo(&free_b, &total_b));
     size_t reserve = capacity_hint ? size_t(capacity_hint) * ix->ld * 4 : total_b;

@@ -119,17 +119,23 @@ __device__ __forceinline__ void finish_scan(const ScanParams& p, SmemHeader* hdr
     if (!hdr->last_flag) return;
     // ---- last CTA: merge the G partial lists of every query ---------------
     __threadfence();
-    const int total = G * k;
-    const int chunk = (total + ncw - 1) / ncw;
+    // Every CTA list is sorted best-first, so the lists are streamed COLUMN by
+    // column (all heads, then all second entries, ...): the threshold rises
+    // after the first few columns and a column in which no list beats it ends
+    // the merge -- deeper entries are smaller still.  Warp cw takes lists
+    // cw, cw+ncw, ...; one lane per list.
     for (int qi = 0; qi < nq; qi++) {
         WarpSelect f;
         f.init(selbuf + size_t(cw * nq + qi) * cap, cap, k);
-        const uint64_t* src = p.partials + size_t(qi) * total;
-        int lo = cw * chunk, hi = min(total, lo + chunk);
-        for (int i = lo; i < hi; i += kWarp) {
-            int j = i + lane;
-            uint64_t key = (j < hi) ? __ldcg(src + j) : kEmptyKey;
-            f.push(j < hi, key, lane);
+        const uint64_t* src = p.partials + size_t(qi) * G * k;
+        for (int col = 0; col < k; col++) {
+            bool any = false;
+            for (int base = cw; base < G; base += ncw * kWarp) {
+                int c = base + lane * ncw;
+                uint64_t key = (c < G) ? __ldcg(src + size_t(c) * k + col) : kEmptyKey;
+                any |= f.push(c < G, key, lane);
+            }
+            if (!any) break;
         }
         f.compact(lane);
         if (lane == 0) hdr->cnts[cw * nq + qi] = f.cnt;

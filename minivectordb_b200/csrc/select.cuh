@@ -66,7 +66,8 @@ struct WarpSelect {
 
     // Called by all 32 lanes (converged).  `key` is considered only where
     // `valid`; kEmptyKey never passes because thr >= kEmptyKey.
-    __device__ __forceinline__ void push(bool valid, uint64_t key, int lane) {
+    // Returns true (warp-uniform) when at least one candidate was admitted.
+    __device__ __forceinline__ bool push(bool valid, uint64_t key, int lane) {
         bool pass = valid && key > thr;
         unsigned m = __ballot_sync(0xFFFFFFFFu, pass);
         if (m) {
@@ -75,6 +76,7 @@ struct WarpSelect {
             cnt += __popc(m);
             if (cnt + kWarp > cap) compact(lane);
         }
+        return m != 0;
     }
 
     // Stream `n` keys from memory (global or shared) through the filter.

@@ -324,3 +324,24 @@ def test_full_size_properties_config2(mv):
     D, I = eng.search(q, k, mask=sub)
     _check(xs, q, k, D, I, sub[:m])
     eng.close()
+
+
+@pytest.mark.parametrize("d", [384, 512, 768, 1024, 1536])
+def test_tma_ring_any_consumer_warp_count(mv, d):
+    """Regression: the ring depth must be a multiple of the consumer-warp count
+    (a warp running ahead must never pass a full-barrier wait on an older
+    phase's parity).  Many tiles per CTA so that warps do drift apart."""
+    n = 120_000
+    eng = mv.FlatIPEngine(d)
+    eng.add_synthetic(7, 0, n, dist=0, normalize=True)
+    q = O.synth_rows(8, 0, 2, d)
+    O.normalize_L2(q)
+    eng.set_option("scan_variant", 2)
+    Dref, Iref = eng.search(q, 10)
+    eng.set_option("scan_variant", 1)
+    for cw in range(1, 9):
+        eng.set_option("consumer_warps", cw)
+        for _ in range(3):
+            D, I = eng.search(q, 10)
+            assert np.array_equal(I, Iref) and np.array_equal(D, Dref), (d, cw)
+    eng.close()
