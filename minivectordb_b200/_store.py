@@ -1,0 +1,328 @@
+"""Shared host-side core of the two drop-in database classes.
+
+What the reference keeps as a numpy matrix + a faiss index + id dicts that are
+all rebuilt or copied on every mutation (ref minivectordb/vector_database.py:
+42-47, 57-155), this keeps as:
+
+* one `FlatIPEngine` (HBM-resident matrix + tombstones) per partition -- one
+  partition for `VectorDatabase`, one per device for `ShardedVectorDatabase`;
+* append-only host arrays indexed by a global insertion id ("gid"): user id,
+  metadata dict, live flag, (partition, slot);
+* a columnar `FilterIndex` over gids that turns the mongo-like filters into
+  the admissible-row bitmask the scan consumes.
+
+Row numbers the user can observe (`id_map`, `inverse_id_map`, `metadata`
+order, `embeddings[i]`) are the reference's dense LOGICAL rows: the rank of a
+row among the live rows in insertion order.  Deleting therefore "renumbers"
+exactly as the reference does (VDB:138-152) without touching the matrix;
+physical compaction happens lazily and preserves order, so exact-tie order
+(ascending row) is the same before and after.
+
+Inserted rows are staged on the host, raw, and flushed to the GPU (normalised
+by the ingest kernel) at the next search -- the analogue of the reference's
+lazy `_build_index` (VDB:477-479), and the reason `get_vector` returns raw
+values before the first search and normalised values after it, as the
+reference does (VDB:45, 49-55).
+"""
+from __future__ import annotations
+
+import threading
+from collections import defaultdict
+from typing import List, Optional
+
+import numpy as np
+
+from . import rerank as _rerank
+from .engine import FlatIPEngine, pack_mask
+from .filters import FilterIndex
+
+
+class _Partition:
+    """One device-resident row shard and the host rows waiting to join it."""
+
+    def __init__(self, device: int):
+        self.device = device
+        self.engine: Optional[FlatIPEngine] = None
+        self.gids: List[int] = []        # slot -> gid, for flushed AND pending slots
+        self.flushed = 0                 # slots [0, flushed) live on the device
+        self.pending: List[np.ndarray] = []
+        self.dead_unflushed: List[int] = []  # slots deleted on the host, not yet tombstoned on the device
+        self.n_dead = 0                  # tombstones currently held by the engine (+ unflushed ones)
+        self._gids_np = None
+
+    def gids_np(self) -> np.ndarray:
+        if self._gids_np is None or self._gids_np.shape[0] != len(self.gids):
+            self._gids_np = np.asarray(self.gids, dtype=np.int64)
+        return self._gids_np
+
+
+class EmbeddingsView:
+    """Read-only stand-in for the reference's `self.embeddings` ndarray
+    (VDB:12): len(), .shape, row indexing and np.asarray() in LOGICAL row order."""
+
+    def __init__(self, store: "GpuStore"):
+        self._s = store
+
+    def __len__(self):
+        return self._s._n_live
+
+    @property
+    def shape(self):
+        return (self._s._n_live, self._s.embedding_size)
+
+    @property
+    def dtype(self):
+        return np.dtype(np.float32)
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._s._materialize()
+        return a if dtype is None else a.astype(dtype)
+
+    def __getitem__(self, idx):
+        if isinstance(idx, (int, np.integer)):
+            with self._s.lock:
+                gids = self._s._live_gids()
+                return self._s._row_of_gid(int(gids[idx]))
+        return self._s._materialize()[idx]
+
+    def __iter__(self):
+        return iter(self._s._materialize())
+
+
+class GpuStore:
+    COMPACT_MIN_DEAD = 4096      # do not bother compacting below this many tombstones
+    COMPACT_DEAD_FRACTION = 0.25
+
+    def __init__(self, devices=None):
+        self.embedding_size = None
+        self.lock = threading.Lock()
+        self.inverted_index = defaultdict(set)   # metadata key -> set of unique ids (VDB:16, 78-79)
+        self._devices = list(devices) if devices else [0]
+        self._parts = [_Partition(dev) for dev in self._devices]
+        self._g_uid: List = []
+        self._g_meta: List[dict] = []
+        self._g_part: List[int] = []
+        self._g_slot: List[int] = []
+        self._g_live = np.zeros(1024, dtype=bool)
+        self._g_n = 0
+        self._n_live = 0
+        self._uid_gid = {}
+        self._filters = FilterIndex()
+        self._ever_stored = False
+        self._active_searches = 0
+        self._views = None               # cached (id_map, inverse_id_map, metadata, unique_ids)
+        self._embeddings_changed = False  # kept for API parity (VDB:18); True while rows wait on the host
+
+    # ------------------------------------------------------------------ views
+    def _live_gids(self) -> np.ndarray:
+        return np.flatnonzero(self._g_live[:self._g_n])
+
+    def _build_views(self):
+        if self._views is None:
+            gids = self._live_gids().tolist()
+            uids = [self._g_uid[g] for g in gids]
+            self._views = ({i: u for i, u in enumerate(uids)}, {u: i for i, u in enumerate(uids)},
+                           [self._g_meta[g] for g in gids], uids)
+        return self._views
+
+    @property
+    def embeddings(self):
+        return EmbeddingsView(self) if self._ever_stored else None
+
+    def _row_of_gid(self, gid: int) -> np.ndarray:
+        part = self._parts[self._g_part[gid]]
+        slot = self._g_slot[gid]
+        if slot >= part.flushed:
+            return part.pending[slot - part.flushed]
+        return part.engine.reconstruct(slot)
+
+    def _materialize(self) -> np.ndarray:
+        """All live rows, logical order, float32 [n_live, d] (what the reference's
+        `self.embeddings` holds: normalised rows once flushed, raw while pending)."""
+        with self.lock:
+            d = self.embedding_size or 0
+            gids = self._live_gids()
+            out = np.empty((gids.shape[0], d), dtype=np.float32)
+            if gids.shape[0] == 0:
+                return out
+            gpart = np.asarray(self._g_part, dtype=np.int64)[gids]
+            gslot = np.asarray(self._g_slot, dtype=np.int64)[gids]
+            for pi, part in enumerate(self._parts):
+                sel = np.flatnonzero(gpart == pi)
+                if sel.size == 0:
+                    continue
+                slots = gslot[sel]
+                on_dev = slots < part.flushed
+                if on_dev.any():
+                    lo, hi = int(slots[on_dev].min()), int(slots[on_dev].max()) + 1
+                    block = part.engine.reconstruct_n(lo, hi - lo)
+                    out[sel[on_dev]] = block[slots[on_dev] - lo]
+                for j in np.flatnonzero(~on_dev):
+                    out[sel[j]] = part.pending[int(slots[j]) - part.flushed]
+            return out
+
+    # --------------------------------------------------------------- mutation
+    def _as_row(self, embedding) -> np.ndarray:
+        row = np.array(embedding, dtype=np.float32)
+        if row.ndim != 1:
+            row = row.reshape(-1)
+        if self.embedding_size is None:
+            self.embedding_size = int(row.shape[0])
+        elif row.shape[0] != self.embedding_size:
+            # np.vstack raises the same type in the reference (VDB:72)
+            raise ValueError(f"embedding has dimension {row.shape[0]}, database has {self.embedding_size}")
+        return row
+
+    def _append(self, uid, row: np.ndarray, metadata: dict) -> None:
+        """Caller holds the lock and has validated uid / dimension."""
+        gid = self._g_n
+        if gid >= self._g_live.shape[0]:
+            grown = np.zeros(self._g_live.shape[0] * 2, dtype=bool)
+            grown[:gid] = self._g_live[:gid]
+            self._g_live = grown
+        pi = min(range(len(self._parts)), key=lambda i: len(self._parts[i].gids)) if len(self._parts) > 1 else 0
+        part = self._parts[pi]
+        self._g_uid.append(uid)
+        self._g_meta.append(metadata)
+        self._g_part.append(pi)
+        self._g_slot.append(len(part.gids))
+        part.gids.append(gid)
+        part.pending.append(row)
+        self._g_live[gid] = True
+        self._g_n = gid + 1
+        self._n_live += 1
+        self._uid_gid[uid] = gid
+        self._filters.add_row(gid, metadata)
+        for key in metadata:
+            self.inverted_index[key].add(uid)
+        self._ever_stored = True
+        self._embeddings_changed = True
+        self._views = None
+
+    def _remove(self, uid) -> None:
+        """Caller holds the lock and has checked that uid exists."""
+        gid = self._uid_gid.pop(uid)
+        self._g_live[gid] = False
+        self._n_live -= 1
+        part = self._parts[self._g_part[gid]]
+        part.dead_unflushed.append(self._g_slot[gid])
+        part.n_dead += 1
+        for key in self._g_meta[gid]:
+            ids = self.inverted_index.get(key)
+            if ids is not None:
+                ids.discard(uid)
+                if not ids:
+                    del self.inverted_index[key]
+        self._embeddings_changed = True
+        self._views = None
+
+    # ------------------------------------------------------------------ flush
+    def _flush(self) -> None:
+        """Move staged rows / tombstones to the GPU.  Caller holds the lock."""
+        for part in self._parts:
+            if part.pending:
+                if part.engine is None:
+                    part.engine = FlatIPEngine(self.embedding_size, device=part.device)
+                block = np.vstack(part.pending) if len(part.pending) > 1 else part.pending[0][None, :]
+                part.engine.add(block, normalize=True)   # faiss.normalize_L2 + index.add (VDB:45-46)
+                part.flushed = len(part.gids)
+                part.pending = []
+            if part.dead_unflushed:
+                part.engine.remove_rows(np.asarray(part.dead_unflushed, dtype=np.int64))
+                part.dead_unflushed = []
+        self._embeddings_changed = False
+        dead = self._g_n - self._n_live
+        if (dead >= self.COMPACT_MIN_DEAD and dead >= self.COMPACT_DEAD_FRACTION * self._g_n
+                and self._active_searches == 0):
+            self._compact()
+
+    def _compact(self) -> None:
+        """Order-preserving squeeze of tombstones on the device and of the host
+        arrays.  Caller holds the lock; no search is in flight."""
+        keep = self._live_gids()
+        remap = np.full(self._g_n, -1, dtype=np.int64)
+        remap[keep] = np.arange(keep.shape[0])
+        for part in self._parts:
+            if part.engine is not None and part.n_dead:
+                part.engine.compact()
+            part.gids = [int(remap[g]) for g in part.gids if remap[g] >= 0]
+            part.flushed = len(part.gids)
+            part.n_dead = 0
+            part._gids_np = None
+        keep_l = keep.tolist()
+        self._g_uid = [self._g_uid[g] for g in keep_l]
+        self._g_meta = [self._g_meta[g] for g in keep_l]
+        self._g_part = [self._g_part[g] for g in keep_l]
+        self._g_n = len(keep_l)
+        self._g_slot = [0] * self._g_n
+        for part in self._parts:
+            for slot, g in enumerate(part.gids):
+                self._g_slot[g] = slot
+        live = np.zeros(max(1024, 2 * self._g_n), dtype=bool)
+        live[:self._g_n] = True
+        self._g_live = live
+        self._uid_gid = {u: g for g, u in enumerate(self._g_uid)}
+        self._filters.clear()
+        for g, meta in enumerate(self._g_meta):
+            self._filters.add_row(g, meta)
+        self._views = None
+
+    # ----------------------------------------------------------------- search
+    def _search(self, embedding, metadata_filter, exclude_filter, or_filters, k, autocut):
+        if not self._ever_stored:
+            return [], [], []
+        q = np.array(embedding, dtype=np.float32).reshape(1, -1)
+        with self.lock:
+            self._flush()
+            n = self._g_n
+            live = self._g_live[:n]
+            if metadata_filter or exclude_filter or or_filters:
+                adm = self._filters.admissible(live, metadata_filter, exclude_filter, or_filters)
+            else:
+                adm = None
+            count = self._n_live if adm is None else int(adm.sum())
+            if count == 0:
+                return [], [], []
+            if adm is not None and count == self._n_live:
+                adm = None  # every live row admissible: plain search (VDB:495-497)
+            jobs = []
+            for part in self._parts:
+                if part.engine is None or part.flushed == 0:
+                    continue
+                if adm is None:
+                    jobs.append((part, part.gids, None, 0))
+                else:
+                    pm = adm[part.gids_np()] if len(self._parts) > 1 or part.flushed != n else adm
+                    jobs.append((part, part.gids, pack_mask(pm), part.flushed))
+            g_uid, g_meta, g_live = self._g_uid, self._g_meta, self._g_live
+            self._active_searches += 1
+        try:
+            search_k = min(int(k), count)  # VDB:489-492
+            cands = []
+            for part, gids, packed, mrows in jobs:
+                D, I = part.engine.search(q, search_k, mask=packed, mask_rows=mrows, normalize=True)
+                for slot, dist in zip(I[0], D[0]):
+                    if slot == -1:
+                        continue  # VDB:500
+                    cands.append((dist, gids[slot]))
+            if len(jobs) > 1:
+                cands.sort(key=lambda c: (-c[0], c[1]))  # score desc, insertion order on exact ties
+                cands = cands[:search_k]
+            found = [(g_uid[g], dist, g_meta[g]) for dist, g in cands if g_live[g]]
+        finally:
+            with self.lock:
+                self._active_searches -= 1
+        ids, distances, metadatas = zip(*found) if found else ([], [], [])
+        if autocut and len(distances) > 1:
+            drop = set(_rerank.autocut_scores(distances))
+            if drop:
+                ids = [v for i, v in enumerate(ids) if i not in drop]
+                distances = [v for i, v in enumerate(distances) if i not in drop]
+                metadatas = [v for i, v in enumerate(metadatas) if i not in drop]
+        return ids, distances, metadatas
+
+    def close(self) -> None:
+        for part in self._parts:
+            if part.engine is not None:
+                part.engine.close()
+                part.engine = None

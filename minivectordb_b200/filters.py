@@ -1,0 +1,183 @@
+"""Columnar evaluation of MiniVectorDB's mongo-like metadata filters.
+
+The reference evaluates filters with per-row Python loops over sets of row
+numbers (ref minivectordb/vector_database.py:157-386) and hands the resulting
+set to the scan, which then gathers the admissible rows.  Here the OUTPUT
+contract is the same -- the admissible set -- but it is produced as a boolean
+column over rows so it can be shipped to the GPU as a bitmask and applied in
+the scan's epilogue.  Semantics kept identical to the reference:
+
+* AND filters (`metadata_filter`): dict or list of dicts, every key must match
+  (VDB:238-318).  A value that is a dict is an operator clause; ONLY ITS FIRST
+  operator is honoured (VDB:243).  Anything else is an equality test.
+* OR filters (`or_filters`): dict or list of dicts; the union over all dicts
+  AND over all keys inside a dict (VDB:157-236), intersected with the AND
+  result (VDB:373-377).  Empty dicts are dropped (VDB:371).
+* Exclude filter: dict or list of dicts, equality only, union is removed
+  (VDB:320-352).
+* Operators $gt $gte $lt $lte $ne $in (VDB:166-173); `$in` is "operand is
+  contained in the stored value" (VDB:172); unknown -> ValueError (VDB:175).
+* Only rows whose metadata HAS the key can match (inverted index, VDB:260), so
+  `$ne` does not match rows lacking the key.
+
+A column caches a typed numpy view (numbers, strings) so the common predicates
+are single vectorised comparisons; every other value type falls back to a
+Python loop over that column only, with the reference's exact operator calls
+(so errors such as comparing incomparable types surface the same way).
+"""
+from __future__ import annotations
+
+import operator
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+
+_OPS = {
+    "$gt": operator.gt,
+    "$gte": operator.ge,
+    "$lt": operator.lt,
+    "$lte": operator.le,
+    "$ne": operator.ne,
+    "$in": lambda stored, operand: operand in stored,
+}
+_NUM_TYPES = (int, float, np.integer, np.floating)
+_EXACT_INT = 1 << 53
+
+
+def _is_plain_number(v) -> bool:
+    return isinstance(v, _NUM_TYPES) and not (isinstance(v, (int, np.integer)) and abs(int(v)) > _EXACT_INT)
+
+
+class Column:
+    """All rows that carry one metadata key: parallel lists (row id, value)."""
+
+    __slots__ = ("rows", "vals", "_rows_np", "_vals_np", "_kind", "_built")
+
+    def __init__(self):
+        self.rows: List[int] = []
+        self.vals: List[Any] = []
+        self._rows_np = None
+        self._vals_np = None
+        self._kind = None
+        self._built = 0
+
+    def append(self, row: int, value) -> None:
+        self.rows.append(row)
+        self.vals.append(value)
+
+    def _typed(self):
+        n = len(self.rows)
+        if self._built != n:
+            self._rows_np = np.asarray(self.rows, dtype=np.int64)
+            vals = self.vals
+            if all(_is_plain_number(v) for v in vals):  # bool is an int: True == 1, as in Python
+                self._kind = "num"
+                self._vals_np = np.asarray(vals, dtype=np.float64)
+            elif all(isinstance(v, str) for v in vals):
+                self._kind = "str"
+                self._vals_np = np.asarray(vals, dtype=object)
+            else:
+                self._kind = "obj"
+                self._vals_np = None
+            self._built = n
+        return self._kind
+
+    def match(self, nrows: int, op: Optional[str], operand) -> np.ndarray:
+        """bool[nrows]: rows of this column whose value satisfies the clause
+        (op None = equality)."""
+        out = np.zeros(nrows, dtype=bool)
+        if not self.rows:
+            return out
+        kind = self._typed()
+        hit = None
+        if kind == "num" and _is_plain_number(operand) and op != "$in":
+            v, x = self._vals_np, float(operand)
+            hit = {None: lambda: v == x, "$gt": lambda: v > x, "$gte": lambda: v >= x, "$lt": lambda: v < x,
+                   "$lte": lambda: v <= x, "$ne": lambda: v != x}[op]()
+        elif kind == "str" and isinstance(operand, str) and op in (None, "$ne"):
+            hit = (self._vals_np == operand) if op is None else (self._vals_np != operand)
+        if hit is None:
+            # generic path: the reference's own operator call per stored value
+            fn = (lambda stored, x: stored == x) if op is None else _OPS[op]
+            hit = np.fromiter((bool(fn(s, operand)) for s in self.vals), dtype=bool, count=len(self.vals))
+        out[self._rows_np[hit]] = True
+        return out
+
+
+class FilterIndex:
+    """Metadata columns of one database + the three filter combinators."""
+
+    def __init__(self):
+        self.columns: Dict[str, Column] = {}
+
+    def clear(self) -> None:
+        self.columns = {}
+
+    def add_row(self, row: int, metadata: dict) -> None:
+        for key, value in metadata.items():
+            col = self.columns.get(key)
+            if col is None:
+                col = self.columns[key] = Column()
+            col.append(row, value)
+
+    # -- clause -------------------------------------------------------------
+    def _clause(self, nrows: int, key, value) -> np.ndarray:
+        if isinstance(value, dict):
+            op = next(iter(value))  # only the first operator counts (VDB:243)
+            if op not in _OPS:
+                raise ValueError(f"Invalid operator: {op}")
+            operand = value[op]
+        else:
+            op, operand = None, value
+        col = self.columns.get(key)
+        if col is None:
+            return np.zeros(nrows, dtype=bool)
+        return col.match(nrows, op, operand)
+
+    # -- combinators ----------------------------------------------------------
+    def admissible(self, live: np.ndarray, metadata_filter, exclude_filter, or_filters) -> Optional[np.ndarray]:
+        """bool[nrows] of admissible rows (already restricted to `live`), or
+        None when every live row is admissible (no mask needed)."""
+        nrows = live.shape[0]
+        cur: Optional[np.ndarray] = None if metadata_filter else live.copy()
+        unfiltered = not metadata_filter
+        if isinstance(metadata_filter, dict):
+            metadata_filter = [metadata_filter]
+        if metadata_filter:
+            for clause_set in metadata_filter:
+                for key, value in clause_set.items():
+                    hit = self._clause(nrows, key, value) & live
+                    cur = hit if cur is None else (cur & hit)
+                    if not cur.any():
+                        break
+        if or_filters:
+            if isinstance(or_filters, dict):
+                or_filters = [or_filters]
+            or_filters = [f for f in or_filters if f]
+            if or_filters:
+                union = np.zeros(nrows, dtype=bool)
+                for clause_set in or_filters:
+                    for key, value in clause_set.items():
+                        union |= self._clause(nrows, key, value)
+                union &= live
+                cur = union if cur is None else (cur & union)
+                unfiltered = False
+        if exclude_filter:
+            if isinstance(exclude_filter, dict):
+                exclude_filter = [exclude_filter]
+            if cur is None:
+                # the reference fails here too (`None -= set`, VDB:348)
+                raise TypeError("unsupported operand type(s) for -=: 'NoneType' and 'set'")
+            for clause_set in exclude_filter:
+                for key, value in clause_set.items():
+                    col = self.columns.get(key)
+                    if col is not None:
+                        cur &= ~col.match(nrows, None, value)  # equality only (VDB:343)
+                        unfiltered = False
+                    if not cur.any():
+                        break
+        if cur is None:
+            return np.zeros(nrows, dtype=bool)
+        if unfiltered:
+            return None
+        return cur

@@ -1,0 +1,84 @@
+"""CPU: host logic of the drop-in classes on the oracle-backed FakeEngine,
+including the golden scenario produced by the REFERENCE's own classes."""
+import pytest
+
+import dropin_cases as C
+from fake_engine import FakeEngine
+
+
+@pytest.fixture()
+def classes(monkeypatch):
+    import minivectordb_b200._store as store
+    monkeypatch.setattr(store, "FlatIPEngine", FakeEngine)
+    from minivectordb_b200.vector_database import VectorDatabase
+    from minivectordb_b200.sharded_vector_database import ShardedVectorDatabase
+    return VectorDatabase, ShardedVectorDatabase
+
+
+def test_golden_scenario_vdb(classes, tmp_path):
+    C.case_golden_scenario_vdb(classes[0], tmp_path)
+
+
+def test_golden_scenario_svdb(classes, tmp_path):
+    C.case_golden_scenario_svdb(classes[1], tmp_path)
+
+
+def test_golden_scenario_svdb_two_partitions(classes, tmp_path):
+    C.case_golden_scenario_svdb(classes[1], tmp_path, devices=[0, 1])
+
+
+def test_loads_reference_pickle(classes, tmp_path):
+    C.case_loads_reference_pickle(classes[0], tmp_path)
+
+
+def test_basics(classes, tmp_path):
+    C.case_basics(classes[0], tmp_path)
+
+
+def test_exclude_enumerates_duplicates(classes, tmp_path):
+    C.case_exclude_enumerates_duplicates(classes[0], tmp_path)
+
+
+def test_mongolike(classes, tmp_path):
+    C.case_mongolike(classes[0], tmp_path)
+    C.case_mongolike(lambda storage_file: classes[1](storage_dir=storage_file + "_d"), tmp_path)
+
+
+def test_autocut_and_rerank(classes, tmp_path):
+    C.case_autocut_and_rerank(classes[0], tmp_path)
+
+
+def test_sharded_basics(classes, tmp_path):
+    C.case_sharded_basics(classes[1], tmp_path)
+
+
+def test_sharded_basics_two_partitions(classes, tmp_path):
+    C.case_sharded_basics(classes[1], tmp_path, devices=[0, 1])
+
+
+def test_migration(classes, tmp_path):
+    C.case_migration(classes[0], classes[1], tmp_path)
+
+
+def test_multithreaded_small(classes, tmp_path):
+    C.case_multithreaded(classes[0], tmp_path, scale=0.1)
+
+
+def test_compaction_keeps_everything_consistent(classes, tmp_path, monkeypatch):
+    import numpy as np
+    import minivectordb_b200._store as store
+    monkeypatch.setattr(store.GpuStore, "COMPACT_MIN_DEAD", 8)
+    db = classes[0](storage_file=str(tmp_path / "cmp.pkl"))
+    rng = np.random.default_rng(0)
+    embs = rng.standard_normal((200, 12)).astype(np.float32)
+    db.store_embeddings_batch(list(range(200)), list(embs), [{"g": i % 4} for i in range(200)])
+    db.find_most_similar(embs[0], k=3)
+    for i in range(0, 200, 2):
+        db.delete_embedding(i)
+    ids, dist, meta = db.find_most_similar(embs[51], k=5, metadata_filter={"g": 3})
+    assert db._g_n == 100 and db._parts[0].engine.ntotal == 100   # compacted
+    assert ids[0] == 51 and all(m["g"] == 3 for m in meta)
+    assert db.id_map[0] == 1 and db.inverse_id_map[199] == 99
+    db.store_embedding("new", embs[0], {"g": 9})
+    assert db.find_most_similar(embs[0], k=1)[0] == ("new",)
+    assert len(db.find_most_similar(embs[0], k=999, metadata_filter={"g": {"$lt": 4}})[0]) == 100

@@ -1,0 +1,121 @@
+"""GPU: the drop-in classes on the real CUDA engine -- the golden scenario the
+REFERENCE's classes produced, and mirrors of the reference's own tests."""
+import numpy as np
+import pytest
+
+import dropin_cases as C
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def classes():
+    from minivectordb_b200 import VectorDatabase, ShardedVectorDatabase
+    return VectorDatabase, ShardedVectorDatabase
+
+
+def _ndev():
+    from minivectordb_b200 import _native
+    return _native.device_count()
+
+
+def test_golden_scenario_vdb(classes, tmp_path):
+    C.case_golden_scenario_vdb(classes[0], tmp_path)
+
+
+def test_golden_scenario_svdb(classes, tmp_path):
+    C.case_golden_scenario_svdb(classes[1], tmp_path)
+
+
+def test_golden_scenario_svdb_two_devices(classes, tmp_path):
+    if _ndev() < 2:
+        pytest.skip("needs 2 GPUs")
+    C.case_golden_scenario_svdb(classes[1], tmp_path, devices=[0, 1])
+
+
+def test_loads_reference_pickle(classes, tmp_path):
+    C.case_loads_reference_pickle(classes[0], tmp_path)
+
+
+def test_basics(classes, tmp_path):
+    C.case_basics(classes[0], tmp_path)
+
+
+def test_exclude_enumerates_duplicates(classes, tmp_path):
+    C.case_exclude_enumerates_duplicates(classes[0], tmp_path)
+
+
+def test_mongolike(classes, tmp_path):
+    C.case_mongolike(classes[0], tmp_path)
+    C.case_mongolike(lambda storage_file: classes[1](storage_dir=storage_file + "_d"), tmp_path)
+
+
+def test_autocut_and_rerank(classes, tmp_path):
+    C.case_autocut_and_rerank(classes[0], tmp_path)
+
+
+def test_sharded_basics(classes, tmp_path):
+    C.case_sharded_basics(classes[1], tmp_path)
+
+
+def test_migration(classes, tmp_path):
+    C.case_migration(classes[0], classes[1], tmp_path)
+
+
+def test_multithreaded_full_size(classes, tmp_path):
+    # ref tests/test_multithreaded_operations.py at its own sizes (5000 + 5x2000 inserts, 3500 deletes)
+    C.case_multithreaded(classes[0], tmp_path, scale=1.0)
+
+
+def test_sharded_multithreaded_with_large_k(classes, tmp_path):
+    """ref tests/test_sharded_multithreaded_operations.py:12-107 (d=512, k=825 search under churn), reduced rows."""
+    import threading
+    import uuid
+    db = classes[1](storage_dir=str(tmp_path / "mt"), shard_size=777)
+    d = 512
+    ids = [str(uuid.uuid4()) for _ in range(3000)]
+    db.store_embeddings_batch(ids, [np.random.rand(d) for _ in ids], [{"f": i} for i in range(3000)])
+    errors = []
+
+    def ins():
+        try:
+            for _ in range(200):
+                db.store_embedding(str(uuid.uuid4()), np.random.rand(d), {"f": -1})
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    def srch():
+        try:
+            for i in range(100):
+                out = db.find_most_similar(np.random.rand(d), k=825 if i % 10 == 0 else 5)
+                assert len(out[0]) == len(out[1]) == len(out[2])
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    def dele():
+        try:
+            for a in range(100, 300, 20):
+                db.delete_embeddings_batch(ids[a:a + 20])
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    ts = [threading.Thread(target=f) for f in (ins, ins, srch, srch, srch, dele)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errors, errors[:1]
+    assert len(db.unique_ids) == len(db.inverse_id_map) == len(db.metadata) == len(db.embeddings) == 3000 + 400 - 200
+
+
+def test_compaction_on_device(classes, tmp_path, monkeypatch):
+    import minivectordb_b200._store as store
+    monkeypatch.setattr(store.GpuStore, "COMPACT_MIN_DEAD", 8)
+    db = classes[0](storage_file=str(tmp_path / "cmp.pkl"))
+    rng = np.random.default_rng(0)
+    embs = rng.standard_normal((2000, 48)).astype(np.float32)
+    db.store_embeddings_batch(list(range(2000)), list(embs), [{"g": i % 4} for i in range(2000)])
+    before = db.find_most_similar(embs[777], k=20, metadata_filter={"g": {"$ne": 0}})
+    for i in range(0, 2000, 4):
+        db.delete_embedding(i)   # g == 0 rows
+    after = db.find_most_similar(embs[777], k=20, metadata_filter={"g": {"$ne": 0}})
+    assert db._parts[0].engine.ntotal == 1500   # physically compacted
+    assert before[0] == after[0] and np.array_equal(np.array(before[1]), np.array(after[1]))
