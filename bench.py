@@ -176,8 +176,10 @@ def run_b200(args):
     n, d, k = N_ROWS, DIM, TOPK
     peak, peak_src = measured_peak()
 
-    eng = mv.FlatIPEngine(d, device=local, capacity_hint=n)
-    eng.add_synthetic(SEED_DB, rank * n, n, dist=0, normalize=True)  # this rank's row shard
+    from minivectordb_b200.distributed import RowShardedIndex
+    index = RowShardedIndex(d, device=local)          # one row shard per rank, resident in HBM
+    index.add(synthetic=(SEED_DB, rank * n, n, 0), normalize=True)
+    eng = index.engine
     ld = eng.device_view()[1]
     adm = synth.synth_mask(SEED_META + rank, n, 0.5)
     packed = mv.pack_mask(adm)
@@ -188,26 +190,12 @@ def run_b200(args):
     q_host /= np.linalg.norm(q_host, axis=1, keepdims=True)
     q_host = np.ascontiguousarray(q_host, dtype=np.float32)
     q_dev = torch.from_numpy(q_host).cuda()
-    D_loc = torch.empty((1, k), dtype=torch.float32, device="cuda")
-    I_loc = torch.empty((1, k), dtype=torch.int64, device="cuda")
-    if world > 1:
-        D_parts = torch.empty((world, 1, k), dtype=torch.float32, device="cuda")
-        I_parts = torch.empty((world, 1, k), dtype=torch.int64, device="cuda")
-        D_out = torch.empty((1, k), dtype=torch.float32, device="cuda")
-        I_out = torch.empty((1, k), dtype=torch.int64, device="cuda")
-    ws = eng.workspace()
     stream = torch.cuda.current_stream()
-    sp = stream.cuda_stream
 
-    def step(i, q_ptr=None, m_ptr=None):
-        eng.search_device(ws, q_ptr or q_dev[i].data_ptr(), 1, k, D_loc.data_ptr(), I_loc.data_ptr(),
-                          mask_ptr=m_ptr or mask_dev.data_ptr(), mask_rows=n, label_offset=rank * n, stream=sp)
-        if world > 1:
-            # exchange step: k scores + k labels per rank over NVLink (NCCL), then merge on every rank
-            dist.all_gather_into_tensor(D_parts.view(-1), D_loc.view(-1))
-            dist.all_gather_into_tensor(I_parts.view(-1), I_loc.view(-1))
-            mv.merge_topk_device(local, D_parts.data_ptr(), I_parts.data_ptr(), world, 1, k,
-                                 D_out.data_ptr(), I_out.data_ptr(), sp)
+    def step(i, q_t=None, m_t=None):
+        # scan this rank's shard (+ for N>1: NCCL all-gather of k (score,label) pairs and merge on every rank)
+        return index.search_device(q_t if q_t is not None else q_dev[i:i + 1], k,
+                                   m_t if m_t is not None else mask_dev, n)
 
     def barrier():
         if world > 1:
@@ -244,16 +232,16 @@ def run_b200(args):
     if world > 1:
         q_pin = torch.from_numpy(q_host).pin_memory()
         m_pin = torch.from_numpy(words.view(np.int32)).pin_memory()
-        q_e2e = torch.empty(d, dtype=torch.float32, device="cuda")
+        q_e2e = torch.empty((1, d), dtype=torch.float32, device="cuda")
         m_e2e = torch.empty_like(mask_dev)
 
     def e2e_step(i):
         if world == 1:
             return eng.search(q_host[i:i + 1], k, mask=packed, mask_rows=n)
-        q_e2e.copy_(q_pin[i], non_blocking=True)
+        q_e2e.copy_(q_pin[i:i + 1], non_blocking=True)
         m_e2e.copy_(m_pin, non_blocking=True)
-        step(i, q_e2e.data_ptr(), m_e2e.data_ptr())
-        return D_out.cpu(), I_out.cpu()
+        D_t, I_t = step(i, q_e2e, m_e2e)
+        return D_t.cpu(), I_t.cpu()
 
     for i in range(W):
         e2e_step(i)
@@ -308,8 +296,7 @@ def run_b200(args):
             if not args.no_cpu_baseline:
                 line["cpu_baseline"] = cpu_baseline_sample()
         print(json.dumps(line), flush=True)
-    del ws
-    eng.close()
+    index.close()
     if world > 1:
         dist.destroy_process_group()
 

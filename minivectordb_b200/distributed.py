@@ -1,0 +1,142 @@
+"""Row-sharded search across the GPUs of one box: one process per GPU.
+
+The reference's `ShardedVectorDatabase` shards FILES, not the search (ref
+minivectordb/sharded_vector_database.py:79-84, 134-154: one in-memory index
+over all rows).  BASELINE.json's north_star maps it onto the hardware instead:
+each rank keeps a contiguous block of rows resident in its GPU's HBM, every
+query is scanned by all ranks at once (no data-path collective: rows are
+independent units), and the only exchange is k (score, label) pairs per rank
+-- an all-gather over NVLink followed by a k-way merge that every rank runs
+redundantly (so every rank holds the answer; 8 x k x 12 B at k=10 is 960 B,
+latency-bound).
+
+Labels are global row numbers: rank r adds `offset_r` (rows held by lower
+ranks) to its local row numbers inside the scan epilogue, and the merge breaks
+exact score ties by (rank, local order) = ascending global row, the same rule
+the single-GPU scan uses.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .engine import FlatIPEngine, merge_topk_device
+
+
+class RowShardedIndex:
+    def __init__(self, d: int, device: Optional[int] = None, group=None,
+                 engine_factory: Callable[..., FlatIPEngine] = None, host_merge=None):
+        """`engine_factory` / `host_merge` exist for the CPU (gloo) tests of the
+        exchange logic; the product path uses the CUDA engine and merge kernel."""
+        self.d = int(d)
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.on_gpu = engine_factory is None
+        if self.on_gpu:
+            self.device = torch.cuda.current_device() if device is None else int(device)
+            self.engine = FlatIPEngine(self.d, device=self.device)
+            self._ws = self.engine.workspace()
+            self._tdev = torch.device("cuda", self.device)
+        else:
+            self.device = -1
+            self.engine = engine_factory(self.d)
+            self._tdev = torch.device("cpu")
+        self._host_merge = host_merge
+        self.offset = 0        # global row number of this rank's row 0
+        self.ntotal_global = 0
+        self._bufs = {}
+
+    # -- ingest (collective: every rank calls it, possibly with zero rows) ---------
+    def add(self, x=None, normalize: bool = True, synthetic=None) -> None:
+        """Append this rank's block.  Ranks hold contiguous global row ranges in
+        rank order, so blocks must be added in one collective step per batch;
+        offsets are re-derived from an all-gather of the per-rank row counts."""
+        if synthetic is not None:
+            seed, row0, n, dist_kind = synthetic
+            self.engine.add_synthetic(seed, row0, n, dist_kind, normalize)
+        elif x is not None and len(x):
+            self.engine.add(np.ascontiguousarray(x, dtype=np.float32), normalize=normalize)
+        self._sync_offsets()
+
+    def _sync_offsets(self) -> None:
+        counts = torch.zeros(self.world, dtype=torch.int64, device=self._tdev)
+        mine = torch.tensor([self.engine.ntotal], dtype=torch.int64, device=self._tdev)
+        if self.world > 1:
+            dist.all_gather_into_tensor(counts, mine, group=self.group)
+        else:
+            counts.copy_(mine)
+        counts = counts.cpu().tolist()
+        self.offset = int(sum(counts[:self.rank]))
+        self.ntotal_global = int(sum(counts))
+
+    # -- search ---------------------------------------------------------------------
+    def _buffers(self, nq: int, k: int):
+        key = (nq, k)
+        if key not in self._bufs:
+            t = dict(
+                D_loc=torch.empty((nq, k), dtype=torch.float32, device=self._tdev),
+                I_loc=torch.empty((nq, k), dtype=torch.int64, device=self._tdev),
+                D_parts=torch.empty((self.world, nq, k), dtype=torch.float32, device=self._tdev),
+                I_parts=torch.empty((self.world, nq, k), dtype=torch.int64, device=self._tdev),
+                D_out=torch.empty((nq, k), dtype=torch.float32, device=self._tdev),
+                I_out=torch.empty((nq, k), dtype=torch.int64, device=self._tdev),
+            )
+            self._bufs[key] = t
+        return self._bufs[key]
+
+    def search_device(self, q_dev: torch.Tensor, k: int, mask_dev: Optional[torch.Tensor] = None,
+                      mask_rows: int = 0, normalize: bool = False):
+        """Enqueue scan -> all-gather -> merge on the current CUDA stream.
+        q_dev: float32 [nq, d] on this rank's GPU (same query on every rank).
+        Returns device tensors (D [nq,k], I [nq,k] global rows), valid after the
+        stream is synchronised."""
+        nq = q_dev.shape[0]
+        b = self._buffers(nq, k)
+        st = torch.cuda.current_stream().cuda_stream
+        self.engine.search_device(self._ws, q_dev.data_ptr(), nq, k, b["D_loc"].data_ptr(), b["I_loc"].data_ptr(),
+                                  mask_ptr=mask_dev.data_ptr() if mask_dev is not None else 0,
+                                  mask_rows=mask_rows, normalize=normalize, label_offset=self.offset, stream=st)
+        if self.world == 1:
+            return b["D_loc"], b["I_loc"]
+        dist.all_gather_into_tensor(b["D_parts"].view(-1), b["D_loc"].view(-1), group=self.group)
+        dist.all_gather_into_tensor(b["I_parts"].view(-1), b["I_loc"].view(-1), group=self.group)
+        merge_topk_device(self.device, b["D_parts"].data_ptr(), b["I_parts"].data_ptr(), self.world, nq, k,
+                          b["D_out"].data_ptr(), b["I_out"].data_ptr(), st)
+        return b["D_out"], b["I_out"]
+
+    def search(self, q, k: int, mask_local: Optional[np.ndarray] = None, normalize: bool = False):
+        """Host-array convenience: same query on every rank; `mask_local` is this
+        rank's slice (bool[n_local]) of the admissible-row mask.  Returns numpy
+        (D, I) with global row numbers, identical on every rank."""
+        q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, self.d)
+        nq = q.shape[0]
+        if self.on_gpu:
+            qd = torch.from_numpy(q).to(self._tdev)
+            md, mrows = None, 0
+            if mask_local is not None:
+                mrows = int(mask_local.shape[0])
+                packed = np.packbits(np.asarray(mask_local, dtype=bool), bitorder="little")
+                words = np.zeros((mrows + 31) // 32 * 4, dtype=np.uint8)
+                words[:packed.size] = packed
+                md = torch.from_numpy(words.view(np.int32)).to(self._tdev)
+            D, I = self.search_device(qd, k, md, mrows, normalize)
+            torch.cuda.current_stream().synchronize()
+            return D.cpu().numpy(), I.cpu().numpy()
+        # CPU test path: injected engine + injected merge, gloo collectives
+        D, I = self.engine.search(q, k, mask=mask_local, normalize=normalize)
+        I = np.where(I >= 0, I + self.offset, -1)
+        if self.world == 1:
+            return D, I
+        b = self._buffers(nq, k)
+        dist.all_gather_into_tensor(b["D_parts"].view(-1), torch.from_numpy(D).contiguous().view(-1), group=self.group)
+        dist.all_gather_into_tensor(b["I_parts"].view(-1), torch.from_numpy(I).contiguous().view(-1), group=self.group)
+        return self._host_merge(b["D_parts"].numpy(), b["I_parts"].numpy(), k)
+
+    def close(self):
+        if self.on_gpu:
+            self._ws.close()
+        self.engine.close()
