@@ -170,6 +170,31 @@ int mvdb_normalize_L2(float* x, uint64_t n, int d, int device);
 int mvdb_merge_topk_device(int device, const float* D_parts, const int64_t* I_parts, int nparts,
                            int64_t nq, int64_t k, float* D_out, int64_t* I_out, void* stream);
 
+/* ---- fused cross-GPU exchange (row-sharded search, one process per GPU) ----
+ * No reference counterpart (the reference's search is one in-memory index,
+ * sharded_vector_database.py:79-84).  Each rank creates an exchange object,
+ * publishes its 64-byte CUDA-IPC handle to the other ranks (any transport),
+ * and connects.  mvdb_index_search_exchange then runs scan + exchange + merge
+ * in ONE kernel launch per query group: the last CTA of every rank stores its
+ * k best (score,row) keys into every peer's receive buffer over NVLink,
+ * publishes a sequence number, waits for the peers' and merges.  Every rank
+ * ends with the same global (D, I); labels are offsets[rank] + local row.
+ * All ranks must issue the same sequence of calls (same nq, k).
+ * Limits: k <= k_max <= 128, world <= 16. */
+typedef struct mvdb_exchange mvdb_exchange;
+int mvdb_exchange_create(int device, int rank, int world, int k_max, int nq_max, mvdb_exchange** out);
+int mvdb_exchange_ipc_handle(mvdb_exchange* x, void* handle64);
+/* handles: world x 64 bytes in rank order (own entry ignored); offsets: world
+ * int64 global row numbers of each rank's row 0. */
+int mvdb_exchange_connect(mvdb_exchange* x, const void* handles, const int64_t* offsets);
+int mvdb_exchange_set_offsets(mvdb_exchange* x, const int64_t* offsets);
+/* *timed_out = 1 if a kernel gave up waiting for a peer (peer died). */
+int mvdb_exchange_status(mvdb_exchange* x, int* timed_out);
+int mvdb_exchange_destroy(mvdb_exchange* x);
+int mvdb_index_search_exchange(mvdb_index* ix, mvdb_workspace* ws, mvdb_exchange* x, const float* q_dev,
+                               int64_t nq, int64_t k, const uint32_t* mask_dev, uint64_t mask_rows,
+                               int normalize_queries, float* D_dev, int64_t* I_dev, void* stream);
+
 /* Number of kernel launches issued by this library since load (bench.py's
  * "gpu_launches" claim is read from here). */
 uint64_t mvdb_launch_count(void);

@@ -34,6 +34,8 @@ EXPORTS = [
     "mvdb_index_reconstruct_n", "mvdb_index_device_view", "mvdb_index_workspace_create",
     "mvdb_index_workspace_destroy", "mvdb_index_search_device", "mvdb_index_search",
     "mvdb_normalize_L2", "mvdb_merge_topk_device", "mvdb_launch_count",
+    "mvdb_exchange_create", "mvdb_exchange_ipc_handle", "mvdb_exchange_connect", "mvdb_exchange_set_offsets",
+    "mvdb_exchange_status", "mvdb_exchange_destroy", "mvdb_index_search_exchange",
 ]
 
 
@@ -123,6 +125,13 @@ def lib():
             "mvdb_normalize_L2": (i, [c_vp, u64, i, i]),
             "mvdb_merge_topk_device": (i, [i, c_vp, c_vp, i, i64, i64, c_vp, c_vp, c_vp]),
             "mvdb_launch_count": (u64, []),
+            "mvdb_exchange_create": (i, [i, i, i, i, i, ctypes.POINTER(c_vp)]),
+            "mvdb_exchange_ipc_handle": (i, [c_vp, c_vp]),
+            "mvdb_exchange_connect": (i, [c_vp, c_vp, c_vp]),
+            "mvdb_exchange_set_offsets": (i, [c_vp, c_vp]),
+            "mvdb_exchange_status": (i, [c_vp, ctypes.POINTER(i)]),
+            "mvdb_exchange_destroy": (i, [c_vp]),
+            "mvdb_index_search_exchange": (i, [c_vp, c_vp, c_vp, c_vp, i64, i64, c_vp, u64, i, c_vp, c_vp, c_vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)

@@ -313,6 +313,18 @@ struct mvdb_index {
     static constexpr int kPoolMax = 16;
 };
 
+struct mvdb_exchange {
+    int device = 0, rank = 0, world = 1, k_max = 0, nq_max = 0;
+    uint64_t* local = nullptr;      // [recv | flags], cudaMalloc (IPC-exportable)
+    size_t recv_words = 0;
+    void* peer_base[kMaxWorld] = {};
+    XchgDev host = {};
+    XchgDev* dev = nullptr;
+    unsigned int* status = nullptr;
+    uint64_t seq = 0;
+    bool connected = false;
+};
+
 struct DeviceGuard {
     int prev = -1;
     bool ok = true;
@@ -387,8 +399,12 @@ static int plan_scan(mvdb_index* ix, ScanParams& p, int nq, ScanPlan* plan) {
         off = align_up(off, 128);
         p.stage_off = uint32_t(off);
         if (!tma) {
+            // LDG variant: a tail region only for the last-CTA merge scratch
             *stages = 0;
-            return off;
+            size_t want = std::min<size_t>(size_t(ix->sm_count) * 4 * p.k * 8, 32 * 1024);
+            p.merge_off = uint32_t(off);
+            p.merge_bytes = uint32_t(want);
+            return off + want;
         }
         if (off + 2 * size_t(p.stage_bytes) > ix->smem_optin) {
             *stages = 0;
@@ -434,6 +450,8 @@ static int plan_scan(mvdb_index* ix, ScanParams& p, int nq, ScanPlan* plan) {
             int s_raw = 0;
             layout(ncw_tma, true, &s_raw);  // re-derive the offsets for the chosen ncw
             smem = size_t(p.stage_off) + size_t(stages) * p.stage_bytes;
+            p.merge_off = p.stage_off;     // the ring is idle once every tile is consumed
+            p.merge_bytes = uint32_t(size_t(stages) * p.stage_bytes);
         }
     }
     if (tma) {
@@ -495,12 +513,32 @@ static int ws_scratch(mvdb_workspace* ws) {
 // Core search on device buffers.  Caller holds move_mu shared.
 static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, int64_t nq, int64_t k,
                       const uint32_t* mask_dev, uint64_t mask_rows, int normalize_q, int64_t label_offset,
-                      float* D_dev, int64_t* I_dev, cudaStream_t stream) {
+                      float* D_dev, int64_t* I_dev, cudaStream_t stream, mvdb_exchange* xch = nullptr) {
     if (nq <= 0) return MVDB_OK;
+    if (xch) {
+        if (!xch->connected) return fail(MVDB_ERR_STATE, "exchange is not connected");
+        if (k > ix->fused_k_max || k > xch->k_max)
+            return fail(MVDB_ERR_ARG, "fused exchange supports k <= %d", std::min(ix->fused_k_max, xch->k_max));
+    }
     uint64_t n64 = ix->ntotal.load(std::memory_order_acquire);
     if (mask_dev) n64 = std::min<uint64_t>(n64, mask_rows);
     if (n64 > 0xFFFFFFF0ull) return fail(MVDB_ERR_ARG, "more than 2^32 rows per index are not supported");
     const uint32_t n = uint32_t(n64);
+    if (n == 0 && xch) {
+        // empty shard: still take part in every exchange round
+        int64_t done = 0;
+        while (done < nq) {
+            int64_t rem = nq - done;
+            int g = rem >= 8 ? 8 : rem >= 4 ? 4 : rem >= 2 ? 2 : 1;
+            g = std::min(g, xch->nq_max);
+            xchg_empty_kernel<<<1, 128, size_t(4) * select_cap(int(k)) * 8, stream>>>(xch->dev, ++xch->seq, g, int(k),
+                                                                                      D_dev + done * k, I_dev + done * k);
+            LAUNCHED();
+            done += g;
+        }
+        CU_OK(cudaGetLastError());
+        return MVDB_OK;
+    }
     if (n == 0) {
         int64_t total = nq * k;
         fill_empty_results_kernel<<<unsigned((total + 255) / 256), 256, 0, stream>>>(D_dev, I_dev, total);
@@ -526,6 +564,11 @@ static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, in
         while (done < nq) {
             int64_t rem = nq - done;
             int g = rem >= 8 ? 8 : rem >= 4 ? 4 : rem >= 2 ? 2 : 1;
+            if (xch) {
+                while (g > xch->nq_max) g >>= 1;
+                p.xchg = xch->dev;
+                p.xchg_seq = ++xch->seq;
+            }
             ScanPlan plan;
             RC_OK(plan_scan(ix, p, g, &plan));
             RC_OK(grow_dev(&ws->partials, &ws->partials_cap, size_t(g) * plan.grid * p.k));
@@ -1045,6 +1088,121 @@ int mvdb_index_search(mvdb_index* ix, const float* q, int64_t nq, int64_t k, con
     memcpy(D, ws->D_pin, on * 4);
     memcpy(I, ws->I_pin, on * 8);
     return MVDB_OK;
+}
+
+int mvdb_exchange_create(int device, int rank, int world, int k_max, int nq_max, mvdb_exchange** out) {
+    if (!out) return fail(MVDB_ERR_ARG, "null out");
+    *out = nullptr;
+    if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world) return fail(MVDB_ERR_ARG, "bad rank/world %d/%d", rank, world);
+    if (k_max < 1 || k_max > 128 || nq_max < 1 || nq_max > 8) return fail(MVDB_ERR_ARG, "need 1 <= k_max <= 128, 1 <= nq_max <= 8");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(MVDB_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    mvdb_exchange* x = new mvdb_exchange();
+    x->device = device;
+    x->rank = rank;
+    x->world = world;
+    x->k_max = k_max;
+    x->nq_max = nq_max;
+    x->recv_words = size_t(2) * world * nq_max * k_max;
+    const size_t words = x->recv_words + size_t(2) * world;
+    cudaError_t e = cudaMalloc(&x->local, words * 8);
+    if (e == cudaSuccess) e = cudaMemset(x->local, 0, words * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&x->dev, sizeof(XchgDev));
+    if (e == cudaSuccess) e = cudaMalloc(&x->status, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(x->status, 0, sizeof(unsigned int));
+    if (e != cudaSuccess) {
+        cudaFree(x->local);
+        cudaFree(x->dev);
+        cudaFree(x->status);
+        delete x;
+        return fail(MVDB_ERR_CUDA, "exchange allocation failed: %s", cudaGetErrorString(e));
+    }
+    *out = x;
+    return MVDB_OK;
+}
+
+int mvdb_exchange_ipc_handle(mvdb_exchange* x, void* handle64) {
+    if (!x || !handle64) return fail(MVDB_ERR_ARG, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DeviceGuard guard(x->device);
+    cudaIpcMemHandle_t h;
+    CU_OK(cudaIpcGetMemHandle(&h, x->local));
+    memcpy(handle64, &h, 64);
+    return MVDB_OK;
+}
+
+static int exchange_upload(mvdb_exchange* x) {
+    CU_OK(cudaMemcpy(x->dev, &x->host, sizeof(XchgDev), cudaMemcpyHostToDevice));
+    return MVDB_OK;
+}
+
+int mvdb_exchange_connect(mvdb_exchange* x, const void* handles, const int64_t* offsets) {
+    if (!x || !handles || !offsets) return fail(MVDB_ERR_ARG, "null argument");
+    DeviceGuard guard(x->device);
+    if (!guard.ok) return fail(MVDB_ERR_CUDA, "cudaSetDevice(%d) failed", x->device);
+    for (int p = 0; p < x->world; p++) {
+        void* base = x->local;
+        if (p != x->rank) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, static_cast<const char*>(handles) + size_t(p) * 64, 64);
+            CU_OK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+            x->peer_base[p] = base;
+        }
+        x->host.recv[p] = static_cast<uint64_t*>(base);
+        x->host.flags[p] = static_cast<uint64_t*>(base) + x->recv_words;
+        x->host.offsets[p] = offsets[p];
+    }
+    x->host.world = x->world;
+    x->host.rank = x->rank;
+    x->host.k_max = x->k_max;
+    x->host.nq_max = x->nq_max;
+    x->host.status = x->status;
+    RC_OK(exchange_upload(x));
+    x->connected = true;
+    return MVDB_OK;
+}
+
+int mvdb_exchange_set_offsets(mvdb_exchange* x, const int64_t* offsets) {
+    if (!x || !offsets) return fail(MVDB_ERR_ARG, "null argument");
+    DeviceGuard guard(x->device);
+    CU_OK(cudaDeviceSynchronize());
+    for (int p = 0; p < x->world; p++) x->host.offsets[p] = offsets[p];
+    return exchange_upload(x);
+}
+
+int mvdb_exchange_status(mvdb_exchange* x, int* timed_out) {
+    if (!x || !timed_out) return fail(MVDB_ERR_ARG, "null argument");
+    DeviceGuard guard(x->device);
+    unsigned int v = 0;
+    CU_OK(cudaMemcpy(&v, x->status, sizeof v, cudaMemcpyDeviceToHost));
+    *timed_out = int(v);
+    return MVDB_OK;
+}
+
+int mvdb_exchange_destroy(mvdb_exchange* x) {
+    if (!x) return MVDB_OK;
+    DeviceGuard guard(x->device);
+    cudaDeviceSynchronize();
+    for (int p = 0; p < x->world; p++)
+        if (x->peer_base[p]) cudaIpcCloseMemHandle(x->peer_base[p]);
+    cudaFree(x->local);
+    cudaFree(x->dev);
+    cudaFree(x->status);
+    delete x;
+    return MVDB_OK;
+}
+
+int mvdb_index_search_exchange(mvdb_index* ix, mvdb_workspace* ws, mvdb_exchange* x, const float* q_dev, int64_t nq,
+                               int64_t k, const uint32_t* mask_dev, uint64_t mask_rows, int normalize_queries,
+                               float* D_dev, int64_t* I_dev, void* stream) {
+    ENTER(ix);
+    if (!ws || ws->ix != ix) return fail(MVDB_ERR_ARG, "workspace does not belong to this index");
+    if (!x || x->device != ix->device) return fail(MVDB_ERR_ARG, "exchange does not belong to this device");
+    if (nq < 0 || k <= 0) return fail(MVDB_ERR_ARG, "need nq >= 0 and k > 0 (got nq=%lld k=%lld)", (long long)nq, (long long)k);
+    if (nq && (!q_dev || !D_dev || !I_dev)) return fail(MVDB_ERR_ARG, "null buffer");
+    std::shared_lock<std::shared_mutex> mv(ix->move_mu);
+    return run_search(ix, ws, q_dev, nq, k, mask_dev, mask_rows, normalize_queries, 0, D_dev, I_dev,
+                      static_cast<cudaStream_t>(stream), x);
 }
 
 int mvdb_normalize_L2(float* x, uint64_t n, int d, int device) {

@@ -50,7 +50,113 @@ struct ScanParams {
     int stages;            // TMA ring depth
     uint32_t stage_bytes;  // 8 * ld * 4 rounded to 128
     uint32_t sel_off, q_off, stage_off;  // byte offsets into dynamic shared memory
+    uint32_t merge_off, merge_bytes;     // scratch for the last-CTA merge (the idle TMA ring, or a tail region)
+    const struct XchgDev* xchg;  // fused cross-GPU exchange (nullptr = single GPU)
+    uint64_t xchg_seq;           // sequence number of this launch (same on every rank, > 0)
 };
+
+// ---------------------------------------------------------------------------
+// Fused cross-GPU exchange (sharded search).  Every rank owns a receive buffer
+// that all peers can write over NVLink (peer-mapped through CUDA IPC):
+//   recv [2 parities][world][nq_max * k_max] keys,  flags [2][world] sequence numbers.
+// The last CTA of rank r stores its final per-query lists into slot r of EVERY
+// rank's buffer (plain st.global on peer pointers), fences system-wide, then
+// publishes the launch's sequence number in every rank's flag r.  It then waits
+// until all world flags of its own buffer carry that number and merges the
+// world x k candidates -- scan, exchange and merge in ONE launch, no NCCL call.
+// Parity double-buffering suffices: a rank can finish query s only after every
+// rank has sent s, so nobody can be two queries ahead of a reader.
+// ---------------------------------------------------------------------------
+constexpr int kMaxWorld = 16;
+struct XchgDev {
+    uint64_t* recv[kMaxWorld];    // recv[p]  = rank p's receive buffer (peer-mapped)
+    uint64_t* flags[kMaxWorld];   // flags[p] = rank p's flag array (peer-mapped)
+    int64_t offsets[kMaxWorld];   // global row number of rank p's row 0
+    int world, rank, k_max, nq_max;
+    unsigned int* status;         // local: set to 1 if a wait timed out
+};
+
+__device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// send query qi's final list (keys[0..cnt), best first) to slot `rank` of every rank
+__device__ __forceinline__ void xchg_send(const XchgDev* x, uint64_t seq, int qi, const uint64_t* keys,
+                                          int cnt, int k, int lane) {
+    const size_t slot = (size_t(seq & 1) * x->world + x->rank) * size_t(x->nq_max) * x->k_max +
+                        size_t(qi) * x->k_max;
+    for (int i = lane; i < k; i += kWarp) {
+        const uint64_t key = (i < cnt) ? keys[i] : kEmptyKey;
+        for (int p = 0; p < x->world; p++) x->recv[p][slot + i] = key;
+    }
+    __threadfence_system();
+}
+
+// merge the world lists of query qi that peers deposited in MY buffer
+__device__ __forceinline__ void xchg_merge(const XchgDev* x, uint64_t seq, int qi, uint64_t* buf, int cap,
+                                           int k, float* D, int64_t* I, int lane) {
+    const uint64_t* mine = x->recv[x->rank] + size_t(seq & 1) * x->world * size_t(x->nq_max) * x->k_max +
+                           size_t(qi) * x->k_max;
+    const size_t src_stride = size_t(x->nq_max) * x->k_max;
+    WarpSelect f;
+    f.init(buf, cap, k);
+    const int total = x->world * k;
+    // candidate position pos = src * k + i encodes the tie order (rank, then in-list order
+    // = ascending global row for contiguous row shards)
+    for (int base = 0; base < total; base += kWarp) {
+        int pos = base + lane;
+        uint64_t key = kEmptyKey;
+        if (pos < total) {
+            uint64_t orig = __ldcg(mine + size_t(pos / k) * src_stride + (pos % k));
+            if (orig != kEmptyKey) key = (orig & 0xFFFFFFFF00000000ull) | uint64_t(0xFFFFFFFFu - uint32_t(pos));
+        }
+        f.push(pos < total, key, lane);
+    }
+    f.compact(lane);
+    __syncwarp();
+    for (int i = lane; i < k; i += kWarp) {
+        uint64_t key = (i < f.cnt) ? f.buf[i] : kEmptyKey;
+        if (key == kEmptyKey) {
+            D[i] = -FLT_MAX;
+            I[i] = -1;
+        } else {
+            int pos = int(key_row(key));
+            int src = pos / k;
+            uint64_t orig = __ldcg(mine + size_t(src) * src_stride + (pos % k));
+            D[i] = key_score(orig);
+            I[i] = int64_t(key_row(orig)) + x->offsets[src];
+        }
+    }
+}
+
+// flags: publish `seq` to every rank, then wait for every rank's `seq` in my own flags.
+// Called by one warp.  Gives up after ~10 s (a peer died) and raises x->status.
+__device__ __forceinline__ void xchg_publish_and_wait(const XchgDev* x, uint64_t seq, int lane) {
+    const int par = int(seq & 1);
+    if (lane < x->world) st_release_sys(x->flags[lane] + par * x->world + x->rank, seq);
+    if (lane < x->world) {
+        const uint64_t* f = x->flags[x->rank] + par * x->world + lane;
+        const uint64_t t0 = global_timer_ns();
+        while (ld_acquire_sys(f) < seq) {
+            __nanosleep(200);
+            if (global_timer_ns() - t0 > 10000000000ull) {
+                *x->status = 1u;
+                break;
+            }
+        }
+    }
+    __syncwarp();
+}
 
 // shared-memory header (first 1024 bytes)
 struct SmemHeader {
@@ -98,8 +204,9 @@ __device__ __forceinline__ WarpSelect merge_cta_lists(SmemHeader* hdr, uint64_t*
 // Called by all consumer warps once their tiles are done.  `sel_cnt[qi]` must
 // already be compacted lists in selbuf[(cw*nq+qi)*cap ..].
 // bar_id/bar_threads: named barrier covering exactly the consumer warps.
-__device__ __forceinline__ void finish_scan(const ScanParams& p, SmemHeader* hdr, uint64_t* selbuf,
-                                            int cw, int ncw, int lane, int bar_id, int bar_threads) {
+__device__ __forceinline__ void finish_scan(const ScanParams& p, uint8_t* smem_base, SmemHeader* hdr,
+                                            uint64_t* selbuf, int cw, int ncw, int lane, int bar_id,
+                                            int bar_threads) {
     const int nq = p.nq, k = p.k, cap = p.cap;
     const int G = gridDim.x;
     named_bar_sync(bar_id, bar_threads);
@@ -124,15 +231,26 @@ __device__ __forceinline__ void finish_scan(const ScanParams& p, SmemHeader* hdr
     // after the first few columns and a column in which no list beats it ends
     // the merge -- deeper entries are smaller still.  Warp cw takes lists
     // cw, cw+ncw, ...; one lane per list.
+    // The G*k keys of a query are first pulled into shared memory with one
+    // coalesced sweep (one L2 round trip instead of one per column).
+    uint64_t* mbuf = reinterpret_cast<uint64_t*>(smem_base + p.merge_off);
+    const bool staged = size_t(G) * k * 8 <= p.merge_bytes;
     for (int qi = 0; qi < nq; qi++) {
         WarpSelect f;
         f.init(selbuf + size_t(cw * nq + qi) * cap, cap, k);
         const uint64_t* src = p.partials + size_t(qi) * G * k;
+        if (staged) {
+            if (qi) named_bar_sync(bar_id, bar_threads);
+            for (int i = cw * kWarp + lane; i < G * k; i += bar_threads) mbuf[i] = __ldcg(src + i);
+            named_bar_sync(bar_id, bar_threads);
+            src = mbuf;
+        }
         for (int col = 0; col < k; col++) {
             bool any = false;
             for (int base = cw; base < G; base += ncw * kWarp) {
                 int c = base + lane * ncw;
-                uint64_t key = (c < G) ? __ldcg(src + size_t(c) * k + col) : kEmptyKey;
+                uint64_t key = kEmptyKey;
+                if (c < G) key = staged ? src[size_t(c) * k + col] : __ldcg(src + size_t(c) * k + col);
                 any |= f.push(c < G, key, lane);
             }
             if (!any) break;
@@ -144,10 +262,33 @@ __device__ __forceinline__ void finish_scan(const ScanParams& p, SmemHeader* hdr
     for (int qi = cw; qi < nq; qi += ncw) {
         WarpSelect m = merge_cta_lists(hdr, selbuf, nq, qi, cw, ncw, cap, k, lane);
         __syncwarp();
-        write_results(m.buf, m.cnt, k, p.outD + size_t(qi) * k, p.outI + size_t(qi) * k,
-                      p.label_offset, lane);
+        if (p.xchg) xchg_send(p.xchg, p.xchg_seq, qi, m.buf, m.cnt, k, lane);
+        else write_results(m.buf, m.cnt, k, p.outD + size_t(qi) * k, p.outI + size_t(qi) * k, p.label_offset, lane);
     }
     if (cw == 0 && lane == 0) *p.ticket = 0u;  // ready for the next launch on this workspace
+    if (!p.xchg) return;
+    // ---- fused exchange: all lists are on their way to every rank -----------
+    named_bar_sync(bar_id, bar_threads);
+    if (cw == 0) xchg_publish_and_wait(p.xchg, p.xchg_seq, lane);
+    named_bar_sync(bar_id, bar_threads);
+    for (int qi = cw; qi < nq; qi += ncw)
+        xchg_merge(p.xchg, p.xchg_seq, qi, selbuf + size_t(cw * nq + qi) * cap, cap, k, p.outD + size_t(qi) * k,
+                   p.outI + size_t(qi) * k, lane);
+}
+
+// Stand-alone exchange for a rank whose shard is empty (it still has to take part).
+__global__ void __launch_bounds__(128) xchg_empty_kernel(const XchgDev* x, uint64_t seq, int nq, int k, float* D,
+                                                         int64_t* I) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint64_t* buf = reinterpret_cast<uint64_t*>(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int cap = select_cap(k);
+    for (int qi = warp; qi < nq; qi += nw) xchg_send(x, seq, qi, nullptr, 0, k, lane);
+    __syncthreads();
+    if (warp == 0) xchg_publish_and_wait(x, seq, lane);
+    __syncthreads();
+    for (int qi = warp; qi < nq; qi += nw)
+        xchg_merge(x, seq, qi, buf + size_t(warp) * cap, cap, k, D + size_t(qi) * k, I + size_t(qi) * k, lane);
 }
 
 // Load (and optionally L2-normalise) this lane's float4 chunks of one query.
@@ -305,7 +446,7 @@ __global__ void __launch_bounds__(kTma ? 288 : 256, kTma ? 1 : 2) scan_q1_kernel
     if (p.all_ord) return;
     sel.compact(lane);
     if (lane == 0) hdr->cnts[cw] = sel.cnt;
-    finish_scan(p, hdr, selbuf, cw, ncw, lane, 1, ncw * 32);
+    finish_scan(p, smem, hdr, selbuf, cw, ncw, lane, 1, ncw * 32);
 }
 
 // ---------------------------------------------------------------------------
@@ -456,7 +597,7 @@ __global__ void __launch_bounds__(kTma ? 288 : 256, (kTma || NQ >= 8) ? 1 : 2) s
         sel[qi].compact(lane);
         if (lane == 0) hdr->cnts[cw * NQ + qi] = sel[qi].cnt;
     }
-    finish_scan(p, hdr, selbuf, cw, ncw, lane, 1, ncw * 32);
+    finish_scan(p, smem, hdr, selbuf, cw, ncw, lane, 1, ncw * 32);
 }
 
 }  // namespace mvdb

@@ -10,6 +10,14 @@ independent units), and the only exchange is k (score, label) pairs per rank
 redundantly (so every rank holds the answer; 8 x k x 12 B at k=10 is 960 B,
 latency-bound).
 
+Two exchange transports:
+* "fused" (default when CUDA IPC works): the scan kernel's last CTA stores the
+  rank's k best keys straight into every peer's receive buffer over NVLink
+  (peer-mapped memory), publishes a sequence flag, waits for the peers' flags
+  and merges -- scan + exchange + merge in ONE kernel launch, no NCCL call on
+  the query path (csrc/scan.cuh, xchg_*).
+* "nccl": scan kernel, two ncclAllGather (scores, labels), merge kernel.
+
 Labels are global row numbers: rank r adds `offset_r` (rows held by lower
 ranks) to its local row numbers inside the scan epilogue, and the merge breaks
 exact score ties by (rank, local order) = ascending global row, the same rule
@@ -23,12 +31,18 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+import ctypes
+
+from . import _native as N
 from .engine import FlatIPEngine, merge_topk_device
 
 
 class RowShardedIndex:
+    FUSED_K_MAX = 128
+    FUSED_NQ_MAX = 8
+
     def __init__(self, d: int, device: Optional[int] = None, group=None,
-                 engine_factory: Callable[..., FlatIPEngine] = None, host_merge=None):
+                 engine_factory: Callable[..., FlatIPEngine] = None, host_merge=None, exchange: str = "auto"):
         """`engine_factory` / `host_merge` exist for the CPU (gloo) tests of the
         exchange logic; the product path uses the CUDA engine and merge kernel."""
         self.d = int(d)
@@ -47,8 +61,46 @@ class RowShardedIndex:
             self._tdev = torch.device("cpu")
         self._host_merge = host_merge
         self.offset = 0        # global row number of this rank's row 0
+        self.offsets = [0] * self.world
         self.ntotal_global = 0
         self._bufs = {}
+        self._xchg = None
+        self.exchange = "none" if self.world == 1 else "nccl"
+        if self.on_gpu and self.world > 1 and exchange in ("auto", "fused"):
+            self._setup_fused(required=(exchange == "fused"))
+
+    def _setup_fused(self, required: bool) -> None:
+        """Create the peer-mapped exchange buffers and swap CUDA-IPC handles."""
+        L = N.lib()
+        h = ctypes.c_void_p()
+        ok, handle = 1, bytes(64)
+        try:
+            N.check(L.mvdb_exchange_create(self.device, self.rank, self.world, self.FUSED_K_MAX, self.FUSED_NQ_MAX,
+                                           ctypes.byref(h)))
+            buf = ctypes.create_string_buffer(64)
+            N.check(L.mvdb_exchange_ipc_handle(h, buf))
+            handle = buf.raw
+        except N.MvdbError:
+            ok = 0
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, (ok, handle), group=self.group)
+        if all(g[0] for g in gathered):
+            blob = b"".join(g[1] for g in gathered)
+            offs = (ctypes.c_int64 * self.world)(*self.offsets)
+            try:
+                N.check(L.mvdb_exchange_connect(h, blob, offs))
+            except N.MvdbError:
+                ok = 0
+        flags = [None] * self.world
+        dist.all_gather_object(flags, ok, group=self.group)
+        if all(flags):
+            self._xchg = h
+            self.exchange = "fused"
+        else:
+            if h.value:
+                L.mvdb_exchange_destroy(h)
+            if required:
+                raise RuntimeError("fused exchange unavailable (CUDA IPC / peer access failed on some rank)")
 
     # -- ingest (collective: every rank calls it, possibly with zero rows) ---------
     def add(self, x=None, normalize: bool = True, synthetic=None) -> None:
@@ -70,8 +122,12 @@ class RowShardedIndex:
         else:
             counts.copy_(mine)
         counts = counts.cpu().tolist()
-        self.offset = int(sum(counts[:self.rank]))
+        self.offsets = [int(sum(counts[:r])) for r in range(self.world)]
+        self.offset = self.offsets[self.rank]
         self.ntotal_global = int(sum(counts))
+        if self._xchg is not None:
+            offs = (ctypes.c_int64 * self.world)(*self.offsets)
+            N.check(N.lib().mvdb_exchange_set_offsets(self._xchg, offs))
 
     # -- search ---------------------------------------------------------------------
     def _buffers(self, nq: int, k: int):
@@ -97,6 +153,13 @@ class RowShardedIndex:
         nq = q_dev.shape[0]
         b = self._buffers(nq, k)
         st = torch.cuda.current_stream().cuda_stream
+        if self._xchg is not None and k <= self.FUSED_K_MAX:
+            N.check(N.lib().mvdb_index_search_exchange(
+                self.engine.handle, self._ws._h, self._xchg, ctypes.c_void_p(q_dev.data_ptr()), nq, int(k),
+                ctypes.c_void_p(mask_dev.data_ptr()) if mask_dev is not None else None, int(mask_rows),
+                int(bool(normalize)), ctypes.c_void_p(b["D_out"].data_ptr()), ctypes.c_void_p(b["I_out"].data_ptr()),
+                ctypes.c_void_p(st) if st else None))
+            return b["D_out"], b["I_out"]
         self.engine.search_device(self._ws, q_dev.data_ptr(), nq, k, b["D_loc"].data_ptr(), b["I_loc"].data_ptr(),
                                   mask_ptr=mask_dev.data_ptr() if mask_dev is not None else 0,
                                   mask_rows=mask_rows, normalize=normalize, label_offset=self.offset, stream=st)
@@ -136,7 +199,20 @@ class RowShardedIndex:
         dist.all_gather_into_tensor(b["I_parts"].view(-1), torch.from_numpy(I).contiguous().view(-1), group=self.group)
         return self._host_merge(b["D_parts"].numpy(), b["I_parts"].numpy(), k)
 
+    def exchange_timed_out(self) -> bool:
+        if self._xchg is None:
+            return False
+        v = ctypes.c_int(0)
+        N.check(N.lib().mvdb_exchange_status(self._xchg, ctypes.byref(v)))
+        return bool(v.value)
+
     def close(self):
+        if self._xchg is not None:
+            torch.cuda.synchronize()
+            if self.world > 1:
+                dist.barrier(group=self.group)  # nobody unmaps while a peer may still write
+            N.lib().mvdb_exchange_destroy(self._xchg)
+            self._xchg = None
         if self.on_gpu:
             self._ws.close()
         self.engine.close()

@@ -51,8 +51,30 @@ def time_search(eng, ws, nq, k, mask_ptr, mask_rows, iters=20, flush_l2=False):
 
 
 configs = [(1_000_000, 384), (100_000, 512), (2_000_000, 512), (1_000_000, 768), (1_000_000, 1024)]
-if len(sys.argv) > 1 and sys.argv[1] == "quick":
+mode = sys.argv[1] if len(sys.argv) > 1 else "full"
+if mode == "quick":
     configs = configs[:2]
+if mode == "latency":
+    # fixed-cost anatomy: 1 tile per CTA, 10 tiles per CTA, config 1 (100k x 512), cold (L2 flushed) and warm
+    for n, d in [(1184, 512), (11840, 512), (100_000, 512), (100_000, 384)]:
+        eng = mv.FlatIPEngine(d)
+        eng.add_synthetic(1234, 0, n, 0, True)
+        ws = eng.workspace()
+        nbytes = n * eng.device_view()[1] * 4
+        for variant in (1, 2):
+            eng.set_option("scan_variant", variant)
+            for k in (10, 100):
+                for cold in (True, False):
+                    med, best = time_search(eng, ws, 1, k, 0, n, iters=30, flush_l2=cold)
+                    rec = dict(mode="latency", n=n, d=d, variant=variant, k=k, cold=cold, med_us=med * 1e6,
+                               best_us=best * 1e6, gbs=nbytes / med / 1e9)
+                    out.append(rec)
+                    print(json.dumps(rec), flush=True)
+        del ws
+        eng.close()
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(out, open("gpurun_out/probe_latency.json", "w"), indent=1)
+    sys.exit(0)
 for n, d in configs:
     eng = mv.FlatIPEngine(d)
     t0 = time.time()
