@@ -271,14 +271,14 @@ def run_b200(args):
                        "filter_keep": float(adm.mean()), "l2": "matrix 1.5 GB >> 126 MB L2 (no flush needed)",
                        "unit_note": "value = shard scans/s over all ranks = n_gpus x global QPS "
                                     "(each rank scans its own 1M x 384 shard per query)",
-                       "parallelism": f"row-shard x{world}" + (", nccl allgather + merge" if world > 1 else "")},
+                       "parallelism": f"row-shard x{world}" + (f", exchange={index.exchange}" if world > 1 else "")},
             "qps_global": qps_global,
             "p50_latency_us": float(np.median(per_step) * 1e6),
             "e2e": {"value": K / e2e_total * world, "unit": "queries/s", "h2d_bytes_per_step": d * 4 + (n + 7) // 8,
                     "d2h_bytes_per_step": k * 12, "p50_latency_us": float(np.median(e2e_lat) * 1e6),
                     "qps_global": K / e2e_total,
                     "api": ("mvdb_index_search (C ABI, host buffers; H2D query+mask, D2H results inside)" if world == 1 else
-                            "pinned H2D query+mask -> mvdb_index_search_device -> nccl allgather -> merge -> D2H")},
+                            "pinned H2D query+mask -> RowShardedIndex.search_device (scan + exchange + merge) -> D2H")},
             "gpu_launches": int(launches),
             "clocks": clk,
         }

@@ -26,28 +26,40 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
 
 def time_search(eng, ws, nq, k, mask_ptr, mask_rows, iters=20, flush_l2=False):
+    """Per-launch device time with the launches enqueued BACK TO BACK (the host
+    enqueue cost of python+ctypes, ~15-25 us, would otherwise sit between the two
+    events of a single launch).  Cold numbers: (flush + search) pairs minus the
+    flush alone, both back to back."""
     d = eng.d
     q = torch.randn(nq, d, device="cuda")
     q = q / q.norm(dim=1, keepdim=True)
     D = torch.empty(nq, k, device="cuda")
     I = torch.empty(nq, k, dtype=torch.int64, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
-    for _ in range(5):
-        eng.search_device(ws, q.data_ptr(), nq, k, D.data_ptr(), I.data_ptr(), mask_ptr, mask_rows, stream=st)
-    torch.cuda.synchronize()
-    ts = []
-    for _ in range(iters):
-        if flush_l2:
-            flush.fill_(1)
+
+    def run(n_it, with_search, with_flush):
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
         e0.record()
-        eng.search_device(ws, q.data_ptr(), nq, k, D.data_ptr(), I.data_ptr(), mask_ptr, mask_rows, stream=st)
+        for _ in range(n_it):
+            if with_flush:
+                flush.fill_(1)
+            if with_search:
+                eng.search_device(ws, q.data_ptr(), nq, k, D.data_ptr(), I.data_ptr(), mask_ptr, mask_rows, stream=st)
         e1.record()
         torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1) * 1e-3)
-    ts.sort()
-    return ts[len(ts) // 2], ts[0]
+        return e0.elapsed_time(e1) * 1e-3 / n_it
+
+    run(5, True, False)
+    reps = []
+    for _ in range(5):
+        if flush_l2:
+            reps.append(run(iters, True, True) - run(iters, False, True))
+        else:
+            reps.append(run(iters, True, False))
+    reps.sort()
+    return reps[len(reps) // 2], reps[0]
 
 
 configs = [(1_000_000, 384), (100_000, 512), (2_000_000, 512), (1_000_000, 768), (1_000_000, 1024)]
