@@ -76,7 +76,12 @@ int mvdb_index_reset(mvdb_index* ix);
 /* Tunables; unknown names -> MVDB_ERR_ARG.
  *   "scan_variant"  MVDB_SCAN_*          "fused_k_max"  largest k served by the fused select
  *   "grid_ctas"     CTAs of the scan kernel (0 = one per SM)
- *   "consumer_warps" consumer warps per CTA of the TMA scan (0 = auto) */
+ *   "consumer_warps" consumer warps per CTA of the TMA scan (0 = auto)
+ *   "batch_mode"    large query batches on the tensor cores: 0 off (always the
+ *                   fp32 scan), 1 exact (bf16 tcgen05 GEMM selects a rigorous
+ *                   candidate superset, survivors re-scored in fp32: same ids and
+ *                   distances as the scan; default), 2 bf16 (scores of the bf16 GEMM)
+ *   "batch_min_nq"  smallest nq routed to the batched path (default 32; k <= 128) */
 int mvdb_index_set_option(mvdb_index* ix, const char* name, int64_t value);
 
 /* ---- ingest -------------------------------------------------------------
@@ -194,6 +199,11 @@ int mvdb_exchange_destroy(mvdb_exchange* x);
 int mvdb_index_search_exchange(mvdb_index* ix, mvdb_workspace* ws, mvdb_exchange* x, const float* q_dev,
                                int64_t nq, int64_t k, const uint32_t* mask_dev, uint64_t mask_rows,
                                int normalize_queries, float* D_dev, int64_t* I_dev, void* stream);
+
+/* Test hook: the raw bf16 tensor-core scores of q[nq,d] against every stored row
+ * (out[nq][ntotal], host).  Exists so that the tcgen05 GEMM can be validated
+ * against an independent bf16 matmul; not used by the product path. */
+int mvdb_debug_gemm_scores(mvdb_index* ix, const float* q, int64_t nq, float* out);
 
 /* Number of kernel launches issued by this library since load (bench.py's
  * "gpu_launches" claim is read from here). */

@@ -35,7 +35,7 @@ EXPORTS = [
     "mvdb_index_workspace_destroy", "mvdb_index_search_device", "mvdb_index_search",
     "mvdb_normalize_L2", "mvdb_merge_topk_device", "mvdb_launch_count",
     "mvdb_exchange_create", "mvdb_exchange_ipc_handle", "mvdb_exchange_connect", "mvdb_exchange_set_offsets",
-    "mvdb_exchange_status", "mvdb_exchange_destroy", "mvdb_index_search_exchange",
+    "mvdb_exchange_status", "mvdb_exchange_destroy", "mvdb_index_search_exchange", "mvdb_debug_gemm_scores",
 ]
 
 
@@ -131,6 +131,7 @@ def lib():
             "mvdb_exchange_set_offsets": (i, [c_vp, c_vp]),
             "mvdb_exchange_status": (i, [c_vp, ctypes.POINTER(i)]),
             "mvdb_exchange_destroy": (i, [c_vp]),
+            "mvdb_debug_gemm_scores": (i, [c_vp, c_vp, i64, c_vp]),
             "mvdb_index_search_exchange": (i, [c_vp, c_vp, c_vp, c_vp, i64, i64, c_vp, u64, i, c_vp, c_vp, c_vp]),
         }
         for name, (res, args) in sig.items():

@@ -15,7 +15,8 @@ namespace mvdb {
 template <bool kSynth>
 __global__ void __launch_bounds__(256) append_rows_kernel(const float* __restrict__ src, float* __restrict__ dst,
                                                           uint64_t n, int d, int64_t ld, int normalize,
-                                                          uint64_t seed, uint64_t synth_row0, int dist) {
+                                                          uint64_t seed, uint64_t synth_row0, int dist,
+                                                          int* max_norm2_bits) {
     const int lane = threadIdx.x & 31;
     const uint64_t warp = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
@@ -29,13 +30,14 @@ __global__ void __launch_bounds__(256) append_rows_kernel(const float* __restric
         }
         float inv = 1.f;
         bool scale = false;
-        if (normalize) {
-            nr = warp_allsum(nr);
-            if (nr > 0.f) {
-                inv = renorm_scale(nr);
-                scale = true;
-            }
+        nr = warp_allsum(nr);
+        if (normalize && nr > 0.f) {
+            inv = renorm_scale(nr);
+            scale = true;
         }
+        // largest squared norm of any stored row (error bound of the bf16 batched path);
+        // non-negative floats order like their bit patterns
+        if (lane == 0) atomicMax(max_norm2_bits, __float_as_int(scale ? nr * inv * inv : nr));
         for (int c = lane; c < ld; c += kWarp) {
             float v = 0.f;
             if (c < d) {

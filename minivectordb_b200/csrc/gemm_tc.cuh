@@ -1,0 +1,446 @@
+// gemm_tc.cuh -- large-batch path: Q[nq,d] x X[N,d]^T on the 5th-gen tensor
+// cores (tcgen05.mma, accumulators in TMEM, operands staged by TMA) with a
+// threshold-filter epilogue that never materialises the nq x N score matrix.
+//
+// Replaces faiss's exhaustive_inner_product_blas + Reservoir/Heap handlers (the
+// nq >= 20 branch of IndexFlatIP.search; reference call site
+// minivectordb/vector_database.py:497 -- the reference itself only ever sends
+// one query, BASELINE.json config 3 is the batched extension).
+//
+// Operands are bf16 (a shadow copy of the fp32 matrix, rounded to nearest at
+// ingest; queries converted per batch), accumulation is fp32 in TMEM.
+//   * "bf16" mode returns the top-k of those scores (recall reported vs fp32);
+//   * "exact" mode keeps every row whose bf16 score is within a RIGOROUS error
+//     bound of the running k-th best (|q~.x~ - q.x| <= 2^-8 (1+2^-10) |q||x| for
+//     round-to-nearest bf16 inputs, plus fp32 accumulation slack) and re-scores
+//     the survivors in fp32 with the GEMV path's exact summation order, so
+//     ids and distances are bit-identical to the single-query scan.
+//
+// Tile: 128 queries (UMMA M, one TMEM lane per query) x 256 rows (UMMA N, one
+// TMEM column per row) x 64 bf16 of K per stage (= 128 B, SWIZZLE_128B).
+// Warp roles (256 threads, 1 CTA/SM, persistent):
+//   warp 0  TMA producer   cp.async.bulk.tensor.2d -> 4-stage smem ring
+//   warp 1  MMA issuer     one elected lane, tcgen05.mma.cta_group::1.kind::f16
+//   warp 2  TMEM allocator 512 columns = 2 accumulator stages x 256
+//   warps 4-7 epilogue     tcgen05.ld 32x32b.x32: thread <-> query, columns <-> rows
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <cfloat>
+
+#include "aux_kernels.cuh"
+#include "select.cuh"
+
+namespace mvdb {
+
+constexpr int kGemmBM = 128;      // queries per tile
+constexpr int kGemmBN = 256;      // rows per tile
+constexpr int kGemmBK = 64;       // bf16 per k-block (128 bytes)
+constexpr int kGemmStages = 4;
+constexpr uint32_t kGemmABytes = kGemmBM * kGemmBK * 2;   // 16 KB
+constexpr uint32_t kGemmBBytes = kGemmBN * kGemmBK * 2;   // 32 KB
+constexpr uint32_t kGemmStageBytes = kGemmABytes + kGemmBBytes;
+constexpr uint32_t kGemmSmemBytes = kGemmStages * kGemmStageBytes + 256 + 1024;  // + barriers + alignment slack
+constexpr uint32_t kTmemCols = 512;
+
+struct GemmParams {
+    int64_t nq;            // queries
+    uint32_t row0, row1;   // rows [row0, row1) of the index are scanned by this launch
+    uint32_t n_valid;      // rows >= n_valid do not exist (mask snapshot / ntotal)
+    int d;
+    const uint32_t* live;  // bitmasks over rows (nullptr = none)
+    const uint32_t* mask;
+    // candidate output (threshold filter)
+    const uint64_t* thr;   // [nq] threshold keys: a candidate must be > thr[q]
+    uint64_t* cand;        // [nq][cand_cap] keys (bf16-score image << 32 | ~row)
+    unsigned int* cand_cnt;  // [nq]
+    uint32_t cand_cap;
+    // debug: dense scores [nq][n_total] (nullptr in production)
+    float* dense;
+    int64_t dense_ld;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T ; bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns: thread t of the warp receives lane (base_lane + t)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor for a K-major bf16 tile whose rows are 128 B
+// (64 bf16) and stored with the 128-byte swizzle TMA produces: 8-row groups are
+// 1024 B apart (SBO), LBO unused, descriptor version 1 (sm_100), layout SWIZZLE_128B.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= uint64_t((smem_addr & 0x3FFFFu) >> 4);   // bits  0-13 start address >> 4
+    d |= uint64_t(1024u >> 4) << 32;              // bits 32-45 stride byte offset >> 4
+    d |= uint64_t(1) << 46;                       // bits 46-47 descriptor version
+    d |= uint64_t(2) << 61;                       // bits 61-63 SWIZZLE_128B
+    return d;
+}
+// Instruction descriptor, kind::f16: D fp32, A/B bf16, both K-major, M x N.
+__device__ __forceinline__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+    return (1u << 4)                 // c_format  = F32
+           | (1u << 7)               // a_format  = BF16
+           | (1u << 10)              // b_format  = BF16
+           | (uint32_t(N >> 3) << 17)
+           | (uint32_t(M >> 4) << 24);
+}
+
+struct GemmBarriers {
+    uint64_t full[kGemmStages];
+    uint64_t empty[kGemmStages];
+    uint64_t tfull[2];
+    uint64_t tempty[2];
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(256, 1)
+gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmX, const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(smem + kGemmStages * kGemmStageBytes);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kGemmStages; s++) {
+            mbar_init(&bars->full[s], 1);
+            mbar_init(&bars->empty[s], 1);
+        }
+        for (int a = 0; a < 2; a++) {
+            mbar_init(&bars->tfull[a], 1);
+            mbar_init(&bars->tempty[a], 4);   // one arrival per epilogue warp
+        }
+        mbar_fence_init();
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmX);
+    }
+    if (warp == 2) tmem_alloc(&bars->tmem_base, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    const uint32_t n_rows = p.row1 - p.row0;
+    const uint32_t n_xt = (n_rows + kGemmBN - 1) / kGemmBN;
+    const uint32_t n_qb = uint32_t((p.nq + kGemmBM - 1) / kGemmBM);
+    const uint32_t n_kb = uint32_t((p.d + kGemmBK - 1) / kGemmBK);
+    // tile t = xt * n_qb + qb; CTA c owns the contiguous range [t_lo, t_hi): consecutive
+    // tiles share the X tile (L2 reuse) and small row chunks still fill the grid.
+    const uint64_t n_tiles = uint64_t(n_xt) * n_qb;
+    const uint32_t t_lo = uint32_t(n_tiles * blockIdx.x / gridDim.x);
+    const uint32_t t_hi = uint32_t(n_tiles * (blockIdx.x + 1) / gridDim.x);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t t = t_lo; t < t_hi; t++) {
+                const uint32_t xt = t / n_qb, qb = t % n_qb;
+                    for (uint32_t kb = 0; kb < n_kb; kb++) {
+                        mbar_wait(&bars->empty[stage], phase ^ 1u);
+                        uint8_t* sA = smem + stage * kGemmStageBytes;
+                        uint8_t* sB = sA + kGemmABytes;
+                        mbar_arrive_expect_tx(&bars->full[stage], kGemmStageBytes);
+                        tma_load_2d(sA, &tmQ, int(kb * kGemmBK), int(qb * kGemmBM), &bars->full[stage]);
+                        tma_load_2d(sB, &tmX, int(kb * kGemmBK), int(p.row0 + xt * kGemmBN), &bars->full[stage]);
+                        if (++stage == kGemmStages) { stage = 0; phase ^= 1u; }
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(kGemmBM, kGemmBN);
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (uint32_t t = t_lo; t < t_hi; t++) {
+                    mbar_wait(&bars->tempty[acc], acc_phase ^ 1u);   // epilogue has drained this accumulator
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * kGemmBN;
+                    for (uint32_t kb = 0; kb < n_kb; kb++) {
+                        mbar_wait(&bars->full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(smem + stage * kGemmStageBytes);
+                        const uint64_t a_desc = umma_desc_sw128(a_addr);
+                        const uint64_t b_desc = umma_desc_sw128(a_addr + kGemmABytes);
+#pragma unroll
+                        for (uint32_t k = 0; k < kGemmBK / 16; k++) {
+                            // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in (addr >> 4)
+                            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
+                        umma_commit(&bars->empty[stage]);   // frees the smem slot when these MMAs retire
+                        if (++stage == kGemmStages) { stage = 0; phase ^= 1u; }
+                    }
+                    umma_commit(&bars->tfull[acc]);         // accumulator complete -> epilogue
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                }
+        }
+    } else if (warp >= 4) {
+        const uint32_t quad = uint32_t(warp - 4);            // == warp % 4: the TMEM lane quadrant this warp may read
+        uint32_t acc = 0, acc_phase = 0;
+        uint32_t cur_xt = 0xFFFFFFFFu, tile_row0 = 0;
+        uint32_t adm[8];
+        for (uint32_t t = t_lo; t < t_hi; t++) {
+            const uint32_t xt = t / n_qb, qb = t % n_qb;
+            if (xt != cur_xt) {
+                cur_xt = xt;
+                tile_row0 = p.row0 + xt * kGemmBN;
+                // admissible bits of the tile's 256 rows (8 words), same for every query
+#pragma unroll
+                for (int w = 0; w < 8; w++) {
+                const uint32_t r = tile_row0 + 32 * w;        // tile_row0 is a multiple of 32 (row0 is, see host)
+                uint32_t bits = 0xFFFFFFFFu;
+                if (r >= p.n_valid) bits = 0;
+                else {
+                    if (p.n_valid - r < 32) bits = (1u << (p.n_valid - r)) - 1u;
+                    if (p.mask) bits &= p.mask[r >> 5];
+                    if (p.live) bits &= p.live[r >> 5];
+                }
+                    adm[w] = bits;
+                }
+            }
+            {
+                const int64_t q = int64_t(qb) * kGemmBM + quad * 32 + lane;
+                const bool q_ok = q < p.nq;
+                const uint64_t thr = (q_ok && p.thr) ? p.thr[q] : kEmptyKey;
+                mbar_wait(&bars->tfull[acc], acc_phase);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c0 = 0; c0 < kGemmBN; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_base + ((quad * 32u) << 16) + acc * kGemmBN + uint32_t(c0), v);
+                    const uint32_t bits = adm[c0 >> 5];
+                    if (p.dense) {
+                        if (q_ok) {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) {
+                                const uint32_t row = tile_row0 + c0 + j;
+                                if (row < p.n_valid) p.dense[q * p.dense_ld + row] = __uint_as_float(v[j]);
+                            }
+                        }
+                    } else if (q_ok && bits) {
+                        const uint32_t thr_ord = uint32_t(thr >> 32);
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const float s = __uint_as_float(v[j]);
+                            // cheap pre-test on the score image; the full key decides ties by row
+                            if (((bits >> j) & 1u) && score_to_ord(s) >= thr_ord && s == s) {
+                                const uint64_t key = make_key(s, tile_row0 + c0 + j);
+                                if (key > thr) {
+                                    const unsigned pos = atomicAdd(p.cand_cnt + q, 1u);
+                                    if (pos < p.cand_cap) p.cand[size_t(q) * p.cand_cap + pos] = key;
+                                }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->tempty[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------
+// helpers around the GEMM
+// ---------------------------------------------------------------------------
+// fp32 rows (pitch ld_in floats) -> bf16 rows (pitch ld_out), round to nearest, zero padding
+__global__ void __launch_bounds__(256) to_bf16_rows_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                                           uint64_t n, int d, int64_t ld_in, int64_t ld_out) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+    for (uint64_t r = warp; r < n; r += nwarps) {
+        const float* src = in + r * ld_in;
+        __nv_bfloat16* dst = out + r * ld_out;
+        for (int c = lane; c < ld_out; c += kWarp) dst[c] = __float2bfloat16_rn(c < d ? src[c] : 0.f);
+    }
+}
+
+// Queries: dense [nq][d] -> padded fp32 [nq][ld] (optionally L2-normalised with
+// EXACTLY the arithmetic of the scan's load_query_regs, so that re-scored
+// distances are bit-identical to the single-query path) + their L2 norms.
+__global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restrict__ q, float* __restrict__ qn,
+                                                           float* __restrict__ qnorm, int64_t nq, int d, int64_t ld,
+                                                           int normalize) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= nq) return;
+    const float* src = q + warp * d;
+    float* dst = qn + warp * ld;
+    const int ld4 = int(ld >> 2);
+    float nr = 0.f;
+    for (int c = lane; c < ld4; c += kWarp) {   // same chunk order as load_query_regs (j ascending)
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        int b = 4 * c;
+        if (b + 0 < d) v.x = src[b + 0];
+        if (b + 1 < d) v.y = src[b + 1];
+        if (b + 2 < d) v.z = src[b + 2];
+        if (b + 3 < d) v.w = src[b + 3];
+        nr = dot4(v, v, nr);
+        reinterpret_cast<float4*>(dst)[c] = v;
+    }
+    nr = warp_allsum(nr);
+    float norm = sqrtf(nr);
+    if (normalize && nr > 0.f) {
+        const float inv = renorm_scale(nr);
+        __syncwarp();
+        for (int c = lane; c < ld4; c += kWarp) {
+            float4 v = reinterpret_cast<float4*>(dst)[c];
+            v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+            reinterpret_cast<float4*>(dst)[c] = v;
+        }
+        norm = 1.0f;
+    }
+    if (lane == 0) qnorm[warp] = norm;
+}
+
+__global__ void init_batch_state_kernel(uint64_t* thr, unsigned int* cnt, unsigned int* overflow, int64_t nq) {
+    int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < nq) {
+        thr[i] = kEmptyKey;
+        cnt[i] = 0;
+        overflow[i] = 0;
+    }
+}
+
+// Per query (one CTA): sort the candidate list best-first, trim it, refresh the
+// threshold.  exact_slack == nullptr: keep the best k, threshold = k-th key.
+// exact mode: threshold = (k-th bf16 score - slack[q]) and EVERYTHING above it is
+// kept (the rigorous superset of the true fp32 top-k).  qnorm == nullptr selects
+// the plain mode; otherwise slack = slack_unit * qnorm[q].
+__global__ void __launch_bounds__(256) cand_update_kernel(uint64_t* cand, unsigned int* cnt, uint64_t* thr,
+                                                          unsigned int* overflow, uint32_t cap, int k,
+                                                          const float* qnorm, float slack_unit) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint64_t* a = reinterpret_cast<uint64_t*>(smem);
+    __shared__ unsigned int keep_s;
+    const int64_t q = blockIdx.x;
+    unsigned int n = cnt[q];
+    if (n > cap) {
+        if (threadIdx.x == 0) overflow[q] = 1u;
+        n = cap;
+    }
+    if (n == 0) return;
+    uint32_t npad = 64;
+    while (npad < n) npad <<= 1;
+    uint64_t* src = cand + size_t(q) * cap;
+    for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x) a[i] = i < n ? src[i] : kEmptyKey;
+    __syncthreads();
+    bitonic_sort_desc(a, int(npad), int(threadIdx.x), int(blockDim.x), BlockSyncer());
+    uint64_t new_thr = kEmptyKey;
+    unsigned int keep = n;
+    if (n >= unsigned(k)) {
+        const uint64_t kth = a[k - 1];
+        if (qnorm == nullptr) {
+            new_thr = kth;
+            keep = unsigned(k);
+        } else {
+            const float t = key_score(kth) - slack_unit * qnorm[q];
+            new_thr = make_key(t, 0xFFFFFFFFu);   // lowest key with score t: every score >= t passes
+            if (threadIdx.x == 0) keep_s = 0;
+            __syncthreads();
+            unsigned int mine = 0;
+            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) mine += (a[i] > new_thr) ? 1u : 0u;
+            if (mine) atomicAdd(&keep_s, mine);
+            __syncthreads();
+            keep = keep_s;
+        }
+    }
+    for (uint32_t i = threadIdx.x; i < keep; i += blockDim.x) src[i] = a[i];
+    if (threadIdx.x == 0) {
+        cnt[q] = keep;
+        thr[q] = new_thr;
+    }
+}
+
+// exact fp32 re-scoring of every surviving candidate, with the scan's summation
+// order (per-lane chunk order + xor butterfly 16,8,4,2,1 == reduce8's tree).
+__global__ void __launch_bounds__(256) rescore_kernel(const float* __restrict__ x, int ld4, const float* __restrict__ qn,
+                                                      uint64_t* cand, const unsigned int* cnt, uint32_t cap) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    float4* qs = reinterpret_cast<float4*>(smem);
+    const int64_t q = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const unsigned int n = min(cnt[q], cap);
+    if (n == 0) return;
+    const float4* qsrc = reinterpret_cast<const float4*>(qn) + q * ld4;
+    for (int c = threadIdx.x; c < ld4; c += blockDim.x) qs[c] = qsrc[c];
+    __syncthreads();
+    uint64_t* list = cand + size_t(q) * cap;
+    for (unsigned int i = warp; i < n; i += nw) {
+        const uint32_t row = key_row(list[i]);
+        const float4* xr = reinterpret_cast<const float4*>(x) + size_t(row) * ld4;
+        float acc = 0.f;
+        for (int c = lane; c < ld4; c += kWarp) acc = dot4(ldg_stream(xr + c), qs[c], acc);
+        acc = warp_allsum(acc);
+        if (lane == 0) list[i] = make_key(acc, row);
+    }
+}
+
+// first k keys of every (sorted) candidate list -> (D, I)
+__global__ void batch_results_kernel(const uint64_t* cand, const unsigned int* cnt, uint32_t cap, int k, int64_t nq,
+                                     int64_t label_offset, float* D, int64_t* I) {
+    int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= nq * k) return;
+    const int64_t q = t / k;
+    const int i = int(t % k);
+    const uint64_t key = (unsigned(i) < min(cnt[q], cap)) ? cand[size_t(q) * cap + i] : kEmptyKey;
+    if (key == kEmptyKey) {
+        D[t] = -FLT_MAX;
+        I[t] = -1;
+    } else {
+        D[t] = key_score(key);
+        I[t] = int64_t(key_row(key)) + label_offset;
+    }
+}
+
+}  // namespace mvdb

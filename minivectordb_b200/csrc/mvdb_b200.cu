@@ -28,6 +28,7 @@
 
 #include "../../include/mvdb_b200.h"
 #include "aux_kernels.cuh"
+#include "gemm_tc.cuh"
 #include "scan.cuh"
 
 using namespace mvdb;
@@ -80,6 +81,23 @@ struct DriverVmm {
     CUresult (*GetGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
     bool ok = false;
 };
+
+typedef CUresult (*TensorMapEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                           const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                           CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeTiledFn tensor_map_encoder() {
+    static TensorMapEncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult st;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &st) == cudaSuccess &&
+            st == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<TensorMapEncodeTiledFn>(p);
+        (void)cudaGetLastError();
+    });
+    return fn;
+}
 
 static DriverVmm* driver_vmm() {
     static DriverVmm api;
@@ -264,6 +282,21 @@ struct mvdb_workspace {
     RadixState* radix = nullptr;
     uint64_t* keys = nullptr;
     size_t keys_cap = 0;
+    // batched tensor-core path
+    float* b_qn = nullptr;
+    size_t b_qn_cap = 0;
+    float* b_qnorm = nullptr;
+    size_t b_qnorm_cap = 0;
+    __nv_bfloat16* b_q16 = nullptr;
+    size_t b_q16_cap = 0;
+    uint64_t* b_thr = nullptr;
+    size_t b_thr_cap = 0;
+    unsigned int* b_cnt = nullptr;
+    size_t b_cnt_cap = 0;
+    unsigned int* b_ovf = nullptr;
+    size_t b_ovf_cap = 0;
+    uint64_t* b_cand = nullptr;
+    size_t b_cand_cap = 0;
     // host-buffer path
     float* q_dev = nullptr;
     size_t q_cap = 0;
@@ -300,7 +333,16 @@ struct mvdb_index {
     size_t stage_cap[2] = {0, 0};
     int64_t* rows_dev = nullptr;
     size_t rows_cap = 0;
+    // bf16 shadow of the matrix for the tensor-core batched path (built lazily, kept in step by
+    // converting rows [shadow_rows, ntotal) at the start of a batched search)
+    GrowBuf mat16;
+    int64_t ld16 = 0;              // bf16 elements per shadow row (multiple of 8)
+    uint64_t shadow_rows = 0;
+    std::mutex shadow_mu;
+    int* max_norm2_bits = nullptr;  // device: bit pattern of the largest squared row norm stored
     // options
+    int batch_mode = 1;            // 0 off, 1 exact (bf16 candidates + fp32 re-scoring), 2 bf16
+    int batch_min_nq = 32;
     int scan_variant = MVDB_SCAN_AUTO;
     int fused_k_max = 128;
     int grid_ctas = 0;
@@ -510,10 +552,156 @@ static int ws_scratch(mvdb_workspace* ws) {
     return MVDB_OK;
 }
 
+
+// ---------------------------------------------------------------------------
+// batched tensor-core path (gemm_tc.cuh)
+// ---------------------------------------------------------------------------
+static int encode_bf16_map(CUtensorMap* tm, const void* base, uint64_t rows, int d, int64_t ld_elems, uint32_t box_rows) {
+    TensorMapEncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) return fail(MVDB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t gdim[2] = {cuuint64_t(d), cuuint64_t(std::max<uint64_t>(rows, 1))};
+    cuuint64_t gstride[1] = {cuuint64_t(ld_elems) * 2};
+    cuuint32_t box[2] = {cuuint32_t(kGemmBK), box_rows};
+    cuuint32_t estride[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estride,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(MVDB_ERR_CUDA, "cuTensorMapEncodeTiled failed: %d", int(r));
+    return MVDB_OK;
+}
+
+// bring the bf16 shadow up to `n` rows (round-to-nearest conversion of the stored fp32 rows)
+static int ensure_shadow(mvdb_index* ix, uint64_t n) {
+    std::lock_guard<std::mutex> g(ix->shadow_mu);
+    if (ix->shadow_rows >= n) return MVDB_OK;
+    cudaStream_t st = ix->mut_stream;
+    RC_OK(ix->mat16.ensure(size_t(n) * ix->ld16 * 2, st));
+    const uint64_t r0 = ix->shadow_rows, m = n - r0;
+    unsigned grid = unsigned(std::min<uint64_t>((m * 32 + 255) / 256, uint64_t(ix->sm_count) * 16));
+    to_bf16_rows_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(ix->mat.ptr()) + r0 * ix->ld,
+                                              static_cast<__nv_bfloat16*>(ix->mat16.ptr()) + r0 * ix->ld16, m, ix->d, ix->ld,
+                                              ix->ld16);
+    LAUNCHED();
+    CU_OK(cudaGetLastError());
+    CU_OK(cudaStreamSynchronize(st));
+    ix->shadow_rows = n;
+    return MVDB_OK;
+}
+
+static constexpr uint32_t kCandCap = 8192;      // candidate slots per query
+static constexpr uint32_t kFirstChunk = 2048;   // rows scanned before the first threshold exists
+
+static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, int64_t nq, int64_t k,
+                      const uint32_t* mask_dev, uint64_t mask_rows, int normalize_q, int64_t label_offset,
+                      float* D_dev, int64_t* I_dev, cudaStream_t stream, mvdb_exchange* xch);
+
+// Q[nq,d] against rows [0,n): bf16 GEMM on tcgen05 with threshold-filter epilogue,
+// geometric row chunks (thresholds tighten between chunks), optional exact re-scoring.
+// dense_out != nullptr: debug mode, write every bf16-GEMM score to dense_out[nq][n].
+static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, int64_t nq, int64_t k,
+                       const uint32_t* mask_dev, uint32_t n, int normalize_q, int64_t label_offset, float* D_dev,
+                       int64_t* I_dev, cudaStream_t stream, int mode, float* dense_out) {
+    RC_OK(ensure_shadow(ix, n));
+    RC_OK(grow_dev(&ws->b_qn, &ws->b_qn_cap, size_t(nq) * ix->ld));
+    RC_OK(grow_dev(&ws->b_qnorm, &ws->b_qnorm_cap, size_t(nq)));
+    RC_OK(grow_dev(&ws->b_q16, &ws->b_q16_cap, size_t(nq) * ix->ld16));
+    RC_OK(grow_dev(&ws->b_thr, &ws->b_thr_cap, size_t(nq)));
+    RC_OK(grow_dev(&ws->b_cnt, &ws->b_cnt_cap, size_t(nq)));
+    RC_OK(grow_dev(&ws->b_ovf, &ws->b_ovf_cap, size_t(nq)));
+    if (!dense_out) RC_OK(grow_dev(&ws->b_cand, &ws->b_cand_cap, size_t(nq) * kCandCap));
+
+    prep_queries_kernel<<<unsigned((nq * 32 + 255) / 256), 256, 0, stream>>>(q_dev, ws->b_qn, ws->b_qnorm, nq, ix->d, ix->ld,
+                                                                            normalize_q);
+    LAUNCHED();
+    to_bf16_rows_kernel<<<unsigned(std::min<int64_t>((nq * 32 + 255) / 256, 4096)), 256, 0, stream>>>(
+        ws->b_qn, ws->b_q16, uint64_t(nq), ix->d, ix->ld, ix->ld16);
+    LAUNCHED();
+    init_batch_state_kernel<<<unsigned((nq + 255) / 256), 256, 0, stream>>>(ws->b_thr, ws->b_cnt, ws->b_ovf, nq);
+    LAUNCHED();
+
+    CUtensorMap tmQ, tmX;
+    RC_OK(encode_bf16_map(&tmQ, ws->b_q16, uint64_t(nq), ix->d, ix->ld16, kGemmBM));
+    RC_OK(encode_bf16_map(&tmX, ix->mat16.ptr(), n, ix->d, ix->ld16, kGemmBN));
+    CU_OK(cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes)));
+    CU_OK(cudaFuncSetAttribute(cand_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kCandCap * 8)));
+
+    // rigorous bound on |bf16 score - fp32 score| per unit |q|: inputs rounded to nearest
+    // bf16 (2^-9 relative each) + fp32 accumulation of d terms, times the largest row norm
+    float slack_unit = 0.f;
+    if (mode == 1 && !dense_out) {
+        int bits = 0;
+        CU_OK(cudaMemcpyAsync(&bits, ix->max_norm2_bits, sizeof bits, cudaMemcpyDeviceToHost, stream));
+        CU_OK(cudaStreamSynchronize(stream));
+        float max_norm2;
+        memcpy(&max_norm2, &bits, 4);
+        const double eps_unit = (std::ldexp(1.0, -8) + std::ldexp(1.0, -18) + double(ix->d) * std::ldexp(1.0, -22)) * 1.01;
+        slack_unit = float(2.0 * eps_unit * std::sqrt(std::max(double(max_norm2), 1e-30)) * 1.0001);
+    }
+
+    GemmParams gp = {};
+    gp.nq = nq;
+    gp.n_valid = n;
+    gp.d = ix->d;
+    gp.live = ix->ndead.load(std::memory_order_acquire) ? static_cast<const uint32_t*>(ix->live.ptr()) : nullptr;
+    gp.mask = mask_dev;
+    gp.thr = ws->b_thr;
+    gp.cand = ws->b_cand;
+    gp.cand_cnt = ws->b_cnt;
+    gp.cand_cap = kCandCap;
+    gp.dense = dense_out;
+    gp.dense_ld = n;
+    const uint32_t n_qb = uint32_t((nq + kGemmBM - 1) / kGemmBM);
+    uint32_t done = 0;
+    while (done < n) {
+        uint32_t chunk = dense_out ? n : std::max(kFirstChunk, done);
+        chunk = std::min<uint32_t>(uint32_t(align_up(chunk, kGemmBN)), uint32_t(align_up(n - done, kGemmBN)));
+        gp.row0 = done;
+        gp.row1 = done + chunk;
+        const uint64_t tiles = uint64_t(chunk / kGemmBN) * n_qb;
+        const unsigned grid = unsigned(std::min<uint64_t>(uint64_t(ix->sm_count), tiles));
+        gemm_topk_kernel<<<grid, 256, kGemmSmemBytes, stream>>>(tmQ, tmX, gp);
+        LAUNCHED();
+        if (!dense_out) {
+            cand_update_kernel<<<unsigned(nq), 256, kCandCap * 8, stream>>>(ws->b_cand, ws->b_cnt, ws->b_thr, ws->b_ovf, kCandCap,
+                                                                           int(k), mode == 1 ? ws->b_qnorm : nullptr, slack_unit);
+            LAUNCHED();
+        }
+        done += chunk;
+    }
+    CU_OK(cudaGetLastError());
+    if (dense_out) return MVDB_OK;
+    if (mode == 1) {
+        rescore_kernel<<<unsigned(nq), 256, size_t(ix->ld) * 4, stream>>>(static_cast<const float*>(ix->mat.ptr()), ix->ld4, ws->b_qn,
+                                                                         ws->b_cand, ws->b_cnt, kCandCap);
+        LAUNCHED();
+        cand_update_kernel<<<unsigned(nq), 256, kCandCap * 8, stream>>>(ws->b_cand, ws->b_cnt, ws->b_thr, ws->b_ovf, kCandCap, int(k),
+                                                                       nullptr, 0.f);
+        LAUNCHED();
+    }
+    batch_results_kernel<<<unsigned((nq * k + 255) / 256), 256, 0, stream>>>(ws->b_cand, ws->b_cnt, kCandCap, int(k), nq, label_offset,
+                                                                            D_dev, I_dev);
+    LAUNCHED();
+    CU_OK(cudaGetLastError());
+    // queries whose candidate list overflowed (adversarial row order) are redone by the exact scan
+    std::vector<unsigned int> ovf(size_t(nq), 0u);
+    CU_OK(cudaMemcpyAsync(ovf.data(), ws->b_ovf, size_t(nq) * 4, cudaMemcpyDeviceToHost, stream));
+    CU_OK(cudaStreamSynchronize(stream));
+    const int saved = ix->batch_mode;
+    int rc = MVDB_OK;
+    for (int64_t q = 0; q < nq && rc == MVDB_OK; q++) {
+        if (!ovf[size_t(q)]) continue;
+        ix->batch_mode = 0;
+        rc = run_search(ix, ws, q_dev + q * ix->d, 1, k, mask_dev, n, normalize_q, label_offset, D_dev + q * k, I_dev + q * k,
+                        stream, nullptr);
+        ix->batch_mode = saved;
+    }
+    return rc;
+}
+
 // Core search on device buffers.  Caller holds move_mu shared.
 static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, int64_t nq, int64_t k,
                       const uint32_t* mask_dev, uint64_t mask_rows, int normalize_q, int64_t label_offset,
-                      float* D_dev, int64_t* I_dev, cudaStream_t stream, mvdb_exchange* xch = nullptr) {
+                      float* D_dev, int64_t* I_dev, cudaStream_t stream, mvdb_exchange* xch) {
     if (nq <= 0) return MVDB_OK;
     if (xch) {
         if (!xch->connected) return fail(MVDB_ERR_STATE, "exchange is not connected");
@@ -546,6 +734,9 @@ static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, in
         CU_OK(cudaGetLastError());
         return MVDB_OK;
     }
+    if (!xch && ix->batch_mode != 0 && nq >= ix->batch_min_nq && k <= 128 && tensor_map_encoder() != nullptr)
+        return run_batched(ix, ws, q_dev, nq, k, mask_dev, n, normalize_q, label_offset, D_dev, I_dev, stream,
+                           ix->batch_mode, nullptr);
     RC_OK(ws_scratch(ws));
     ScanParams p = {};
     p.x = static_cast<const float*>(ix->mat.ptr());
@@ -645,6 +836,13 @@ static void ws_free(mvdb_workspace* ws) {
     cudaFree(ws->all_ord);
     cudaFree(ws->radix);
     cudaFree(ws->keys);
+    cudaFree(ws->b_qn);
+    cudaFree(ws->b_qnorm);
+    cudaFree(ws->b_q16);
+    cudaFree(ws->b_thr);
+    cudaFree(ws->b_cnt);
+    cudaFree(ws->b_ovf);
+    cudaFree(ws->b_cand);
     cudaFree(ws->q_dev);
     cudaFree(ws->mask_dev);
     cudaFree(ws->D_dev);
@@ -751,10 +949,15 @@ int mvdb_index_create(int d, int device, uint64_t capacity_hint, mvdb_index** ou
     reserve = std::max(reserve, size_t(1) << 21);
     int rc = ix->mat.init(device, reserve);
     if (rc == MVDB_OK) rc = ix->live.init(device, std::max<size_t>(reserve / (size_t(ix->ld) * 4) / 8 + 4096, size_t(1) << 21));
+    ix->ld16 = int64_t(align_up(size_t(d), 8));
+    if (rc == MVDB_OK) rc = ix->mat16.init(device, std::max<size_t>(reserve / (size_t(ix->ld) * 4) * ix->ld16 * 2, size_t(1) << 21));
     cudaError_t e = cudaStreamCreateWithFlags(&ix->mut_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&ix->max_norm2_bits, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(ix->max_norm2_bits, 0, sizeof(int));
     if (rc != MVDB_OK || e != cudaSuccess) {
         ix->mat.destroy();
         ix->live.destroy();
+        ix->mat16.destroy();
         delete ix;
         return rc != MVDB_OK ? rc : fail(MVDB_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
     }
@@ -770,6 +973,8 @@ int mvdb_index_destroy(mvdb_index* ix) {
     ix->pool_free.clear();
     ix->mat.destroy();
     ix->live.destroy();
+    ix->mat16.destroy();
+    cudaFree(ix->max_norm2_bits);
     cudaFree(ix->stage_dev[0]);
     cudaFree(ix->stage_dev[1]);
     cudaFree(ix->rows_dev);
@@ -788,6 +993,10 @@ int mvdb_index_reset(mvdb_index* ix) {
     ix->live_host.clear();
     ix->ntotal.store(0);
     ix->ndead.store(0);
+    {
+        std::lock_guard<std::mutex> sg(ix->shadow_mu);
+        ix->shadow_rows = 0;
+    }
     return MVDB_OK;
 }
 
@@ -803,6 +1012,12 @@ int mvdb_index_set_option(mvdb_index* ix, const char* name, int64_t value) {
     } else if (s == "grid_ctas") {
         if (value < 0 || value > 65535) return fail(MVDB_ERR_ARG, "grid_ctas out of range");
         ix->grid_ctas = int(value);
+    } else if (s == "batch_mode") {
+        if (value < 0 || value > 2) return fail(MVDB_ERR_ARG, "batch_mode must be 0 (off), 1 (exact) or 2 (bf16)");
+        ix->batch_mode = int(value);
+    } else if (s == "batch_min_nq") {
+        if (value < 1) return fail(MVDB_ERR_ARG, "batch_min_nq must be >= 1");
+        ix->batch_min_nq = int(value);
     } else if (s == "consumer_warps") {
         if (value < 0 || value > 8) return fail(MVDB_ERR_ARG, "consumer_warps must be 0..8");
         ix->consumer_warps = int(value);
@@ -830,10 +1045,11 @@ static int add_common(mvdb_index* ix, const float* x_host, const float* x_dev, b
     auto grid_for = [&](uint64_t rows) { return unsigned(std::min<uint64_t>((rows * 32 + threads - 1) / threads, uint64_t(ix->sm_count) * 16)); };
     if (synth) {
         append_rows_kernel<true><<<grid_for(n), threads, 0, st>>>(nullptr, base, n, ix->d, ix->ld, normalize, seed,
-                                                                  uint64_t(synth_row0), dist);
+                                                                  uint64_t(synth_row0), dist, ix->max_norm2_bits);
         LAUNCHED();
     } else if (x_dev) {
-        append_rows_kernel<false><<<grid_for(n), threads, 0, st>>>(x_dev, base, n, ix->d, ix->ld, normalize, 0, 0, 0);
+        append_rows_kernel<false><<<grid_for(n), threads, 0, st>>>(x_dev, base, n, ix->d, ix->ld, normalize, 0, 0, 0,
+                                                                   ix->max_norm2_bits);
         LAUNCHED();
     } else {
         // host rows: stream through two device staging buffers so the H2D copy
@@ -847,7 +1063,7 @@ static int add_common(mvdb_index* ix, const float* x_host, const float* x_dev, b
             RC_OK(grow_dev(&ix->stage_dev[b], &ix->stage_cap[b], size_t(m) * ix->d));
             CU_OK(cudaMemcpyAsync(ix->stage_dev[b], x_host + done * ix->d, m * row_bytes, cudaMemcpyHostToDevice, st));
             append_rows_kernel<false><<<grid_for(m), threads, 0, st>>>(ix->stage_dev[b], base + done * ix->ld, m, ix->d,
-                                                                       ix->ld, normalize, 0, 0, 0);
+                                                                       ix->ld, normalize, 0, 0, 0, ix->max_norm2_bits);
             LAUNCHED();
             done += m;
             b ^= 1;
@@ -978,6 +1194,10 @@ int mvdb_index_compact(mvdb_index* ix, int64_t* ntotal_out) {
     ix->live_host.resize(new_words);
     ix->ntotal.store(nl, std::memory_order_release);
     ix->ndead.store(0, std::memory_order_release);
+    {
+        std::lock_guard<std::mutex> sg(ix->shadow_mu);
+        ix->shadow_rows = std::min<uint64_t>(ix->shadow_rows, first);  // rows past the first moved one are stale
+    }
     if (ntotal_out) *ntotal_out = int64_t(nl);
     return MVDB_OK;
 }
@@ -1039,7 +1259,7 @@ int mvdb_index_search_device(mvdb_index* ix, mvdb_workspace* ws, const float* q_
     if (nq && (!q_dev || !D_dev || !I_dev)) return fail(MVDB_ERR_ARG, "null buffer");
     std::shared_lock<std::shared_mutex> mv(ix->move_mu);
     return run_search(ix, ws, q_dev, nq, k, mask_dev, mask_rows, normalize_queries, label_offset, D_dev, I_dev,
-                      static_cast<cudaStream_t>(stream));
+                      static_cast<cudaStream_t>(stream), nullptr);
 }
 
 int mvdb_index_search(mvdb_index* ix, const float* q, int64_t nq, int64_t k, const uint8_t* mask, uint64_t mask_rows,
@@ -1081,7 +1301,7 @@ int mvdb_index_search(mvdb_index* ix, const float* q, int64_t nq, int64_t k, con
         }
         mask_dev = ws->mask_dev;
     }
-    RC_OK(run_search(ix, ws, ws->q_dev, nq, k, mask_dev, mask_rows, normalize_queries, 0, ws->D_dev, ws->I_dev, st));
+    RC_OK(run_search(ix, ws, ws->q_dev, nq, k, mask_dev, mask_rows, normalize_queries, 0, ws->D_dev, ws->I_dev, st, nullptr));
     CU_OK(cudaMemcpyAsync(ws->D_pin, ws->D_dev, on * 4, cudaMemcpyDeviceToHost, st));
     CU_OK(cudaMemcpyAsync(ws->I_pin, ws->I_dev, on * 8, cudaMemcpyDeviceToHost, st));
     CU_OK(cudaStreamSynchronize(st));
@@ -1203,6 +1423,40 @@ int mvdb_index_search_exchange(mvdb_index* ix, mvdb_workspace* ws, mvdb_exchange
     std::shared_lock<std::shared_mutex> mv(ix->move_mu);
     return run_search(ix, ws, q_dev, nq, k, mask_dev, mask_rows, normalize_queries, 0, D_dev, I_dev,
                       static_cast<cudaStream_t>(stream), x);
+}
+
+int mvdb_debug_gemm_scores(mvdb_index* ix, const float* q, int64_t nq, float* out) {
+    ENTER(ix);
+    if (!q || !out || nq <= 0) return fail(MVDB_ERR_ARG, "bad arguments");
+    const uint64_t n = ix->ntotal.load(std::memory_order_acquire);
+    if (n == 0 || n > 0xFFFFFFF0ull) return fail(MVDB_ERR_ARG, "index empty or too large");
+    mvdb_workspace* ws = nullptr;
+    RC_OK(pool_acquire(ix, &ws));
+    struct Release {
+        mvdb_index* ix;
+        mvdb_workspace* ws;
+        ~Release() { pool_release(ix, ws); }
+    } rel{ix, ws};
+    std::shared_lock<std::shared_mutex> mv(ix->move_mu);
+    float *q_dev = nullptr, *o_dev = nullptr;
+    CU_OK(cudaMalloc(&q_dev, size_t(nq) * ix->d * 4));
+    cudaError_t e = cudaMalloc(&o_dev, size_t(nq) * n * 4);
+    int rc = MVDB_OK;
+    if (e != cudaSuccess) rc = fail(MVDB_ERR_OOM, "cudaMalloc failed");
+    if (rc == MVDB_OK) {
+        e = cudaMemcpyAsync(q_dev, q, size_t(nq) * ix->d * 4, cudaMemcpyHostToDevice, ws->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(o_dev, 0, size_t(nq) * n * 4, ws->stream);
+        if (e != cudaSuccess) rc = fail(MVDB_ERR_CUDA, "copy failed: %s", cudaGetErrorString(e));
+    }
+    if (rc == MVDB_OK) rc = run_batched(ix, ws, q_dev, nq, 1, nullptr, uint32_t(n), 0, 0, nullptr, nullptr, ws->stream, 2, o_dev);
+    if (rc == MVDB_OK) {
+        e = cudaMemcpyAsync(out, o_dev, size_t(nq) * n * 4, cudaMemcpyDeviceToHost, ws->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ws->stream);
+        if (e != cudaSuccess) rc = fail(MVDB_ERR_CUDA, "debug gemm failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(q_dev);
+    cudaFree(o_dev);
+    return rc;
 }
 
 int mvdb_normalize_L2(float* x, uint64_t n, int d, int device) {

@@ -162,6 +162,13 @@ class FlatIPEngine:
                                           int(bool(normalize)), D.ctypes.data, I.ctypes.data))
         return D, I
 
+    def debug_gemm_scores(self, q) -> np.ndarray:
+        """Raw bf16 tensor-core scores [nq, ntotal] (test hook for the tcgen05 GEMM)."""
+        q = _as_f32_2d(q, self.d, "queries")
+        out = np.empty((q.shape[0], self.ntotal), dtype=np.float32)
+        N.check(N.lib().mvdb_debug_gemm_scores(self._h, q.ctypes.data, q.shape[0], out.ctypes.data))
+        return out
+
     # -- device-buffer flavour (sharded path, bench) -----------------------------
     def workspace(self) -> "Workspace":
         return Workspace(self)

@@ -1,0 +1,116 @@
+"""GPU: the tcgen05/TMEM batched path (large query batches, BASELINE config 3 shape).
+
+* the raw tensor-core GEMM against an independent bf16 matmul (torch);
+* "exact" mode (bf16 candidates + fp32 re-scoring) must return BIT-IDENTICAL
+  ids and distances to the fp32 scan;
+* "bf16" mode: recall@k against the fp32 oracle."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mv():
+    import minivectordb_b200 as m
+    return m
+
+
+def _data(n, d, nq, seed=1):
+    x = O.synth_rows(seed, 0, n, d)
+    O.normalize_L2(x)
+    q = O.synth_rows(seed + 100, 0, nq, d)
+    O.normalize_L2(q)
+    return x, q
+
+
+@pytest.mark.parametrize("n,d,nq", [(256, 64, 1), (1000, 64, 128), (777, 384, 200), (5000, 1000, 130),
+                                    (4096, 1024, 256), (300, 40, 5)])
+def test_tcgen05_gemm_matches_bf16_matmul(mv, n, d, nq):
+    import torch
+    x, q = _data(n, d, nq, seed=n + d)
+    eng = mv.FlatIPEngine(d)
+    eng.add(x)
+    got = eng.debug_gemm_scores(q)
+    xb = torch.from_numpy(x).to(torch.bfloat16).to(torch.float64)
+    qb = torch.from_numpy(q).to(torch.bfloat16).to(torch.float64)
+    want = (qb @ xb.T).numpy()
+    assert got.shape == want.shape
+    err = np.abs(got - want).max()
+    assert err < 2e-5, err   # products of bf16 are exact in fp32; only the accumulation order differs
+    eng.close()
+
+
+@pytest.mark.parametrize("n,d,nq,k", [(50_000, 384, 200, 10), (30_000, 1024, 129, 100), (9_000, 100, 64, 10),
+                                      (2_000, 768, 33, 128)])
+def test_batched_exact_is_bit_identical_to_the_scan(mv, n, d, nq, k):
+    x, q = _data(n, d, nq, seed=k + d)
+    eng = mv.FlatIPEngine(d)
+    eng.add(x)
+    rng = np.random.default_rng(0)
+    dead = rng.choice(n, n // 10, replace=False)
+    adm = rng.random(n) < 0.5
+    for step in range(3):
+        mask = adm if step >= 1 else None
+        if step == 2:
+            eng.remove_rows(dead)
+        eng.set_option("batch_mode", 0)
+        Ds, Is = eng.search(q, k, mask=mask)
+        eng.set_option("batch_mode", 1)
+        Db, Ib = eng.search(q, k, mask=mask)
+        assert np.array_equal(Is, Ib), (step, np.argwhere(Is != Ib)[:5])
+        assert np.array_equal(Ds, Db), step
+    # and against the oracle
+    live = np.ones(n, dtype=bool)
+    live[dead] = False
+    Dr, Ir = O.search_masked(x, adm & live, q, k)
+    rep = O.classify_parity(x, q, Ib, Db, Ir, Dr, admissible=adm & live)
+    assert rep["ok"], rep
+    eng.close()
+
+
+def test_batched_bf16_mode_recall(mv):
+    n, d, nq, k = 100_000, 384, 256, 10
+    x, q = _data(n, d, nq, seed=3)
+    eng = mv.FlatIPEngine(d)
+    eng.add(x)
+    eng.set_option("batch_mode", 2)
+    D, I = eng.search(q, k)
+    Dr, Ir = O.search_flat_ip(x, q, k)
+    recall = np.mean([len(set(I[i]) & set(Ir[i])) / k for i in range(nq)])
+    assert recall > 0.9, recall
+    assert np.all(np.diff(D, axis=1) <= 0)
+    assert np.abs(D - Dr).max() < 1e-2
+    eng.close()
+
+
+def test_batched_overflow_falls_back_to_the_scan(mv):
+    """Rows ordered by INCREASING similarity to a query make every row beat the
+    running threshold: the candidate list overflows and that query is redone by
+    the exact scan."""
+    n, d, nq, k = 30_000, 64, 40, 10
+    x, q = _data(n, d, nq, seed=5)
+    order = np.argsort(x @ q[0])
+    x = np.ascontiguousarray(x[order])
+    eng = mv.FlatIPEngine(d)
+    eng.add(x)
+    D, I = eng.search(q, k)
+    Dr, Ir = O.search_flat_ip(x, q, k)
+    rep = O.classify_parity(x, q, I, D, Ir, Dr)
+    assert rep["ok"], rep
+    eng.close()
+
+
+def test_batched_path_follows_appends(mv):
+    x, q = _data(20_000, 128, 64, seed=9)
+    eng = mv.FlatIPEngine(128)
+    eng.add(x[:5000])
+    eng.search(q, 10)              # builds the bf16 shadow for 5000 rows
+    eng.add(x[5000:])              # shadow must be extended lazily
+    D, I = eng.search(q, 10)
+    Dr, Ir = O.search_flat_ip(x, q, 10)
+    rep = O.classify_parity(x, q, I, D, Ir, Dr)
+    assert rep["ok"], rep
+    eng.close()
