@@ -248,12 +248,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 const uint64_t thr = (q_ok && p.thr) ? p.thr[q] : kEmptyKey;
                 mbar_wait(&bars->tfull[acc], acc_phase);
                 tc_fence_after();
+                const uint32_t t_lane = tmem_base + ((quad * 32u) << 16) + acc * kGemmBN;
+                if (p.dense) {
 #pragma unroll 1
-                for (int c0 = 0; c0 < kGemmBN; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(tmem_base + ((quad * 32u) << 16) + acc * kGemmBN + uint32_t(c0), v);
-                    const uint32_t bits = adm[c0 >> 5];
-                    if (p.dense) {
+                    for (int c0 = 0; c0 < kGemmBN; c0 += 32) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(t_lane + uint32_t(c0), v);
                         if (q_ok) {
 #pragma unroll
                             for (int j = 0; j < 32; j++) {
@@ -261,17 +261,47 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                                 if (row < p.n_valid) p.dense[q * p.dense_ld + row] = __uint_as_float(v[j]);
                             }
                         }
-                    } else if (q_ok && bits) {
-                        const uint32_t thr_ord = uint32_t(thr >> 32);
+                    }
+                } else {
+                    // Pass 1: which of my query's 256 scores beat its threshold?  Pure register
+                    // work -- no memory operation sits inside a divergent branch.
+                    const uint32_t thr_ord = uint32_t(thr >> 32), thr_low = uint32_t(thr);
+                    uint32_t hit[8];
+                    uint32_t total = 0;
+#pragma unroll
+                    for (int g = 0; g < 8; g++) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(t_lane + uint32_t(32 * g), v);
+                        uint32_t m = 0;
+                        const uint32_t low0 = 0xFFFFFFFFu - (tile_row0 + 32 * g);   // ~row of column 0 of this group
 #pragma unroll
                         for (int j = 0; j < 32; j++) {
                             const float s = __uint_as_float(v[j]);
-                            // cheap pre-test on the score image; the full key decides ties by row
-                            if (((bits >> j) & 1u) && score_to_ord(s) >= thr_ord && s == s) {
-                                const uint64_t key = make_key(s, tile_row0 + c0 + j);
-                                if (key > thr) {
-                                    const unsigned pos = atomicAdd(p.cand_cnt + q, 1u);
-                                    if (pos < p.cand_cap) p.cand[size_t(q) * p.cand_cap + pos] = key;
+                            const uint32_t o = score_to_ord(s);
+                            // key > thr  <=>  ord > thr_ord, or equal ord and ~row > thr_low; NaN never passes
+                            const bool pass = (s == s) && (o > thr_ord || (o == thr_ord && (low0 - j) > thr_low));
+                            m |= (pass ? 1u : 0u) << j;
+                        }
+                        m &= q_ok ? adm[g] : 0u;
+                        hit[g] = m;
+                        total += __popc(m);
+                    }
+                    // One reservation per thread per tile, then (rarely) pass 2: re-read the groups
+                    // that had a hit (TMEM reads are cheap) and store the keys.
+                    uint32_t pos = 0;
+                    if (total) pos = atomicAdd(p.cand_cnt + q, total);
+#pragma unroll
+                    for (int g = 0; g < 8; g++) {
+                        if (__any_sync(0xFFFFFFFFu, hit[g] != 0u)) {
+                            uint32_t v[32];
+                            tmem_ld_32x32(t_lane + uint32_t(32 * g), v);
+                            uint32_t m = hit[g];
+#pragma unroll
+                            for (int j = 0; j < 32; j++) {
+                                if ((m >> j) & 1u) {
+                                    if (pos < p.cand_cap)
+                                        p.cand[size_t(q) * p.cand_cap + pos] = make_key(__uint_as_float(v[j]), tile_row0 + 32 * g + j);
+                                    pos++;
                                 }
                             }
                         }

@@ -342,7 +342,7 @@ struct mvdb_index {
     int* max_norm2_bits = nullptr;  // device: bit pattern of the largest squared row norm stored
     // options
     int batch_mode = 1;            // 0 off, 1 exact (bf16 candidates + fp32 re-scoring), 2 bf16
-    int batch_min_nq = 32;
+    int batch_min_nq = 9;
     int scan_variant = MVDB_SCAN_AUTO;
     int fused_k_max = 128;
     int grid_ctas = 0;
