@@ -173,11 +173,14 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     K, W = args.steps, args.warmup
-    n, d, k = N_ROWS, DIM, TOPK
+    n, d, k = args.rows, args.dim, TOPK
+    custom = (n, d) != (N_ROWS, DIM) or args.no_filter
+    workload = WORKLOAD if not custom else (
+        f"custom: {n} x {d} fp32 per GPU, nq=1, k={k}, " + ("no filter" if args.no_filter else "~50% filter bitmask"))
     peak, peak_src = measured_peak()
 
     from minivectordb_b200.distributed import RowShardedIndex
-    index = RowShardedIndex(d, device=local)          # one row shard per rank, resident in HBM
+    index = RowShardedIndex(d, device=local, exchange=args.exchange)   # one row shard per rank, resident in HBM
     index.add(synthetic=(SEED_DB, rank * n, n, 0), normalize=True)
     eng = index.engine
     ld = eng.device_view()[1]
@@ -194,6 +197,8 @@ def run_b200(args):
 
     def step(i, q_t=None, m_t=None):
         # scan this rank's shard (+ for N>1: NCCL all-gather of k (score,label) pairs and merge on every rank)
+        if args.no_filter:
+            return index.search_device(q_t if q_t is not None else q_dev[i:i + 1], k)
         return index.search_device(q_t if q_t is not None else q_dev[i:i + 1], k,
                                    m_t if m_t is not None else mask_dev, n)
 
@@ -237,9 +242,12 @@ def run_b200(args):
 
     def e2e_step(i):
         if world == 1:
+            if args.no_filter:
+                return eng.search(q_host[i:i + 1], k)
             return eng.search(q_host[i:i + 1], k, mask=packed, mask_rows=n)
         q_e2e.copy_(q_pin[i:i + 1], non_blocking=True)
-        m_e2e.copy_(m_pin, non_blocking=True)
+        if not args.no_filter:
+            m_e2e.copy_(m_pin, non_blocking=True)
         D_t, I_t = step(i, q_e2e, m_e2e)
         return D_t.cpu(), I_t.cpu()
 
@@ -260,21 +268,23 @@ def run_b200(args):
     clk = clocks.stop() if rank == 0 else None
 
     if rank == 0:
-        alg_bytes = n * ld * 4 + (n + 7) // 8           # N*d*4 + ceil(N/8) with a filter mask
+        alg_bytes = n * ld * 4 + (0 if args.no_filter else (n + 7) // 8)   # N*d*4 + ceil(N/8) with a filter mask
         kern_s = float(np.mean(per_step)) if world == 1 else None
         qps_global = K / total_s
         line = {
             "metric": METRIC, "value": qps_global * world, "unit": "queries/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": total_s / K * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rows_per_gpu": n, "rows_total": n * world, "dim": d, "k": k,
-                       "filter_keep": float(adm.mean()), "l2": "matrix 1.5 GB >> 126 MB L2 (no flush needed)",
+            "config": {"workload": workload, "rows_per_gpu": n, "rows_total": n * world, "dim": d, "k": k,
+                       "filter_keep": None if args.no_filter else float(adm.mean()),
+                       "l2": f"matrix {n * ld * 4 / 1e9:.2f} GB per GPU >> 126 MB L2 (no flush needed)",
                        "unit_note": "value = shard scans/s over all ranks = n_gpus x global QPS "
                                     "(each rank scans its own 1M x 384 shard per query)",
                        "parallelism": f"row-shard x{world}" + (f", exchange={index.exchange}" if world > 1 else "")},
             "qps_global": qps_global,
             "p50_latency_us": float(np.median(per_step) * 1e6),
-            "e2e": {"value": K / e2e_total * world, "unit": "queries/s", "h2d_bytes_per_step": d * 4 + (n + 7) // 8,
+            "e2e": {"value": K / e2e_total * world, "unit": "queries/s",
+                    "h2d_bytes_per_step": d * 4 + (0 if args.no_filter else (n + 7) // 8),
                     "d2h_bytes_per_step": k * 12, "p50_latency_us": float(np.median(e2e_lat) * 1e6),
                     "qps_global": K / e2e_total,
                     "api": ("mvdb_index_search (C ABI, host buffers; H2D query+mask, D2H results inside)" if world == 1 else
@@ -285,15 +295,16 @@ def run_b200(args):
         if world == 1:
             ach = alg_bytes / kern_s / 1e9
             line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                                "traffic": None, "kernel": "scan_q1_kernel<3,tma>",
+                                "traffic": None, "kernel": f"scan_q1_kernel<{(ld // 4 + 31) // 32},tma>",
                                 "alg_bytes_per_launch": alg_bytes, "avg_launch_us": kern_s * 1e6,
                                 "peak_source": peak_src}
             try:
-                prof = json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json")))
-                line["roofline"]["traffic"] = prof.get("dram_bytes_per_launch")
+                if not custom:
+                    prof = json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json")))
+                    line["roofline"]["traffic"] = prof.get("dram_bytes_per_launch")
             except Exception:
                 pass
-            if not args.no_cpu_baseline:
+            if not args.no_cpu_baseline and not custom:
                 line["cpu_baseline"] = cpu_baseline_sample()
         print(json.dumps(line), flush=True)
     index.close()
@@ -330,6 +341,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiling runs under ncu)")
+    ap.add_argument("--rows", type=int, default=N_ROWS, help="rows per GPU (default: BASELINE config 2)")
+    ap.add_argument("--dim", type=int, default=DIM)
+    ap.add_argument("--no-filter", action="store_true", help="unfiltered queries (BASELINE config 4 shape)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "fused", "nccl"])
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 20:
