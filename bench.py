@@ -334,7 +334,26 @@ def cpu_baseline_sample():
             "unfiltered_scan_single_thread_s": scan_1t}
 
 
+def _quiet_stdout():
+    """Everything that libraries print on fd 1 (e.g. NCCL's version banner) goes to
+    stderr; the returned file object writes to the real stdout so that rank 0 emits
+    exactly ONE JSON line there."""
+    real = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    global print
+    real_stdout = _quiet_stdout()
+    _print = print
+
+    def print(*a, **kw):  # noqa: A001 - the JSON line goes to the real stdout
+        kw.setdefault("file", real_stdout)
+        _print(*a, **kw)
+        real_stdout.flush()
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
