@@ -21,6 +21,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <mutex>
 #include <shared_mutex>
 #include <string>
@@ -316,6 +317,20 @@ struct mvdb_workspace {
     size_t I_pin_cap = 0;
 };
 
+struct CoalesceReq {
+    const float* q;
+    int64_t k;
+    const uint8_t* mask;
+    uint64_t mask_rows;
+    int normalize;
+    float* D;
+    int64_t* I;
+    int rc = MVDB_OK;
+    bool done = false, promote = false;
+    std::string err;
+    std::condition_variable cv;
+};
+
 struct mvdb_index {
     int d = 0, device = 0;
     int64_t ld = 0;  // floats, multiple of 4
@@ -347,6 +362,12 @@ struct mvdb_index {
     int fused_k_max = 128;
     int grid_ctas = 0;
     int consumer_warps = 0;
+    // query coalescer: concurrent single-query host searches share one pass over the matrix
+    int coalesce = 1;
+    int coalesce_max = 64;
+    std::mutex co_mu;
+    std::deque<struct CoalesceReq*> co_queue;
+    int co_leaders = 0;
     // workspace pool for host-buffer searches
     std::mutex pool_mu;
     std::condition_variable pool_cv;
@@ -593,7 +614,8 @@ static constexpr uint32_t kFirstChunk = 2048;   // rows scanned before the first
 
 static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, int64_t nq, int64_t k,
                       const uint32_t* mask_dev, uint64_t mask_rows, int normalize_q, int64_t label_offset,
-                      float* D_dev, int64_t* I_dev, cudaStream_t stream, mvdb_exchange* xch);
+                      float* D_dev, int64_t* I_dev, cudaStream_t stream, mvdb_exchange* xch,
+                      const uint32_t* const* qmasks = nullptr);
 
 // Q[nq,d] against rows [0,n): bf16 GEMM on tcgen05 with threshold-filter epilogue,
 // geometric row chunks (thresholds tighten between chunks), optional exact re-scoring.
@@ -701,7 +723,10 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
 // Core search on device buffers.  Caller holds move_mu shared.
 static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, int64_t nq, int64_t k,
                       const uint32_t* mask_dev, uint64_t mask_rows, int normalize_q, int64_t label_offset,
-                      float* D_dev, int64_t* I_dev, cudaStream_t stream, mvdb_exchange* xch) {
+                      float* D_dev, int64_t* I_dev, cudaStream_t stream, mvdb_exchange* xch,
+                      const uint32_t* const* qmasks) {
+    // qmasks: optional per-query admissible bitmasks (device pointers, nullptr entries allowed);
+    // used by the coalescer, fused path only (k <= fused_k_max)
     if (nq <= 0) return MVDB_OK;
     if (xch) {
         if (!xch->connected) return fail(MVDB_ERR_STATE, "exchange is not connected");
@@ -734,7 +759,11 @@ static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, in
         CU_OK(cudaGetLastError());
         return MVDB_OK;
     }
-    if (!xch && ix->batch_mode != 0 && nq >= ix->batch_min_nq && k <= 128 && tensor_map_encoder() != nullptr)
+    bool any_qmask = false;
+    if (qmasks)
+        for (int64_t i = 0; i < nq; i++) any_qmask |= qmasks[i] != nullptr;
+    if (any_qmask && k > ix->fused_k_max) return fail(MVDB_ERR_ARG, "per-query masks need k <= %d", ix->fused_k_max);
+    if (!xch && !any_qmask && ix->batch_mode != 0 && nq >= ix->batch_min_nq && k <= 128 && tensor_map_encoder() != nullptr)
         return run_batched(ix, ws, q_dev, nq, k, mask_dev, n, normalize_q, label_offset, D_dev, I_dev, stream,
                            ix->batch_mode, nullptr);
     RC_OK(ws_scratch(ws));
@@ -759,6 +788,19 @@ static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, in
                 while (g > xch->nq_max) g >>= 1;
                 p.xchg = xch->dev;
                 p.xchg_seq = ++xch->seq;
+            }
+            p.mask = mask_dev;
+            p.has_qmask = 0;
+            for (int i = 0; i < 8; i++) p.qmask[i] = nullptr;
+            if (any_qmask) {
+                if (g == 1) {
+                    if (qmasks[done]) p.mask = qmasks[done];   // the single-query kernel takes it as the common mask
+                } else {
+                    for (int i = 0; i < g; i++) {
+                        p.qmask[i] = qmasks[done + i];
+                        p.has_qmask |= p.qmask[i] != nullptr;
+                    }
+                }
             }
             ScanPlan plan;
             RC_OK(plan_scan(ix, p, g, &plan));
@@ -1012,6 +1054,12 @@ int mvdb_index_set_option(mvdb_index* ix, const char* name, int64_t value) {
     } else if (s == "grid_ctas") {
         if (value < 0 || value > 65535) return fail(MVDB_ERR_ARG, "grid_ctas out of range");
         ix->grid_ctas = int(value);
+    } else if (s == "coalesce") {
+        if (value < 0 || value > 1) return fail(MVDB_ERR_ARG, "coalesce must be 0 or 1");
+        ix->coalesce = int(value);
+    } else if (s == "coalesce_max") {
+        if (value < 1 || value > 1024) return fail(MVDB_ERR_ARG, "coalesce_max must be 1..1024");
+        ix->coalesce_max = int(value);
     } else if (s == "batch_mode") {
         if (value < 0 || value > 2) return fail(MVDB_ERR_ARG, "batch_mode must be 0 (off), 1 (exact) or 2 (bf16)");
         ix->batch_mode = int(value);
@@ -1262,12 +1310,9 @@ int mvdb_index_search_device(mvdb_index* ix, mvdb_workspace* ws, const float* q_
                       static_cast<cudaStream_t>(stream), nullptr);
 }
 
-int mvdb_index_search(mvdb_index* ix, const float* q, int64_t nq, int64_t k, const uint8_t* mask, uint64_t mask_rows,
-                      int normalize_queries, float* D, int64_t* I) {
-    ENTER(ix);
-    if (nq < 0 || k <= 0) return fail(MVDB_ERR_ARG, "need nq >= 0 and k > 0 (got nq=%lld k=%lld)", (long long)nq, (long long)k);
-    if (nq == 0) return MVDB_OK;
-    if (!q || !D || !I) return fail(MVDB_ERR_ARG, "null buffer");
+// One host-buffer search on its own workspace: stage query (+mask), run, copy results back.
+static int search_host_direct(mvdb_index* ix, const float* q, int64_t nq, int64_t k, const uint8_t* mask,
+                              uint64_t mask_rows, int normalize_queries, float* D, int64_t* I) {
     mvdb_workspace* ws = nullptr;
     RC_OK(pool_acquire(ix, &ws));
     struct Release {
@@ -1308,6 +1353,154 @@ int mvdb_index_search(mvdb_index* ix, const float* q, int64_t nq, int64_t k, con
     memcpy(D, ws->D_pin, on * 4);
     memcpy(I, ws->I_pin, on * 8);
     return MVDB_OK;
+}
+
+// B concurrent single-query requests (same k, same normalise flag, each with its own optional
+// filter) as ONE pass over the matrix: <= 8 queries per scan launch with per-query masks, or --
+// when none is filtered and there are >= batch_min_nq of them -- one tensor-core batch.
+static int exec_coalesced(mvdb_index* ix, std::vector<CoalesceReq*>& batch) {
+    const int64_t B = int64_t(batch.size());
+    if (B == 1) {
+        CoalesceReq* r = batch[0];
+        return search_host_direct(ix, r->q, 1, r->k, r->mask, r->mask_rows, r->normalize, r->D, r->I);
+    }
+    const int64_t k = batch[0]->k;
+    mvdb_workspace* ws = nullptr;
+    RC_OK(pool_acquire(ix, &ws));
+    struct Release {
+        mvdb_index* ix;
+        mvdb_workspace* ws;
+        ~Release() { pool_release(ix, ws); }
+    } rel{ix, ws};
+    std::shared_lock<std::shared_mutex> mv(ix->move_mu);
+    cudaStream_t st = ws->stream;
+    const uint64_t n = ix->ntotal.load(std::memory_order_acquire);
+    const size_t qn = size_t(B) * ix->d, on = size_t(B) * k, words = (n + 31) / 32;
+    int n_masked = 0;
+    for (auto* r : batch) n_masked += r->mask != nullptr;
+    RC_OK(grow_dev(&ws->q_dev, &ws->q_cap, qn));
+    RC_OK(grow_pin(&ws->q_pin, &ws->q_pin_cap, qn));
+    RC_OK(grow_dev(&ws->D_dev, &ws->D_cap, on));
+    RC_OK(grow_dev(&ws->I_dev, &ws->I_cap, on));
+    RC_OK(grow_pin(&ws->D_pin, &ws->D_pin_cap, on));
+    RC_OK(grow_pin(&ws->I_pin, &ws->I_pin_cap, on));
+    if (n_masked) {
+        RC_OK(grow_dev(&ws->mask_dev, &ws->mask_cap, std::max<size_t>(words * n_masked, 1)));
+        RC_OK(grow_pin(&ws->mask_pin, &ws->mask_pin_cap, std::max<size_t>(words * n_masked, 1)));
+    }
+    std::vector<const uint32_t*> qmasks(size_t(B), nullptr);
+    int slot = 0;
+    for (int64_t i = 0; i < B; i++) {
+        CoalesceReq* r = batch[size_t(i)];
+        memcpy(ws->q_pin + i * ix->d, r->q, size_t(ix->d) * 4);
+        if (r->mask) {
+            // rows past the caller's mask_rows are not admissible: zero-filled tail
+            uint32_t* dst = ws->mask_pin + size_t(slot) * words;
+            const uint64_t rows = std::min<uint64_t>(r->mask_rows, n);
+            const size_t bytes = (rows + 7) / 8;
+            memset(dst, 0, words * 4);
+            memcpy(dst, r->mask, bytes);
+            if (rows & 7) reinterpret_cast<uint8_t*>(dst)[bytes - 1] &= uint8_t((1u << (rows & 7)) - 1u);
+            qmasks[size_t(i)] = ws->mask_dev + size_t(slot) * words;
+            slot++;
+        }
+    }
+    CU_OK(cudaMemcpyAsync(ws->q_dev, ws->q_pin, qn * 4, cudaMemcpyHostToDevice, st));
+    if (n_masked && words)
+        CU_OK(cudaMemcpyAsync(ws->mask_dev, ws->mask_pin, words * 4 * n_masked, cudaMemcpyHostToDevice, st));
+    RC_OK(run_search(ix, ws, ws->q_dev, B, k, nullptr, 0, batch[0]->normalize, 0, ws->D_dev, ws->I_dev, st, nullptr,
+                     n_masked ? qmasks.data() : nullptr));
+    CU_OK(cudaMemcpyAsync(ws->D_pin, ws->D_dev, on * 4, cudaMemcpyDeviceToHost, st));
+    CU_OK(cudaMemcpyAsync(ws->I_pin, ws->I_dev, on * 8, cudaMemcpyDeviceToHost, st));
+    CU_OK(cudaStreamSynchronize(st));
+    for (int64_t i = 0; i < B; i++) {
+        memcpy(batch[size_t(i)]->D, ws->D_pin + i * k, size_t(k) * 4);
+        memcpy(batch[size_t(i)]->I, ws->I_pin + i * k, size_t(k) * 8);
+    }
+    return MVDB_OK;
+}
+
+// Leader/follower coalescing with zero added latency when idle: a thread that finds fewer than
+// two leaders active becomes one and serves whatever is queued (including its own request);
+// while a batch runs on the GPU new arrivals queue up and form the next batch.
+static int coalesced_search(mvdb_index* ix, CoalesceReq& req) {
+    std::unique_lock<std::mutex> lk(ix->co_mu);
+    ix->co_queue.push_back(&req);
+    bool seat;   // does this thread hold one of the (at most two) leader seats?
+    if (ix->co_leaders >= 2) {
+        req.cv.wait(lk, [&] { return req.done || req.promote; });
+        seat = req.promote;   // a departing leader handed its seat over (possibly after our request was served)
+    } else {
+        ix->co_leaders++;
+        seat = true;
+    }
+    if (seat) {
+        while (!req.done) {
+            // batch = the queue head plus every compatible request behind it (same k, same
+            // normalise flag): up to coalesce_max unfiltered ones, or up to 8 once a filter is in
+            std::vector<CoalesceReq*> batch;
+            CoalesceReq* head = ix->co_queue.front();
+            const bool single = head->k > ix->fused_k_max;   // large-k path serves one query at a time
+            bool masked = false;
+            for (auto it = ix->co_queue.begin(); it != ix->co_queue.end();) {
+                CoalesceReq* r = *it;
+                const bool would_mask = masked || r->mask != nullptr;
+                const size_t cap = single ? 1 : (would_mask ? 8 : size_t(ix->coalesce_max));
+                if (r->k == head->k && r->normalize == head->normalize && batch.size() < cap) {
+                    batch.push_back(r);
+                    masked = would_mask;
+                    it = ix->co_queue.erase(it);
+                } else {
+                    ++it;
+                }
+            }
+            lk.unlock();
+            int rc = exec_coalesced(ix, batch);
+            std::string err = rc != MVDB_OK ? g_err : std::string();
+            lk.lock();
+            for (CoalesceReq* r : batch) {
+                r->rc = rc;
+                r->err = err;
+                r->done = true;
+                if (r != &req) r->cv.notify_one();
+            }
+        }
+        // leave the seat to the first waiter that has not been promoted yet, else free it
+        CoalesceReq* next = nullptr;
+        for (CoalesceReq* r : ix->co_queue)
+            if (!r->promote) {
+                next = r;
+                break;
+            }
+        if (next) {
+            next->promote = true;
+            next->cv.notify_one();
+        } else {
+            ix->co_leaders--;
+        }
+    }
+    if (req.rc != MVDB_OK) g_err = req.err;
+    return req.rc;
+}
+
+int mvdb_index_search(mvdb_index* ix, const float* q, int64_t nq, int64_t k, const uint8_t* mask, uint64_t mask_rows,
+                      int normalize_queries, float* D, int64_t* I) {
+    ENTER(ix);
+    if (nq < 0 || k <= 0) return fail(MVDB_ERR_ARG, "need nq >= 0 and k > 0 (got nq=%lld k=%lld)", (long long)nq, (long long)k);
+    if (nq == 0) return MVDB_OK;
+    if (!q || !D || !I) return fail(MVDB_ERR_ARG, "null buffer");
+    if (nq == 1 && ix->coalesce) {
+        CoalesceReq req;
+        req.q = q;
+        req.k = k;
+        req.mask = mask;
+        req.mask_rows = mask_rows;
+        req.normalize = normalize_queries ? 1 : 0;
+        req.D = D;
+        req.I = I;
+        return coalesced_search(ix, req);
+    }
+    return search_host_direct(ix, q, nq, k, mask, mask_rows, normalize_queries, D, I);
 }
 
 int mvdb_exchange_create(int device, int rank, int world, int k_max, int nq_max, mvdb_exchange** out) {

@@ -51,6 +51,8 @@ struct ScanParams {
     uint32_t stage_bytes;  // 8 * ld * 4 rounded to 128
     uint32_t sel_off, q_off, stage_off;  // byte offsets into dynamic shared memory
     uint32_t merge_off, merge_bytes;     // scratch for the last-CTA merge (the idle TMA ring, or a tail region)
+    const uint32_t* qmask[8];    // per-query admissible bitmasks (coalesced searches; nullptr = none); multi kernel only
+    int has_qmask;
     const struct XchgDev* xchg;  // fused cross-GPU exchange (nullptr = single GPU)
     uint64_t xchg_seq;           // sequence number of this launch (same on every rank, > 0)
 };
@@ -583,11 +585,14 @@ __global__ void __launch_bounds__(kTma ? 288 : 256, (kTma || NQ >= 8) ? 1 : 2) s
 #pragma unroll
         for (int qi = 0; qi < NQ; qi++) {
             const float score = reduce8(acc[qi], lane);
+            bool ok_q = ok;
+            if (p.has_qmask && p.qmask[qi])   // coalesced single-query searches keep their own filters
+                ok_q = ok && ((reinterpret_cast<const uint8_t*>(p.qmask[qi])[tile] >> my_row) & 1u);
             if (p.all_ord) {
                 if (leader && row < p.n)
-                    p.all_ord[size_t(qi) * p.n + row] = (ok && score == score) ? score_to_ord(score) : 0u;
+                    p.all_ord[size_t(qi) * p.n + row] = (ok_q && score == score) ? score_to_ord(score) : 0u;
             } else {
-                sel[qi].push(ok, make_key(score, row), lane);
+                sel[qi].push(ok_q, make_key(score, row), lane);
             }
         }
     }

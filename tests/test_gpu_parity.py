@@ -345,3 +345,56 @@ def test_tma_ring_any_consumer_warp_count(mv, d):
             D, I = eng.search(q, 10)
             assert np.array_equal(I, Iref) and np.array_equal(D, Dref), (d, cw)
     eng.close()
+
+
+def test_coalesced_concurrent_searches_equal_direct_ones(mv):
+    """Concurrent single-query calls are coalesced into shared passes (<= 8 per scan launch with
+    per-query filters, tensor-core batch when unfiltered); every caller must get exactly what a
+    lone call returns."""
+    import threading
+    n, d, k, nthreads, per = 60_000, 256, 10, 24, 12
+    x, q = _data(n, d, nthreads * per, seed=12)
+    eng = mv.FlatIPEngine(d)
+    eng.add(x)
+    eng.remove_rows(np.arange(0, n, 17))
+    rng = np.random.default_rng(3)
+    masks = [None if i % 3 == 0 else (rng.random(n) < (0.05 if i % 3 == 1 else 0.6)) for i in range(nthreads * per)]
+    packed = [None if m is None else mv.pack_mask(m) for m in masks]
+    eng.set_option("coalesce", 0)
+    want = [eng.search(q[i:i + 1], k, mask=packed[i], mask_rows=n if packed[i] is not None else None)
+            for i in range(nthreads * per)]
+    eng.set_option("coalesce", 1)
+    got = [None] * (nthreads * per)
+    errs = []
+
+    def worker(t):
+        try:
+            for j in range(per):
+                i = t * per + j
+                got[i] = eng.search(q[i:i + 1], k, mask=packed[i], mask_rows=n if packed[i] is not None else None)
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=worker, args=(t,)) for t in range(nthreads)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs[:1]
+    for i in range(nthreads * per):
+        assert np.array_equal(got[i][1], want[i][1]), i
+        assert np.array_equal(got[i][0], want[i][0]), i
+    # mixed k and large k in flight at the same time
+    def worker2(t):
+        try:
+            for j in range(6):
+                kk = (3, 10, 200)[(t + j) % 3]
+                D, I = eng.search(q[t:t + 1], kk)
+                eng.set_option  # noqa: B018
+                assert D.shape == (1, kk) and np.all(np.diff(D[0][I[0] >= 0]) <= 0)
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=worker2, args=(t,)) for t in range(12)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs[:1]
+    eng.close()
