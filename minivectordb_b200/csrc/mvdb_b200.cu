@@ -1436,6 +1436,11 @@ static int coalesced_search(mvdb_index* ix, CoalesceReq& req) {
     }
     if (seat) {
         while (!req.done) {
+            if (ix->co_queue.empty()) {
+                // our own request is in flight inside the other leader's batch
+                req.cv.wait(lk, [&] { return req.done; });
+                break;
+            }
             // batch = the queue head plus every compatible request behind it (same k, same
             // normalise flag): up to coalesce_max unfiltered ones, or up to 8 once a filter is in
             std::vector<CoalesceReq*> batch;
