@@ -148,6 +148,19 @@ int mvdb_index_device_view(mvdb_index* ix, const float** matrix_dev, int64_t* ld
 int mvdb_index_search(mvdb_index* ix, const float* q, int64_t nq, int64_t k, const uint8_t* mask,
                       uint64_t mask_rows, int normalize_queries, float* D, int64_t* I);
 
+/* Device-resident filters.  A filter that is used by many queries (the same
+ * metadata_filter repeated, vector_database.py:482) can be uploaded ONCE and
+ * referenced by handle; searches through a handle move no mask bytes, and
+ * concurrent single-query calls that carry handles are coalesced into one
+ * tensor-core batch with per-query filters.  Rows >= mask_rows (appended after
+ * the handle was made) are not admissible through it. */
+typedef struct mvdb_mask mvdb_mask;
+int mvdb_index_mask_create(mvdb_index* ix, const uint8_t* mask, uint64_t mask_rows, mvdb_mask** out);
+int mvdb_mask_destroy(mvdb_mask* m);
+/* mvdb_index_search with the filter given as a handle (NULL = unfiltered). */
+int mvdb_index_search_with_mask(mvdb_index* ix, const float* q, int64_t nq, int64_t k, const mvdb_mask* m,
+                                int normalize_queries, float* D, int64_t* I);
+
 /* Device-buffer flavour for callers that keep queries/results in HBM (the
  * sharded path and the bench's device-resident leg).  All pointers are device
  * pointers on the index's device; `stream` is a cudaStream_t (NULL = default

@@ -36,6 +36,7 @@ EXPORTS = [
     "mvdb_normalize_L2", "mvdb_merge_topk_device", "mvdb_launch_count",
     "mvdb_exchange_create", "mvdb_exchange_ipc_handle", "mvdb_exchange_connect", "mvdb_exchange_set_offsets",
     "mvdb_exchange_status", "mvdb_exchange_destroy", "mvdb_index_search_exchange", "mvdb_debug_gemm_scores",
+    "mvdb_index_mask_create", "mvdb_mask_destroy", "mvdb_index_search_with_mask",
 ]
 
 
@@ -132,6 +133,9 @@ def lib():
             "mvdb_exchange_status": (i, [c_vp, ctypes.POINTER(i)]),
             "mvdb_exchange_destroy": (i, [c_vp]),
             "mvdb_debug_gemm_scores": (i, [c_vp, c_vp, i64, c_vp]),
+            "mvdb_index_mask_create": (i, [c_vp, c_vp, u64, ctypes.POINTER(c_vp)]),
+            "mvdb_mask_destroy": (i, [c_vp]),
+            "mvdb_index_search_with_mask": (i, [c_vp, c_vp, i64, i64, c_vp, i, c_vp, c_vp]),
             "mvdb_index_search_exchange": (i, [c_vp, c_vp, c_vp, c_vp, i64, i64, c_vp, u64, i, c_vp, c_vp, c_vp]),
         }
         for name, (res, args) in sig.items():

@@ -51,6 +51,8 @@ struct GemmParams {
     int d;
     const uint32_t* live;  // bitmasks over rows (nullptr = none)
     const uint32_t* mask;
+    const uint32_t* const* qmask;   // [nq] per-query admissible bitmasks (nullptr array or nullptr entries = none)
+    const uint32_t* qmask_words;    // [nq] 32-row words available behind qmask[q]; rows past them are not admissible
     // candidate output (threshold filter)
     const uint64_t* thr;   // [nq] threshold keys: a candidate must be > thr[q]
     uint64_t* cand;        // [nq][cand_cap] keys (bf16-score image << 32 | ~row)
@@ -246,6 +248,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 const int64_t q = int64_t(qb) * kGemmBM + quad * 32 + lane;
                 const bool q_ok = q < p.nq;
                 const uint64_t thr = (q_ok && p.thr) ? p.thr[q] : kEmptyKey;
+                const uint32_t* qm = (q_ok && p.qmask) ? p.qmask[q] : nullptr;   // this query's own filter
+                const uint32_t qm_words = qm ? p.qmask_words[q] : 0u;
                 mbar_wait(&bars->tfull[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t t_lane = tmem_base + ((quad * 32u) << 16) + acc * kGemmBN;
@@ -283,6 +287,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                             m |= pass << j;
                         }
                         m &= q_ok ? adm[g] : 0u;
+                        if (qm) {
+                            const uint32_t w = (tile_row0 >> 5) + uint32_t(g);
+                            m &= (w < qm_words) ? qm[w] : 0u;
+                        }
                         hit[g] = m;
                         total += __popc(m);
                     }

@@ -298,6 +298,10 @@ struct mvdb_workspace {
     size_t b_ovf_cap = 0;
     uint64_t* b_cand = nullptr;
     size_t b_cand_cap = 0;
+    const uint32_t** b_qmptr = nullptr;
+    size_t b_qmptr_cap = 0;
+    uint32_t* b_qmwords = nullptr;
+    size_t b_qmwords_cap = 0;
     // host-buffer path
     float* q_dev = nullptr;
     size_t q_cap = 0;
@@ -317,11 +321,24 @@ struct mvdb_workspace {
     size_t I_pin_cap = 0;
 };
 
+struct QMaskRef {          // one query's own admissible bitmask, resident on the device
+    const uint32_t* dev;
+    uint32_t words;        // 32-row words behind dev; rows past them are not admissible
+};
+
+struct mvdb_mask {         // device-resident filter, uploaded once, reusable by any number of searches
+    mvdb_index* ix;
+    uint32_t* dev;
+    uint64_t rows;
+    uint32_t words;
+};
+
 struct CoalesceReq {
     const float* q;
     int64_t k;
     const uint8_t* mask;
     uint64_t mask_rows;
+    const mvdb_mask* handle = nullptr;
     int normalize;
     float* D;
     int64_t* I;
@@ -615,14 +632,15 @@ static constexpr uint32_t kFirstChunk = 2048;   // rows scanned before the first
 static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, int64_t nq, int64_t k,
                       const uint32_t* mask_dev, uint64_t mask_rows, int normalize_q, int64_t label_offset,
                       float* D_dev, int64_t* I_dev, cudaStream_t stream, mvdb_exchange* xch,
-                      const uint32_t* const* qmasks = nullptr);
+                      const QMaskRef* qmasks = nullptr);
 
 // Q[nq,d] against rows [0,n): bf16 GEMM on tcgen05 with threshold-filter epilogue,
 // geometric row chunks (thresholds tighten between chunks), optional exact re-scoring.
 // dense_out != nullptr: debug mode, write every bf16-GEMM score to dense_out[nq][n].
 static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, int64_t nq, int64_t k,
                        const uint32_t* mask_dev, uint32_t n, int normalize_q, int64_t label_offset, float* D_dev,
-                       int64_t* I_dev, cudaStream_t stream, int mode, float* dense_out) {
+                       int64_t* I_dev, cudaStream_t stream, int mode, float* dense_out,
+                       const QMaskRef* qmasks = nullptr) {
     RC_OK(ensure_shadow(ix, n));
     RC_OK(grow_dev(&ws->b_qn, &ws->b_qn_cap, size_t(nq) * ix->ld));
     RC_OK(grow_dev(&ws->b_qnorm, &ws->b_qnorm_cap, size_t(nq)));
@@ -661,6 +679,22 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
     }
 
     GemmParams gp = {};
+    if (qmasks) {
+        // per-query filters: thread <-> query in the epilogue, so each thread reads its own words
+        std::vector<const uint32_t*> ptrs(size_t(nq), nullptr);
+        std::vector<uint32_t> wrds(size_t(nq), 0u);
+        for (int64_t i = 0; i < nq; i++) {
+            ptrs[size_t(i)] = qmasks[i].dev;
+            wrds[size_t(i)] = qmasks[i].words;
+        }
+        RC_OK(grow_dev(&ws->b_qmptr, &ws->b_qmptr_cap, size_t(nq)));
+        RC_OK(grow_dev(&ws->b_qmwords, &ws->b_qmwords_cap, size_t(nq)));
+        CU_OK(cudaMemcpyAsync(ws->b_qmptr, ptrs.data(), size_t(nq) * 8, cudaMemcpyHostToDevice, stream));
+        CU_OK(cudaMemcpyAsync(ws->b_qmwords, wrds.data(), size_t(nq) * 4, cudaMemcpyHostToDevice, stream));
+        CU_OK(cudaStreamSynchronize(stream));   // the host vectors go out of scope
+        gp.qmask = ws->b_qmptr;
+        gp.qmask_words = ws->b_qmwords;
+    }
     gp.nq = nq;
     gp.n_valid = n;
     gp.d = ix->d;
@@ -714,7 +748,7 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
         if (!ovf[size_t(q)]) continue;
         ix->batch_mode = 0;
         rc = run_search(ix, ws, q_dev + q * ix->d, 1, k, mask_dev, n, normalize_q, label_offset, D_dev + q * k, I_dev + q * k,
-                        stream, nullptr);
+                        stream, nullptr, qmasks ? qmasks + q : nullptr);
         ix->batch_mode = saved;
     }
     return rc;
@@ -724,9 +758,9 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
 static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, int64_t nq, int64_t k,
                       const uint32_t* mask_dev, uint64_t mask_rows, int normalize_q, int64_t label_offset,
                       float* D_dev, int64_t* I_dev, cudaStream_t stream, mvdb_exchange* xch,
-                      const uint32_t* const* qmasks) {
-    // qmasks: optional per-query admissible bitmasks (device pointers, nullptr entries allowed);
-    // used by the coalescer, fused path only (k <= fused_k_max)
+                      const QMaskRef* qmasks) {
+    // qmasks: optional per-query admissible bitmasks ([nq], dev == nullptr = unfiltered); used by
+    // the coalescer; k <= fused_k_max
     if (nq <= 0) return MVDB_OK;
     if (xch) {
         if (!xch->connected) return fail(MVDB_ERR_STATE, "exchange is not connected");
@@ -761,11 +795,11 @@ static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, in
     }
     bool any_qmask = false;
     if (qmasks)
-        for (int64_t i = 0; i < nq; i++) any_qmask |= qmasks[i] != nullptr;
+        for (int64_t i = 0; i < nq; i++) any_qmask |= qmasks[i].dev != nullptr;
     if (any_qmask && k > ix->fused_k_max) return fail(MVDB_ERR_ARG, "per-query masks need k <= %d", ix->fused_k_max);
-    if (!xch && !any_qmask && ix->batch_mode != 0 && nq >= ix->batch_min_nq && k <= 128 && tensor_map_encoder() != nullptr)
+    if (!xch && ix->batch_mode != 0 && nq >= ix->batch_min_nq && k <= 128 && tensor_map_encoder() != nullptr)
         return run_batched(ix, ws, q_dev, nq, k, mask_dev, n, normalize_q, label_offset, D_dev, I_dev, stream,
-                           ix->batch_mode, nullptr);
+                           ix->batch_mode, nullptr, any_qmask ? qmasks : nullptr);
     RC_OK(ws_scratch(ws));
     ScanParams p = {};
     p.x = static_cast<const float*>(ix->mat.ptr());
@@ -790,14 +824,25 @@ static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, in
                 p.xchg_seq = ++xch->seq;
             }
             p.mask = mask_dev;
+            p.n = n;
             p.has_qmask = 0;
             for (int i = 0; i < 8; i++) p.qmask[i] = nullptr;
             if (any_qmask) {
                 if (g == 1) {
-                    if (qmasks[done]) p.mask = qmasks[done];   // the single-query kernel takes it as the common mask
+                    if (qmasks[done].dev) {   // the single-query kernel takes it as the common mask
+                        p.mask = qmasks[done].dev;
+                        p.n = uint32_t(std::min<uint64_t>(n, uint64_t(qmasks[done].words) * 32));
+                        if (p.n == 0) {
+                            fill_empty_results_kernel<<<unsigned((k + 255) / 256), 256, 0, stream>>>(D_dev + done * k, I_dev + done * k, k);
+                            LAUNCHED();
+                            done += 1;
+                            continue;
+                        }
+                    }
                 } else {
                     for (int i = 0; i < g; i++) {
-                        p.qmask[i] = qmasks[done + i];
+                        p.qmask[i] = qmasks[done + i].dev;
+                        p.qmask_bytes[i] = qmasks[done + i].words * 4u;
                         p.has_qmask |= p.qmask[i] != nullptr;
                     }
                 }
@@ -885,6 +930,8 @@ static void ws_free(mvdb_workspace* ws) {
     cudaFree(ws->b_cnt);
     cudaFree(ws->b_ovf);
     cudaFree(ws->b_cand);
+    cudaFree(ws->b_qmptr);
+    cudaFree(ws->b_qmwords);
     cudaFree(ws->q_dev);
     cudaFree(ws->mask_dev);
     cudaFree(ws->D_dev);
@@ -1312,7 +1359,8 @@ int mvdb_index_search_device(mvdb_index* ix, mvdb_workspace* ws, const float* q_
 
 // One host-buffer search on its own workspace: stage query (+mask), run, copy results back.
 static int search_host_direct(mvdb_index* ix, const float* q, int64_t nq, int64_t k, const uint8_t* mask,
-                              uint64_t mask_rows, int normalize_queries, float* D, int64_t* I) {
+                              uint64_t mask_rows, int normalize_queries, float* D, int64_t* I,
+                              const mvdb_mask* handle = nullptr) {
     mvdb_workspace* ws = nullptr;
     RC_OK(pool_acquire(ix, &ws));
     struct Release {
@@ -1332,7 +1380,10 @@ static int search_host_direct(mvdb_index* ix, const float* q, int64_t nq, int64_
     memcpy(ws->q_pin, q, qn * 4);
     CU_OK(cudaMemcpyAsync(ws->q_dev, ws->q_pin, qn * 4, cudaMemcpyHostToDevice, st));
     const uint32_t* mask_dev = nullptr;
-    if (mask) {
+    if (handle) {
+        mask_dev = handle->dev;      // already resident: no per-query upload
+        mask_rows = handle->rows;
+    } else if (mask) {
         const uint64_t rows = std::min<uint64_t>(mask_rows, ix->ntotal.load(std::memory_order_acquire));
         mask_rows = rows;
         const size_t words = (rows + 31) / 32, bytes = (rows + 7) / 8;
@@ -1362,7 +1413,7 @@ static int exec_coalesced(mvdb_index* ix, std::vector<CoalesceReq*>& batch) {
     const int64_t B = int64_t(batch.size());
     if (B == 1) {
         CoalesceReq* r = batch[0];
-        return search_host_direct(ix, r->q, 1, r->k, r->mask, r->mask_rows, r->normalize, r->D, r->I);
+        return search_host_direct(ix, r->q, 1, r->k, r->mask, r->mask_rows, r->normalize, r->D, r->I, r->handle);
     }
     const int64_t k = batch[0]->k;
     mvdb_workspace* ws = nullptr;
@@ -1376,8 +1427,12 @@ static int exec_coalesced(mvdb_index* ix, std::vector<CoalesceReq*>& batch) {
     cudaStream_t st = ws->stream;
     const uint64_t n = ix->ntotal.load(std::memory_order_acquire);
     const size_t qn = size_t(B) * ix->d, on = size_t(B) * k, words = (n + 31) / 32;
-    int n_masked = 0;
-    for (auto* r : batch) n_masked += r->mask != nullptr;
+    int n_masked = 0;   // requests whose filter still has to be staged from host memory
+    bool any_filter = false;
+    for (auto* r : batch) {
+        n_masked += (r->mask != nullptr && !r->handle);
+        any_filter |= r->mask != nullptr || r->handle != nullptr;
+    }
     RC_OK(grow_dev(&ws->q_dev, &ws->q_cap, qn));
     RC_OK(grow_pin(&ws->q_pin, &ws->q_pin_cap, qn));
     RC_OK(grow_dev(&ws->D_dev, &ws->D_cap, on));
@@ -1388,12 +1443,14 @@ static int exec_coalesced(mvdb_index* ix, std::vector<CoalesceReq*>& batch) {
         RC_OK(grow_dev(&ws->mask_dev, &ws->mask_cap, std::max<size_t>(words * n_masked, 1)));
         RC_OK(grow_pin(&ws->mask_pin, &ws->mask_pin_cap, std::max<size_t>(words * n_masked, 1)));
     }
-    std::vector<const uint32_t*> qmasks(size_t(B), nullptr);
+    std::vector<QMaskRef> qmasks(size_t(B), QMaskRef{nullptr, 0u});
     int slot = 0;
     for (int64_t i = 0; i < B; i++) {
         CoalesceReq* r = batch[size_t(i)];
         memcpy(ws->q_pin + i * ix->d, r->q, size_t(ix->d) * 4);
-        if (r->mask) {
+        if (r->handle) {
+            qmasks[size_t(i)] = QMaskRef{r->handle->dev, r->handle->words};
+        } else if (r->mask) {
             // rows past the caller's mask_rows are not admissible: zero-filled tail
             uint32_t* dst = ws->mask_pin + size_t(slot) * words;
             const uint64_t rows = std::min<uint64_t>(r->mask_rows, n);
@@ -1401,7 +1458,7 @@ static int exec_coalesced(mvdb_index* ix, std::vector<CoalesceReq*>& batch) {
             memset(dst, 0, words * 4);
             memcpy(dst, r->mask, bytes);
             if (rows & 7) reinterpret_cast<uint8_t*>(dst)[bytes - 1] &= uint8_t((1u << (rows & 7)) - 1u);
-            qmasks[size_t(i)] = ws->mask_dev + size_t(slot) * words;
+            qmasks[size_t(i)] = QMaskRef{ws->mask_dev + size_t(slot) * words, uint32_t(words)};
             slot++;
         }
     }
@@ -1409,7 +1466,7 @@ static int exec_coalesced(mvdb_index* ix, std::vector<CoalesceReq*>& batch) {
     if (n_masked && words)
         CU_OK(cudaMemcpyAsync(ws->mask_dev, ws->mask_pin, words * 4 * n_masked, cudaMemcpyHostToDevice, st));
     RC_OK(run_search(ix, ws, ws->q_dev, B, k, nullptr, 0, batch[0]->normalize, 0, ws->D_dev, ws->I_dev, st, nullptr,
-                     n_masked ? qmasks.data() : nullptr));
+                     any_filter ? qmasks.data() : nullptr));
     CU_OK(cudaMemcpyAsync(ws->D_pin, ws->D_dev, on * 4, cudaMemcpyDeviceToHost, st));
     CU_OK(cudaMemcpyAsync(ws->I_pin, ws->I_dev, on * 8, cudaMemcpyDeviceToHost, st));
     CU_OK(cudaStreamSynchronize(st));
@@ -1449,7 +1506,9 @@ static int coalesced_search(mvdb_index* ix, CoalesceReq& req) {
             bool masked = false;
             for (auto it = ix->co_queue.begin(); it != ix->co_queue.end();) {
                 CoalesceReq* r = *it;
-                const bool would_mask = masked || r->mask != nullptr;
+                // filters that must be staged from host memory limit the batch to one scan launch;
+                // unfiltered queries and device-resident filters (mask handles) batch freely
+                const bool would_mask = masked || (r->mask != nullptr && r->handle == nullptr);
                 const size_t cap = single ? 1 : (would_mask ? 8 : size_t(ix->coalesce_max));
                 if (r->k == head->k && r->normalize == head->normalize && batch.size() < cap) {
                     batch.push_back(r);
@@ -1488,8 +1547,52 @@ static int coalesced_search(mvdb_index* ix, CoalesceReq& req) {
     return req.rc;
 }
 
+int mvdb_index_mask_create(mvdb_index* ix, const uint8_t* mask, uint64_t mask_rows, mvdb_mask** out) {
+    ENTER(ix);
+    if (!out) return fail(MVDB_ERR_ARG, "null out");
+    *out = nullptr;
+    if (!mask && mask_rows) return fail(MVDB_ERR_ARG, "null mask");
+    if (mask_rows > 0xFFFFFFF0ull) return fail(MVDB_ERR_ARG, "mask too long");
+    const size_t words = (mask_rows + 31) / 32, bytes = (mask_rows + 7) / 8;
+    std::vector<uint32_t> host(std::max<size_t>(words, 1), 0u);   // zero tail: rows past mask_rows are not admissible
+    if (bytes) memcpy(host.data(), mask, bytes);
+    if (mask_rows & 7) reinterpret_cast<uint8_t*>(host.data())[bytes - 1] &= uint8_t((1u << (mask_rows & 7)) - 1u);
+    mvdb_mask* m = new mvdb_mask{ix, nullptr, mask_rows, uint32_t(words)};
+    cudaError_t e = cudaMalloc(&m->dev, host.size() * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(m->dev, host.data(), host.size() * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(m->dev);
+        delete m;
+        return fail(e == cudaErrorMemoryAllocation ? MVDB_ERR_OOM : MVDB_ERR_CUDA, "mask upload failed: %s", cudaGetErrorString(e));
+    }
+    *out = m;
+    return MVDB_OK;
+}
+
+int mvdb_mask_destroy(mvdb_mask* m) {
+    if (!m) return MVDB_OK;
+    DeviceGuard guard(m->ix->device);
+    cudaFree(m->dev);
+    delete m;
+    return MVDB_OK;
+}
+
+static int search_entry(mvdb_index* ix, const float* q, int64_t nq, int64_t k, const uint8_t* mask, uint64_t mask_rows,
+                        const mvdb_mask* handle, int normalize_queries, float* D, int64_t* I);
+
+int mvdb_index_search_with_mask(mvdb_index* ix, const float* q, int64_t nq, int64_t k, const mvdb_mask* m,
+                                int normalize_queries, float* D, int64_t* I) {
+    if (m && m->ix != ix) return fail(MVDB_ERR_ARG, "mask handle belongs to another index");
+    return search_entry(ix, q, nq, k, nullptr, 0, m, normalize_queries, D, I);
+}
+
 int mvdb_index_search(mvdb_index* ix, const float* q, int64_t nq, int64_t k, const uint8_t* mask, uint64_t mask_rows,
                       int normalize_queries, float* D, int64_t* I) {
+    return search_entry(ix, q, nq, k, mask, mask_rows, nullptr, normalize_queries, D, I);
+}
+
+static int search_entry(mvdb_index* ix, const float* q, int64_t nq, int64_t k, const uint8_t* mask, uint64_t mask_rows,
+                        const mvdb_mask* handle, int normalize_queries, float* D, int64_t* I) {
     ENTER(ix);
     if (nq < 0 || k <= 0) return fail(MVDB_ERR_ARG, "need nq >= 0 and k > 0 (got nq=%lld k=%lld)", (long long)nq, (long long)k);
     if (nq == 0) return MVDB_OK;
@@ -1500,12 +1603,13 @@ int mvdb_index_search(mvdb_index* ix, const float* q, int64_t nq, int64_t k, con
         req.k = k;
         req.mask = mask;
         req.mask_rows = mask_rows;
+        req.handle = handle;
         req.normalize = normalize_queries ? 1 : 0;
         req.D = D;
         req.I = I;
         return coalesced_search(ix, req);
     }
-    return search_host_direct(ix, q, nq, k, mask, mask_rows, normalize_queries, D, I);
+    return search_host_direct(ix, q, nq, k, mask, mask_rows, normalize_queries, D, I, handle);
 }
 
 int mvdb_exchange_create(int device, int rank, int world, int k_max, int nq_max, mvdb_exchange** out) {

@@ -52,6 +52,7 @@ struct ScanParams {
     uint32_t sel_off, q_off, stage_off;  // byte offsets into dynamic shared memory
     uint32_t merge_off, merge_bytes;     // scratch for the last-CTA merge (the idle TMA ring, or a tail region)
     const uint32_t* qmask[8];    // per-query admissible bitmasks (coalesced searches; nullptr = none); multi kernel only
+    uint32_t qmask_bytes[8];     // bytes available behind qmask[i]; rows past them are not admissible
     int has_qmask;
     const struct XchgDev* xchg;  // fused cross-GPU exchange (nullptr = single GPU)
     uint64_t xchg_seq;           // sequence number of this launch (same on every rank, > 0)
@@ -587,7 +588,8 @@ __global__ void __launch_bounds__(kTma ? 288 : 256, (kTma || NQ >= 8) ? 1 : 2) s
             const float score = reduce8(acc[qi], lane);
             bool ok_q = ok;
             if (p.has_qmask && p.qmask[qi])   // coalesced single-query searches keep their own filters
-                ok_q = ok && ((reinterpret_cast<const uint8_t*>(p.qmask[qi])[tile] >> my_row) & 1u);
+                ok_q = ok && tile < p.qmask_bytes[qi] &&
+                       ((reinterpret_cast<const uint8_t*>(p.qmask[qi])[tile] >> my_row) & 1u);
             if (p.all_ord) {
                 if (leader && row < p.n)
                     p.all_ord[size_t(qi) * p.n + row] = (ok_q && score == score) ? score_to_ord(score) : 0u;

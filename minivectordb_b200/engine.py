@@ -40,6 +40,35 @@ def pack_mask(admissible: np.ndarray) -> np.ndarray:
     return np.packbits(np.asarray(admissible, dtype=bool), bitorder="little")
 
 
+class MaskHandle:
+    """A filter bitmask uploaded once and kept in HBM (mvdb_index_mask_create).  Pass it as
+    `mask=` to FlatIPEngine.search: no mask bytes move per query, and concurrent single-query
+    searches carrying handles are coalesced into one tensor-core batch."""
+
+    def __init__(self, engine: "FlatIPEngine", admissible):
+        a = np.asarray(admissible)
+        if a.dtype == np.bool_:
+            self.rows = int(a.shape[0])
+            packed = pack_mask(a)
+        else:
+            raise TypeError("MaskHandle needs a bool[n] array of admissible rows")
+        self._engine = engine
+        self._h = ctypes.c_void_p()
+        N.check(N.lib().mvdb_index_mask_create(engine.handle, packed.ctypes.data if packed.size else None, self.rows,
+                                               ctypes.byref(self._h)))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            N.lib().mvdb_mask_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class FlatIPEngine:
     def __init__(self, d: int, device: int = 0, capacity_hint: int = 0):
         self._h = ctypes.c_void_p()
@@ -146,6 +175,10 @@ class FlatIPEngine:
         nq = q.shape[0]
         D = np.empty((nq, k), dtype=np.float32)
         I = np.empty((nq, k), dtype=np.int64)
+        if isinstance(mask, MaskHandle):
+            N.check(N.lib().mvdb_index_search_with_mask(self._h, q.ctypes.data, nq, k, mask._h, int(bool(normalize)),
+                                                        D.ctypes.data, I.ctypes.data))
+            return D, I
         mptr, mrows = None, 0
         if mask is not None:
             mask = np.asarray(mask)
@@ -161,6 +194,10 @@ class FlatIPEngine:
         N.check(N.lib().mvdb_index_search(self._h, q.ctypes.data, nq, k, mptr, mrows,
                                           int(bool(normalize)), D.ctypes.data, I.ctypes.data))
         return D, I
+
+    def mask_handle(self, admissible) -> MaskHandle:
+        """Upload a bool[n] filter once; reuse it across searches."""
+        return MaskHandle(self, admissible)
 
     def debug_gemm_scores(self, q) -> np.ndarray:
         """Raw bf16 tensor-core scores [nq, ntotal] (test hook for the tcgen05 GEMM)."""

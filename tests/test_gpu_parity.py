@@ -398,3 +398,60 @@ def test_coalesced_concurrent_searches_equal_direct_ones(mv):
     [t.join() for t in ts]
     assert not errs, errs[:1]
     eng.close()
+
+
+def test_mask_handles_and_coalesced_filtered_batches(mv):
+    """Device-resident filters: same results as host-supplied masks, alone, in explicit
+    batches (nq > 1, one common handle) and when many threads each bring their own handle
+    (coalesced into a tensor-core batch with per-query filters)."""
+    import threading
+    n, d, k = 80_000, 384, 10
+    x, q = _data(n, d, 96, seed=21)
+    eng = mv.FlatIPEngine(d)
+    eng.add(x[:70_000])
+    rng = np.random.default_rng(4)
+    adms = [rng.random(70_000) < f for f in (0.5, 0.1, 0.9, 0.001)]
+    handles = [eng.mask_handle(a) for a in adms]
+    eng.add(x[70_000:])           # rows appended after the handles were made are not admissible through them
+    eng.remove_rows(np.arange(5, 70_000, 13))
+    live = np.ones(n, dtype=bool)
+    live[np.arange(5, 70_000, 13)] = False
+    for a, h in zip(adms, handles):
+        full = np.zeros(n, dtype=bool)
+        full[:70_000] = a
+        D, I = eng.search(q[:3], k, mask=h)            # nq > 1: common handle
+        _check(x, q[:3], k, D, I, full & live)
+        D1, I1 = eng.search(q[:1], k, mask=h)          # single query
+        assert np.array_equal(I1[0], I[0]) and np.array_equal(D1[0], D[0])
+        D40, I40 = eng.search(q[:40], k, mask=h)       # tensor-core batch with a common filter
+        _check(x, q[:40], k, D40, I40, full & live)
+    want = []
+    for i in range(96):
+        full = np.zeros(n, dtype=bool)
+        full[:70_000] = adms[i % 4]
+        want.append(O.search_masked(x, full & live, q[i:i + 1], k))
+    got = [None] * 96
+    errs = []
+
+    def worker(t):
+        try:
+            for i in range(t, 96, 32):
+                got[i] = eng.search(q[i:i + 1], k, mask=handles[i % 4] if i % 5 else None)
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=worker, args=(t,)) for t in range(32)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs[:1]
+    for i in range(96):
+        if i % 5:
+            full = np.zeros(n, dtype=bool)
+            full[:70_000] = adms[i % 4]
+            rep = O.classify_parity(x, q[i:i + 1], got[i][1], got[i][0], want[i][1], want[i][0], admissible=full & live)
+        else:
+            Dr, Ir = O.search_masked(x, live, q[i:i + 1], k)
+            rep = O.classify_parity(x, q[i:i + 1], got[i][1], got[i][0], Ir, Dr, admissible=live)
+        assert rep["ok"], (i, rep)
+    [h.close() for h in handles]
+    eng.close()

@@ -18,11 +18,13 @@ d = int(sys.argv[2]) if len(sys.argv) > 2 else 768
 secs = float(sys.argv[3]) if len(sys.argv) > 3 else 20.0
 k = 10
 out = []
-for coalesce, nthreads in ((0, 8), (1, 8), (1, 32)):
+for coalesce, nthreads, handles in ((0, 8, 0), (1, 8, 0), (1, 8, 1), (1, 32, 1), (1, 64, 1)):
     eng = mv.FlatIPEngine(d, capacity_hint=n + 2_000_000)
     eng.add_synthetic(1234, 0, n, 0, True)
     eng.set_option("coalesce", coalesce)
     masks = [mv.pack_mask(synth.synth_mask(100 + i, n, 0.5)) for i in range(4)]
+    if handles:
+        masks_h = [eng.mask_handle(synth.synth_mask(100 + i, n, 0.5)) for i in range(4)]
     stop = threading.Event()
     lat = [[] for _ in range(nthreads)]
     counts = dict(ins=0, dele=0)
@@ -35,7 +37,10 @@ for coalesce, nthreads in ((0, 8), (1, 8), (1, 32)):
                 q = rng.standard_normal((1, d)).astype(np.float32)
                 a = time.perf_counter()
                 if rng.random() < 0.5:   # 50 % of the queries carry a metadata filter
-                    eng.search(q, k, mask=masks[int(rng.integers(0, 4))], mask_rows=n, normalize=True)
+                    if handles:
+                        eng.search(q, k, mask=masks_h[int(rng.integers(0, 4))], normalize=True)
+                    else:
+                        eng.search(q, k, mask=masks[int(rng.integers(0, 4))], mask_rows=n, normalize=True)
                 else:
                     eng.search(q, k, normalize=True)
                 lat[t].append(time.perf_counter() - a)
@@ -70,7 +75,7 @@ for coalesce, nthreads in ((0, 8), (1, 8), (1, 32)):
     [t.join() for t in ts]
     dt = time.perf_counter() - t0
     all_lat = np.concatenate([np.asarray(x) for x in lat if x])
-    rec = dict(rows=n, dim=d, k=k, query_threads=nthreads, coalesce=coalesce, seconds=dt, queries=int(all_lat.size),
+    rec = dict(rows=n, dim=d, k=k, query_threads=nthreads, coalesce=coalesce, mask_handles=handles, seconds=dt, queries=int(all_lat.size),
                qps=all_lat.size / dt, p50_ms=float(np.median(all_lat) * 1e3), p99_ms=float(np.percentile(all_lat, 99) * 1e3),
                inserted=counts["ins"], deleted=counts["dele"], ntotal=eng.ntotal, nlive=eng.nlive, errors=len(errs),
                scan_bytes=n * eng.device_view()[1] * 4)
