@@ -46,8 +46,10 @@ constexpr uint32_t kTmemCols = 512;
 
 struct GemmParams {
     int64_t nq;            // queries
-    uint32_t row0, row1;   // rows [row0, row1) of the index are scanned by this launch
-    uint32_t n_valid;      // rows >= n_valid do not exist (mask snapshot / ntotal)
+    uint32_t row0, row1;   // SAMPLED rows [row0, row1) are scanned by this launch
+    uint32_t n_valid;      // sampled rows >= n_valid do not exist
+    uint32_t row_stride;   // sampled row i is index row i * row_stride (the tensor map and the
+                           // bitmasks handed to this launch are already in sampled-row space)
     int d;
     const uint32_t* live;  // bitmasks over rows (nullptr = none)
     const uint32_t* mask;
@@ -278,11 +280,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                         uint32_t v[32];
                         tmem_ld_32x32(t_lane + uint32_t(32 * g), v);
                         uint32_t m = 0;
-                        const uint32_t low0 = 0xFFFFFFFFu - (tile_row0 + 32 * g);   // ~row of column 0 of this group
+                        // ~row of column 0 of this group; column j is index row (tile_row0 + 32g + j) * stride
+                        const uint32_t low0 = 0xFFFFFFFFu - (tile_row0 + 32 * g) * p.row_stride;
 #pragma unroll
                         for (int j = 0; j < 32; j++) {
                             const float s = __uint_as_float(v[j]);
-                            const uint64_t key = (uint64_t(score_to_ord(s)) << 32) | uint64_t(low0 - uint32_t(j));
+                            const uint64_t key = (uint64_t(score_to_ord(s)) << 32) | uint64_t(low0 - uint32_t(j) * p.row_stride);
                             const uint32_t pass = uint32_t(key > thr) & uint32_t(s == s);   // NaN never passes
                             m |= pass << j;
                         }
@@ -309,7 +312,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                             for (int j = 0; j < 32; j++) {
                                 if ((m >> j) & 1u) {
                                     if (pos < p.cand_cap)
-                                        p.cand[size_t(q) * p.cand_cap + pos] = make_key(__uint_as_float(v[j]), tile_row0 + 32 * g + j);
+                                        p.cand[size_t(q) * p.cand_cap + pos] =
+                                            make_key(__uint_as_float(v[j]), (tile_row0 + 32 * g + j) * p.row_stride);
                                     pos++;
                                 }
                             }
@@ -380,6 +384,59 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restri
         norm = 1.0f;
     }
     if (lane == 0) qnorm[warp] = norm;
+}
+
+// Bitmask in sampled-row space: bit i of dst = AND over the given source masks of bit (i * stride).
+// srcs: up to two common masks (live, filter; nullptr = all ones).  One thread per output word.
+__global__ void sample_mask_kernel(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, uint32_t n_src_rows,
+                                   uint32_t stride, uint32_t* __restrict__ dst, uint32_t m_rows) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= (m_rows + 31) / 32) return;
+    uint32_t out = 0;
+    for (int j = 0; j < 32; j++) {
+        const uint64_t i = uint64_t(w) * 32 + j;
+        if (i >= m_rows) break;
+        const uint64_t r = i * stride;
+        if (r >= n_src_rows) break;
+        uint32_t bit = 1u;
+        if (a) bit &= (a[r >> 5] >> (r & 31)) & 1u;
+        if (b) bit &= (b[r >> 5] >> (r & 31)) & 1u;
+        out |= bit << j;
+    }
+    dst[w] = out;
+}
+// Same for per-query masks: query q's sampled mask goes to dst + q * words_per_query (all zero
+// and pointer left null when the query has no filter).  grid.y = query.
+__global__ void sample_qmask_kernel(const uint32_t* const* __restrict__ src, const uint32_t* __restrict__ src_words,
+                                    uint32_t stride, uint32_t* __restrict__ dst, uint32_t m_rows, uint32_t words_per_query) {
+    const uint32_t q = blockIdx.y;
+    const uint32_t* s = src[q];
+    if (!s) return;
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= (m_rows + 31) / 32) return;
+    const uint64_t src_rows = uint64_t(src_words[q]) * 32;
+    uint32_t out = 0;
+    for (int j = 0; j < 32; j++) {
+        const uint64_t i = uint64_t(w) * 32 + j;
+        if (i >= m_rows) break;
+        const uint64_t r = i * stride;
+        if (r >= src_rows) break;
+        out |= ((s[r >> 5] >> (r & 31)) & 1u) << j;
+    }
+    dst[size_t(q) * words_per_query + w] = out;
+}
+// pointer / length tables for a level's sampled per-query masks
+__global__ void qmask_table_kernel(const uint32_t* const* __restrict__ src, uint32_t* dst_base, uint32_t words_per_query,
+                                   const uint32_t** out_ptr, uint32_t* out_words, int64_t nq) {
+    int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    out_ptr[q] = src[q] ? dst_base + size_t(q) * words_per_query : nullptr;
+    out_words[q] = src[q] ? words_per_query : 0u;
+}
+// a new sampling level starts from an empty candidate list but keeps the thresholds
+__global__ void reset_counts_kernel(unsigned int* cnt, int64_t nq) {
+    int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < nq) cnt[i] = 0;
 }
 
 __global__ void init_batch_state_kernel(uint64_t* thr, unsigned int* cnt, unsigned int* overflow, int64_t nq) {

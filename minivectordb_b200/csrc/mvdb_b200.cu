@@ -302,6 +302,14 @@ struct mvdb_workspace {
     size_t b_qmptr_cap = 0;
     uint32_t* b_qmwords = nullptr;
     size_t b_qmwords_cap = 0;
+    uint32_t* b_lmask = nullptr;      // sampled-row-space masks of the current level
+    size_t b_lmask_cap = 0;
+    uint32_t* b_lqmask = nullptr;
+    size_t b_lqmask_cap = 0;
+    const uint32_t** b_lqptr = nullptr;
+    size_t b_lqptr_cap = 0;
+    uint32_t* b_lqwords = nullptr;
+    size_t b_lqwords_cap = 0;
     // host-buffer path
     float* q_dev = nullptr;
     size_t q_cap = 0;
@@ -594,6 +602,7 @@ static int ws_scratch(mvdb_workspace* ws) {
 // ---------------------------------------------------------------------------
 // batched tensor-core path (gemm_tc.cuh)
 // ---------------------------------------------------------------------------
+// rows x d bf16 matrix whose consecutive (sampled) rows are ld_elems elements apart
 static int encode_bf16_map(CUtensorMap* tm, const void* base, uint64_t rows, int d, int64_t ld_elems, uint32_t box_rows) {
     TensorMapEncodeTiledFn enc = tensor_map_encoder();
     if (!enc) return fail(MVDB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
@@ -627,15 +636,15 @@ static int ensure_shadow(mvdb_index* ix, uint64_t n) {
 }
 
 static constexpr uint32_t kCandCap = 8192;      // candidate slots per query
-static constexpr uint32_t kFirstChunk = 2048;   // rows scanned before the first threshold exists
+static constexpr uint32_t kFirstLevel = 4096;   // sampled rows of the coarsest level (all admissible ones become candidates)
 
 static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, int64_t nq, int64_t k,
                       const uint32_t* mask_dev, uint64_t mask_rows, int normalize_q, int64_t label_offset,
                       float* D_dev, int64_t* I_dev, cudaStream_t stream, mvdb_exchange* xch,
                       const QMaskRef* qmasks = nullptr);
 
-// Q[nq,d] against rows [0,n): bf16 GEMM on tcgen05 with threshold-filter epilogue,
-// geometric row chunks (thresholds tighten between chunks), optional exact re-scoring.
+// Q[nq,d] against rows [0,n): bf16 GEMM on tcgen05 with threshold-filter epilogue over
+// multi-resolution strided samples (thresholds tighten level by level), optional exact re-scoring.
 // dense_out != nullptr: debug mode, write every bf16-GEMM score to dense_out[nq][n].
 static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, int64_t nq, int64_t k,
                        const uint32_t* mask_dev, uint32_t n, int normalize_q, int64_t label_offset, float* D_dev,
@@ -661,7 +670,6 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
 
     CUtensorMap tmQ, tmX;
     RC_OK(encode_bf16_map(&tmQ, ws->b_q16, uint64_t(nq), ix->d, ix->ld16, kGemmBM));
-    RC_OK(encode_bf16_map(&tmX, ix->mat16.ptr(), n, ix->d, ix->ld16, kGemmBN));
     CU_OK(cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes)));
     CU_OK(cudaFuncSetAttribute(cand_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kCandCap * 8)));
 
@@ -678,6 +686,7 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
         slack_unit = float(2.0 * eps_unit * std::sqrt(std::max(double(max_norm2), 1e-30)) * 1.0001);
     }
 
+    const uint32_t* live_dev = ix->ndead.load(std::memory_order_acquire) ? static_cast<const uint32_t*>(ix->live.ptr()) : nullptr;
     GemmParams gp = {};
     if (qmasks) {
         // per-query filters: thread <-> query in the epilogue, so each thread reads its own words
@@ -692,14 +701,9 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
         CU_OK(cudaMemcpyAsync(ws->b_qmptr, ptrs.data(), size_t(nq) * 8, cudaMemcpyHostToDevice, stream));
         CU_OK(cudaMemcpyAsync(ws->b_qmwords, wrds.data(), size_t(nq) * 4, cudaMemcpyHostToDevice, stream));
         CU_OK(cudaStreamSynchronize(stream));   // the host vectors go out of scope
-        gp.qmask = ws->b_qmptr;
-        gp.qmask_words = ws->b_qmwords;
     }
     gp.nq = nq;
-    gp.n_valid = n;
     gp.d = ix->d;
-    gp.live = ix->ndead.load(std::memory_order_acquire) ? static_cast<const uint32_t*>(ix->live.ptr()) : nullptr;
-    gp.mask = mask_dev;
     gp.thr = ws->b_thr;
     gp.cand = ws->b_cand;
     gp.cand_cnt = ws->b_cnt;
@@ -707,13 +711,65 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
     gp.dense = dense_out;
     gp.dense_ld = n;
     const uint32_t n_qb = uint32_t((nq + kGemmBM - 1) / kGemmBM);
-    uint32_t done = 0;
-    while (done < n) {
-        uint32_t chunk = dense_out ? n : std::max(kFirstChunk, done);
-        chunk = std::min<uint32_t>(uint32_t(align_up(chunk, kGemmBN)), uint32_t(align_up(n - done, kGemmBN)));
-        gp.row0 = done;
-        gp.row1 = done + chunk;
-        const uint64_t tiles = uint64_t(chunk / kGemmBN) * n_qb;
+
+    // Multi-resolution strided sampling.  Level strides are powers of 16 down to 1: the
+    // coarsest level holds <= kFirstLevel rows spread evenly over the whole index (every
+    // admissible one becomes a candidate and fixes a first threshold per query), each finer
+    // level contains the previous one (so its threshold stays a valid lower bound), restarts
+    // its candidate list and admits ~16 k rows per query; the last level is the full matrix.
+    // Unlike contiguous chunks this does not depend on the ORDER of the rows: a deleted or
+    // filtered-out prefix (time-ordered data with a date filter, churn that deletes the oldest
+    // rows) cannot flood the candidate lists.  Extra flops: 1/16 + 1/256 + ... = 6.7 %.
+    std::vector<uint32_t> strides;
+    {
+        uint32_t s0 = 1;
+        while (!dense_out && (uint64_t(n) + s0 - 1) / s0 > kFirstLevel) s0 *= 16;
+        for (uint32_t st_ = s0;; st_ /= 16) {
+            strides.push_back(st_);
+            if (st_ == 1) break;
+        }
+    }
+    for (size_t lv = 0; lv < strides.size(); lv++) {
+        const uint32_t S = strides[lv];
+        const uint32_t m = uint32_t((uint64_t(n) + S - 1) / S);   // sampled rows of this level
+        const uint32_t words = (m + 31) / 32;
+        RC_OK(encode_bf16_map(&tmX, ix->mat16.ptr(), m, ix->d, ix->ld16 * int64_t(S), kGemmBN));
+        gp.row_stride = S;
+        gp.row0 = 0;
+        gp.row1 = uint32_t(align_up(m, kGemmBN));
+        gp.n_valid = m;
+        gp.live = live_dev;
+        gp.mask = mask_dev;
+        gp.qmask = qmasks ? ws->b_qmptr : nullptr;
+        gp.qmask_words = qmasks ? ws->b_qmwords : nullptr;
+        if (S > 1) {
+            // bring the bitmasks into this level's sampled-row space
+            if (live_dev || mask_dev) {
+                RC_OK(grow_dev(&ws->b_lmask, &ws->b_lmask_cap, size_t(words)));
+                sample_mask_kernel<<<(words + 255) / 256, 256, 0, stream>>>(live_dev, mask_dev, n, S, ws->b_lmask, m);
+                LAUNCHED();
+                gp.live = nullptr;
+                gp.mask = ws->b_lmask;
+            }
+            if (qmasks) {
+                RC_OK(grow_dev(&ws->b_lqmask, &ws->b_lqmask_cap, size_t(words) * nq));
+                RC_OK(grow_dev(&ws->b_lqptr, &ws->b_lqptr_cap, size_t(nq)));
+                RC_OK(grow_dev(&ws->b_lqwords, &ws->b_lqwords_cap, size_t(nq)));
+                sample_qmask_kernel<<<dim3((words + 255) / 256, unsigned(nq)), 256, 0, stream>>>(ws->b_qmptr, ws->b_qmwords, S,
+                                                                                              ws->b_lqmask, m, words);
+                LAUNCHED();
+                qmask_table_kernel<<<unsigned((nq + 255) / 256), 256, 0, stream>>>(ws->b_qmptr, ws->b_lqmask, words, ws->b_lqptr,
+                                                                                 ws->b_lqwords, nq);
+                LAUNCHED();
+                gp.qmask = ws->b_lqptr;
+                gp.qmask_words = ws->b_lqwords;
+            }
+        }
+        if (lv > 0) {
+            reset_counts_kernel<<<unsigned((nq + 255) / 256), 256, 0, stream>>>(ws->b_cnt, nq);
+            LAUNCHED();
+        }
+        const uint64_t tiles = uint64_t(gp.row1 / kGemmBN) * n_qb;
         const unsigned grid = unsigned(std::min<uint64_t>(uint64_t(ix->sm_count), tiles));
         gemm_topk_kernel<<<grid, 256, kGemmSmemBytes, stream>>>(tmQ, tmX, gp);
         LAUNCHED();
@@ -722,7 +778,6 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
                                                                            int(k), mode == 1 ? ws->b_qnorm : nullptr, slack_unit);
             LAUNCHED();
         }
-        done += chunk;
     }
     CU_OK(cudaGetLastError());
     if (dense_out) return MVDB_OK;
@@ -932,6 +987,10 @@ static void ws_free(mvdb_workspace* ws) {
     cudaFree(ws->b_cand);
     cudaFree(ws->b_qmptr);
     cudaFree(ws->b_qmwords);
+    cudaFree(ws->b_lmask);
+    cudaFree(ws->b_lqmask);
+    cudaFree(ws->b_lqptr);
+    cudaFree(ws->b_lqwords);
     cudaFree(ws->q_dev);
     cudaFree(ws->mask_dev);
     cudaFree(ws->D_dev);

@@ -114,3 +114,42 @@ def test_batched_path_follows_appends(mv):
     rep = O.classify_parity(x, q, I, D, Ir, Dr)
     assert rep["ok"], rep
     eng.close()
+
+
+def test_batched_is_robust_to_row_order_and_dead_prefixes(mv):
+    """The threshold schedule samples rows at power-of-16 strides, so neither a deleted /
+    filtered-out PREFIX (time-ordered data with a date filter, churn deleting the oldest
+    rows) nor rows sorted by similarity may flood the candidate lists."""
+    n, d, nq, k = 120_000, 128, 48, 10
+    x, q = _data(n, d, nq, seed=31)
+    eng = mv.FlatIPEngine(d)
+    eng.add(x)
+    eng.remove_rows(np.arange(0, 70_000))             # the first 58 % of the rows are tombstones
+    live = np.ones(n, dtype=bool)
+    live[:70_000] = False
+    D, I = eng.search(q, k)
+    Dr, Ir = O.search_masked(x, live, q, k)
+    assert O.classify_parity(x, q, I, D, Ir, Dr, admissible=live)["ok"]
+    late = np.zeros(n, dtype=bool)
+    late[100_000:] = True                             # filter admits only the newest rows
+    D, I = eng.search(q, k, mask=late)
+    Dr, Ir = O.search_masked(x, late, q, k)
+    assert O.classify_parity(x, q, I, D, Ir, Dr, admissible=late)["ok"]
+    eng.set_option("batch_mode", 0)
+    Ds, Is = eng.search(q, k, mask=late)
+    assert np.array_equal(I, Is) and np.array_equal(D, Ds)
+    eng.close()
+
+
+def test_batched_adversarial_periodic_filter_overflows_and_falls_back(mv):
+    """Only ODD rows admissible: every sampling level (even strides) sees nothing, the last
+    level floods the candidate lists, and the queries are redone by the exact scan."""
+    n, d, nq, k = 40_000, 64, 40, 10
+    x, q = _data(n, d, nq, seed=33)
+    eng = mv.FlatIPEngine(d)
+    eng.add(x)
+    odd = (np.arange(n) % 2) == 1
+    D, I = eng.search(q, k, mask=odd)
+    Dr, Ir = O.search_masked(x, odd, q, k)
+    assert O.classify_parity(x, q, I, D, Ir, Dr, admissible=odd)["ok"]
+    eng.close()
