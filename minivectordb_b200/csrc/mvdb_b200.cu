@@ -636,7 +636,7 @@ static int ensure_shadow(mvdb_index* ix, uint64_t n) {
 }
 
 static constexpr uint32_t kCandCap = 8192;      // candidate slots per query
-static constexpr uint32_t kFirstLevel = 4096;   // sampled rows of the coarsest level (all admissible ones become candidates)
+static constexpr uint32_t kFirstLevel = 2048;   // sampled rows of the coarsest level (all admissible ones become candidates)
 
 static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, int64_t nq, int64_t k,
                       const uint32_t* mask_dev, uint64_t mask_rows, int normalize_q, int64_t label_offset,
@@ -769,14 +769,31 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
             reset_counts_kernel<<<unsigned((nq + 255) / 256), 256, 0, stream>>>(ws->b_cnt, nq);
             LAUNCHED();
         }
-        const uint64_t tiles = uint64_t(gp.row1 / kGemmBN) * n_qb;
-        const unsigned grid = unsigned(std::min<uint64_t>(uint64_t(ix->sm_count), tiles));
-        gemm_topk_kernel<<<grid, 256, kGemmSmemBytes, stream>>>(tmQ, tmX, gp);
-        LAUNCHED();
-        if (!dense_out) {
-            cand_update_kernel<<<unsigned(nq), 256, kCandCap * 8, stream>>>(ws->b_cand, ws->b_cnt, ws->b_thr, ws->b_ovf, kCandCap,
-                                                                           int(k), mode == 1 ? ws->b_qnorm : nullptr, slack_unit);
+        // The full-matrix level runs as 4 contiguous pieces (1/8, 1/8, 1/4, 1/2) with a threshold
+        // refresh after each: the sampled levels already bound what can pass (<= ~16 k per
+        // query whatever the row order), the refreshes cut that to ~5 k.
+        std::vector<uint32_t> cuts;
+        const uint32_t rows_al = gp.row1;
+        if (S == 1 && strides.size() > 1 && rows_al >= 64 * kGemmBN) {
+            const uint32_t e = uint32_t(align_up(rows_al / 8, kGemmBN));
+            cuts = {e, 2 * e, 4 * e, rows_al};
+        } else {
+            cuts = {rows_al};
+        }
+        uint32_t lo = 0;
+        for (uint32_t hi : cuts) {
+            gp.row0 = lo;
+            gp.row1 = hi;
+            const uint64_t tiles = uint64_t((hi - lo) / kGemmBN) * n_qb;
+            const unsigned grid = unsigned(std::min<uint64_t>(uint64_t(ix->sm_count), tiles));
+            gemm_topk_kernel<<<grid, 256, kGemmSmemBytes, stream>>>(tmQ, tmX, gp);
             LAUNCHED();
+            if (!dense_out) {
+                cand_update_kernel<<<unsigned(nq), 256, kCandCap * 8, stream>>>(ws->b_cand, ws->b_cnt, ws->b_thr, ws->b_ovf, kCandCap,
+                                                                               int(k), mode == 1 ? ws->b_qnorm : nullptr, slack_unit);
+                LAUNCHED();
+            }
+            lo = hi;
         }
     }
     CU_OK(cudaGetLastError());
