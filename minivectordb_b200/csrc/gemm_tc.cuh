@@ -494,7 +494,9 @@ __global__ void __launch_bounds__(256) cand_update_kernel(uint64_t* cand, unsign
     for (uint32_t i = threadIdx.x; i < keep; i += blockDim.x) src[i] = a[i];
     if (threadIdx.x == 0) {
         cnt[q] = keep;
-        thr[q] = new_thr;
+        // a threshold, once established (by a coarser sampling level or an earlier piece), is a
+        // valid lower bound for good: a piece that yields fewer than k hits must not lower it
+        if (new_thr > thr[q]) thr[q] = new_thr;
     }
 }
 
