@@ -27,13 +27,13 @@ reference does (VDB:45, 49-55).
 from __future__ import annotations
 
 import threading
-from collections import defaultdict
+from collections import OrderedDict, defaultdict
 from typing import List, Optional
 
 import numpy as np
 
 from . import rerank as _rerank
-from .engine import FlatIPEngine, pack_mask
+from .engine import FlatIPEngine
 from .filters import FilterIndex
 
 
@@ -90,6 +90,7 @@ class EmbeddingsView:
 
 
 class GpuStore:
+    MASK_CACHE_ENTRIES = 16      # device-resident filter masks kept per database
     COMPACT_MIN_DEAD = 4096      # do not bother compacting below this many tombstones
     COMPACT_DEAD_FRACTION = 0.25
 
@@ -111,6 +112,9 @@ class GpuStore:
         self._ever_stored = False
         self._active_searches = 0
         self._views = None               # cached (id_map, inverse_id_map, metadata, unique_ids)
+        self._version = 0                # bumped by every mutation: invalidates cached filter masks
+        self._mask_cache = OrderedDict()  # filter repr -> (version, count, per-partition device-resident masks)
+        self._mask_seen = OrderedDict()   # filter repr -> version at which it was last evaluated
         self._embeddings_changed = False  # kept for API parity (VDB:18); True while rows wait on the host
 
     # ------------------------------------------------------------------ views
@@ -198,6 +202,7 @@ class GpuStore:
         self._ever_stored = True
         self._embeddings_changed = True
         self._views = None
+        self._version += 1
 
     def _remove(self, uid) -> None:
         """Caller holds the lock and has checked that uid exists."""
@@ -215,6 +220,7 @@ class GpuStore:
                     del self.inverted_index[key]
         self._embeddings_changed = True
         self._views = None
+        self._version += 1
 
     # ------------------------------------------------------------------ flush
     def _flush(self) -> None:
@@ -266,6 +272,8 @@ class GpuStore:
         for g, meta in enumerate(self._g_meta):
             self._filters.add_row(g, meta)
         self._views = None
+        self._version += 1
+        self._mask_cache.clear()
 
     # ----------------------------------------------------------------- search
     def _search(self, embedding, metadata_filter, exclude_filter, or_filters, k, autocut):
@@ -276,31 +284,59 @@ class GpuStore:
             self._flush()
             n = self._g_n
             live = self._g_live[:n]
+            jobs = None
             if metadata_filter or exclude_filter or or_filters:
-                adm = self._filters.admissible(live, metadata_filter, exclude_filter, or_filters)
+                # A filter that repeats (same expression, no mutation since) reuses its
+                # device-resident masks: no evaluation, no upload, and concurrent callers
+                # can be coalesced into one tensor-core batch with per-query filters.
+                try:
+                    key = repr((metadata_filter, exclude_filter, or_filters))
+                except Exception:  # noqa: BLE001 - unreprable operands: just do not cache
+                    key = None
+                hit = self._mask_cache.get(key) if key is not None else None
+                if hit is not None and hit[0] == self._version:
+                    self._mask_cache.move_to_end(key)
+                    count, jobs = hit[1], hit[2]
+                    adm = False  # placeholder: "filtered"
+                else:
+                    adm = self._filters.admissible(live, metadata_filter, exclude_filter, or_filters)
             else:
                 adm = None
-            count = self._n_live if adm is None else int(adm.sum())
+            if jobs is None:
+                count = self._n_live if adm is None else int(adm.sum())
             if count == 0:
                 return [], [], []
-            if adm is not None and count == self._n_live:
-                adm = None  # every live row admissible: plain search (VDB:495-497)
-            jobs = []
-            for part in self._parts:
-                if part.engine is None or part.flushed == 0:
-                    continue
-                if adm is None:
-                    jobs.append((part, part.gids, None, 0))
-                else:
-                    pm = adm[part.gids_np()] if len(self._parts) > 1 or part.flushed != n else adm
-                    jobs.append((part, part.gids, pack_mask(pm), part.flushed))
+            if jobs is None:
+                if adm is not None and count == self._n_live:
+                    adm = None  # every live row admissible: plain search (VDB:495-497)
+                jobs = []
+                for part in self._parts:
+                    if part.engine is None or part.flushed == 0:
+                        continue
+                    if adm is None:
+                        jobs.append((part, part.gids, None))
+                    else:
+                        pm = adm[part.gids_np()] if len(self._parts) > 1 or part.flushed != n else adm
+                        # a filter seen for the first time travels as host bytes (no device
+                        # allocation); when it comes back it is promoted to a resident handle
+                        repeat = key is not None and self._mask_seen.get(key) == self._version
+                        jobs.append((part, part.gids, part.engine.mask_handle(pm) if repeat else pm))
+                if adm is not None and key is not None:
+                    if self._mask_seen.get(key) == self._version:
+                        self._mask_cache[key] = (self._version, count, jobs)
+                        while len(self._mask_cache) > self.MASK_CACHE_ENTRIES:
+                            self._mask_cache.popitem(last=False)  # handles are freed when their last user drops them
+                    else:
+                        self._mask_seen[key] = self._version
+                        while len(self._mask_seen) > 4 * self.MASK_CACHE_ENTRIES:
+                            self._mask_seen.popitem(last=False)
             g_uid, g_meta, g_live = self._g_uid, self._g_meta, self._g_live
             self._active_searches += 1
         try:
             search_k = min(int(k), count)  # VDB:489-492
             cands = []
-            for part, gids, packed, mrows in jobs:
-                D, I = part.engine.search(q, search_k, mask=packed, mask_rows=mrows, normalize=True)
+            for part, gids, handle in jobs:
+                D, I = part.engine.search(q, search_k, mask=handle, normalize=True)
                 for slot, dist in zip(I[0], D[0]):
                     if slot == -1:
                         continue  # VDB:500

@@ -869,7 +869,12 @@ static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, in
     if (qmasks)
         for (int64_t i = 0; i < nq; i++) any_qmask |= qmasks[i].dev != nullptr;
     if (any_qmask && k > ix->fused_k_max) return fail(MVDB_ERR_ARG, "per-query masks need k <= %d", ix->fused_k_max);
-    if (!xch && ix->batch_mode != 0 && nq >= ix->batch_min_nq && k <= 128 && tensor_map_encoder() != nullptr)
+    // Large batches always go to the tensor cores.  On big matrices even 2..8 queries do: the
+    // bf16 shadow is half the bytes of the fp32 matrix, so one shadow pass (+ ~0.5 ms of fixed
+    // cost, + exact re-scoring) beats the fp32 multi-query scan once a pass costs ~1 ms.
+    const bool big_matrix = uint64_t(n) * uint64_t(ix->ld) * 4 >= (uint64_t(6) << 30);
+    if (!xch && ix->batch_mode != 0 && (nq >= ix->batch_min_nq || (nq >= 2 && big_matrix)) && k <= 128 &&
+        tensor_map_encoder() != nullptr)
         return run_batched(ix, ws, q_dev, nq, k, mask_dev, n, normalize_q, label_offset, D_dev, I_dev, stream,
                            ix->batch_mode, nullptr, any_qmask ? qmasks : nullptr);
     RC_OK(ws_scratch(ws));

@@ -57,5 +57,8 @@ class FakeEngine:
             adm &= full
         return O.search_masked(self.x, adm, q, int(k))
 
+    def mask_handle(self, admissible):
+        return np.asarray(admissible, dtype=bool).copy()
+
     def close(self):
         pass
