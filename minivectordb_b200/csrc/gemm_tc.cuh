@@ -60,6 +60,7 @@ struct GemmParams {
     uint64_t* cand;        // [nq][cand_cap] keys (bf16-score image << 32 | ~row)
     unsigned int* cand_cnt;  // [nq]
     uint32_t cand_cap;
+    int l2_hint;           // 0 none, 1 keep X tiles (evict_last), 2 keep X and Q
     // debug: dense scores [nq][n_total] (nullptr in production)
     float* dense;
     int64_t dense_ld;
@@ -71,6 +72,14 @@ __device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* m
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
             smem_u32(dst_smem)),
         "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_hint(void* dst_smem, const CUtensorMap* map, int c0, int c1, uint64_t* bar,
+                                                 uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1, {%2, %3}], [%4], %5;" ::"r"(smem_u32(dst_smem)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
@@ -183,6 +192,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     if (warp == 0) {
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
+            const uint64_t keep = policy_evict_last();
             for (uint32_t t = t_lo; t < t_hi; t++) {
                 const uint32_t xt = t / n_qb, qb = t % n_qb;
                     for (uint32_t kb = 0; kb < n_kb; kb++) {
@@ -190,8 +200,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                         uint8_t* sA = smem + stage * kGemmStageBytes;
                         uint8_t* sB = sA + kGemmABytes;
                         mbar_arrive_expect_tx(&bars->full[stage], kGemmStageBytes);
-                        tma_load_2d(sA, &tmQ, int(kb * kGemmBK), int(qb * kGemmBM), &bars->full[stage]);
-                        tma_load_2d(sB, &tmX, int(kb * kGemmBK), int(p.row0 + xt * kGemmBN), &bars->full[stage]);
+                        if (p.l2_hint >= 2) tma_load_2d_hint(sA, &tmQ, int(kb * kGemmBK), int(qb * kGemmBM), &bars->full[stage], keep);
+                        else tma_load_2d(sA, &tmQ, int(kb * kGemmBK), int(qb * kGemmBM), &bars->full[stage]);
+                        if (p.l2_hint >= 1) tma_load_2d_hint(sB, &tmX, int(kb * kGemmBK), int(p.row0 + xt * kGemmBN), &bars->full[stage], keep);
+                        else tma_load_2d(sB, &tmX, int(kb * kGemmBK), int(p.row0 + xt * kGemmBN), &bars->full[stage]);
                         if (++stage == kGemmStages) { stage = 0; phase ^= 1u; }
                     }
             }

@@ -383,6 +383,7 @@ struct mvdb_index {
     // options
     int batch_mode = 1;            // 0 off, 1 exact (bf16 candidates + fp32 re-scoring), 2 bf16
     int batch_min_nq = 9;
+    int gemm_l2_hint = 0;
     int scan_variant = MVDB_SCAN_AUTO;
     int fused_k_max = 128;
     int grid_ctas = 0;
@@ -704,6 +705,7 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
     }
     gp.nq = nq;
     gp.d = ix->d;
+    gp.l2_hint = ix->gemm_l2_hint;
     gp.thr = ws->b_thr;
     gp.cand = ws->b_cand;
     gp.cand_cnt = ws->b_cnt;
@@ -1191,6 +1193,9 @@ int mvdb_index_set_option(mvdb_index* ix, const char* name, int64_t value) {
     } else if (s == "batch_mode") {
         if (value < 0 || value > 2) return fail(MVDB_ERR_ARG, "batch_mode must be 0 (off), 1 (exact) or 2 (bf16)");
         ix->batch_mode = int(value);
+    } else if (s == "gemm_l2_hint") {
+        if (value < 0 || value > 2) return fail(MVDB_ERR_ARG, "gemm_l2_hint must be 0..2");
+        ix->gemm_l2_hint = int(value);
     } else if (s == "batch_min_nq") {
         if (value < 1) return fail(MVDB_ERR_ARG, "batch_min_nq must be >= 1");
         ix->batch_min_nq = int(value);
