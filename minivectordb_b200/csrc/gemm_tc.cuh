@@ -145,6 +145,82 @@ __device__ __forceinline__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
            | (uint32_t(M >> 4) << 24);
 }
 
+// Epilogue of one 128 x 256 accumulator tile for the query owned by this thread (TMEM lane).
+// t_lane: TMEM address of this warp's lane quadrant and accumulator stage; tile_row0: first
+// (sampled) row of the tile; adm: admissible bits of the tile's 256 rows (common masks).
+__device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t t_lane, int64_t q, uint32_t tile_row0,
+                                                   const uint32_t (&adm)[8]) {
+    const bool q_ok = q < p.nq;
+    const uint64_t thr = (q_ok && p.thr) ? p.thr[q] : kEmptyKey;
+    const uint32_t* qm = (q_ok && p.qmask) ? p.qmask[q] : nullptr;   // this query's own filter
+    const uint32_t qm_words = qm ? p.qmask_words[q] : 0u;
+    if (p.dense) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < kGemmBN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(t_lane + uint32_t(c0), v);
+            if (q_ok) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const uint32_t row = tile_row0 + c0 + j;
+                    if (row < p.n_valid) p.dense[q * p.dense_ld + row] = __uint_as_float(v[j]);
+                }
+            }
+        }
+    } else {
+        // Pass 1: which of my query's 256 scores beat its threshold?  Pure register
+        // work, branch-free, no memory operation inside a divergent region.  The
+        // group loop is deliberately NOT unrolled: fully unrolled the epilogue is
+        // ~200 KB of SASS and becomes instruction-fetch bound (measured: 10x slower).
+        uint32_t hit[8];
+        uint32_t total = 0;
+#pragma unroll 1
+        for (int g = 0; g < 8; g++) {
+            uint32_t v[32];
+            tmem_ld_32x32(t_lane + uint32_t(32 * g), v);
+            uint32_t m = 0;
+            // ~row of column 0 of this group; column j is index row (tile_row0 + 32g + j) * stride
+            const uint32_t low0 = 0xFFFFFFFFu - (tile_row0 + 32 * g) * p.row_stride;
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const float s = __uint_as_float(v[j]);
+                const uint64_t key = (uint64_t(score_to_ord(s)) << 32) | uint64_t(low0 - uint32_t(j) * p.row_stride);
+                const uint32_t pass = uint32_t(key > thr) & uint32_t(s == s);   // NaN never passes
+                m |= pass << j;
+            }
+            m &= q_ok ? adm[g] : 0u;
+            if (qm) {
+                const uint32_t w = (tile_row0 >> 5) + uint32_t(g);
+                m &= (w < qm_words) ? qm[w] : 0u;
+            }
+            hit[g] = m;
+            total += __popc(m);
+        }
+        // One reservation per thread per tile, then (rarely) pass 2: re-read the groups
+        // that had a hit (TMEM reads are cheap) and store the keys.
+        uint32_t pos = 0;
+        if (total) pos = atomicAdd(p.cand_cnt + q, total);
+        if (__any_sync(0xFFFFFFFFu, total != 0u)) {
+#pragma unroll 1
+            for (int g = 0; g < 8; g++) {
+                uint32_t m = hit[g];
+                if (!__any_sync(0xFFFFFFFFu, m != 0u)) continue;
+                uint32_t v[32];
+                tmem_ld_32x32(t_lane + uint32_t(32 * g), v);
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    if ((m >> j) & 1u) {
+                        if (pos < p.cand_cap)
+                            p.cand[size_t(q) * p.cand_cap + pos] =
+                                make_key(__uint_as_float(v[j]), (tile_row0 + 32 * g + j) * p.row_stride);
+                        pos++;
+                    }
+                }
+            }
+        }
+    }
+}
+
 struct GemmBarriers {
     uint64_t full[kGemmStages];
     uint64_t empty[kGemmStages];
@@ -260,78 +336,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             }
             {
                 const int64_t q = int64_t(qb) * kGemmBM + quad * 32 + lane;
-                const bool q_ok = q < p.nq;
-                const uint64_t thr = (q_ok && p.thr) ? p.thr[q] : kEmptyKey;
-                const uint32_t* qm = (q_ok && p.qmask) ? p.qmask[q] : nullptr;   // this query's own filter
-                const uint32_t qm_words = qm ? p.qmask_words[q] : 0u;
                 mbar_wait(&bars->tfull[acc], acc_phase);
                 tc_fence_after();
-                const uint32_t t_lane = tmem_base + ((quad * 32u) << 16) + acc * kGemmBN;
-                if (p.dense) {
-#pragma unroll 1
-                    for (int c0 = 0; c0 < kGemmBN; c0 += 32) {
-                        uint32_t v[32];
-                        tmem_ld_32x32(t_lane + uint32_t(c0), v);
-                        if (q_ok) {
-#pragma unroll
-                            for (int j = 0; j < 32; j++) {
-                                const uint32_t row = tile_row0 + c0 + j;
-                                if (row < p.n_valid) p.dense[q * p.dense_ld + row] = __uint_as_float(v[j]);
-                            }
-                        }
-                    }
-                } else {
-                    // Pass 1: which of my query's 256 scores beat its threshold?  Pure register
-                    // work, branch-free, no memory operation inside a divergent region.  The
-                    // group loop is deliberately NOT unrolled: fully unrolled the epilogue is
-                    // ~200 KB of SASS and becomes instruction-fetch bound (measured: 10x slower).
-                    uint32_t hit[8];
-                    uint32_t total = 0;
-#pragma unroll 1
-                    for (int g = 0; g < 8; g++) {
-                        uint32_t v[32];
-                        tmem_ld_32x32(t_lane + uint32_t(32 * g), v);
-                        uint32_t m = 0;
-                        // ~row of column 0 of this group; column j is index row (tile_row0 + 32g + j) * stride
-                        const uint32_t low0 = 0xFFFFFFFFu - (tile_row0 + 32 * g) * p.row_stride;
-#pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            const float s = __uint_as_float(v[j]);
-                            const uint64_t key = (uint64_t(score_to_ord(s)) << 32) | uint64_t(low0 - uint32_t(j) * p.row_stride);
-                            const uint32_t pass = uint32_t(key > thr) & uint32_t(s == s);   // NaN never passes
-                            m |= pass << j;
-                        }
-                        m &= q_ok ? adm[g] : 0u;
-                        if (qm) {
-                            const uint32_t w = (tile_row0 >> 5) + uint32_t(g);
-                            m &= (w < qm_words) ? qm[w] : 0u;
-                        }
-                        hit[g] = m;
-                        total += __popc(m);
-                    }
-                    // One reservation per thread per tile, then (rarely) pass 2: re-read the groups
-                    // that had a hit (TMEM reads are cheap) and store the keys.
-                    uint32_t pos = 0;
-                    if (total) pos = atomicAdd(p.cand_cnt + q, total);
-                    if (__any_sync(0xFFFFFFFFu, total != 0u)) {
-#pragma unroll 1
-                        for (int g = 0; g < 8; g++) {
-                            uint32_t m = hit[g];
-                            if (!__any_sync(0xFFFFFFFFu, m != 0u)) continue;
-                            uint32_t v[32];
-                            tmem_ld_32x32(t_lane + uint32_t(32 * g), v);
-#pragma unroll
-                            for (int j = 0; j < 32; j++) {
-                                if ((m >> j) & 1u) {
-                                    if (pos < p.cand_cap)
-                                        p.cand[size_t(q) * p.cand_cap + pos] =
-                                            make_key(__uint_as_float(v[j]), (tile_row0 + 32 * g + j) * p.row_stride);
-                                    pos++;
-                                }
-                            }
-                        }
-                    }
-                }
+                gemm_epilogue_tile(p, tmem_base + ((quad * 32u) << 16) + acc * kGemmBN, q, tile_row0, adm);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->tempty[acc]);
@@ -342,6 +349,212 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------
+// 2-CTA variant (cta_group::2): a CTA PAIR (cluster of 2, same TPC) computes one
+// 256-query x 256-row tile.  Each CTA stages only ITS half of both operands -- 128
+// queries (A) and 128 rows (B), 32 KB per stage instead of 48 KB -- and the leader
+// CTA's single MMA thread issues tcgen05.mma.cta_group::2 (M = 256), which reads both
+// CTAs' shared memory and writes a 128 x 256 accumulator into each CTA's TMEM.
+// Per SM this halves the B-operand traffic from L2 and makes room for a 6-stage ring.
+//
+// Synchronisation (every barrier is local to the CTA that waits on it):
+//   full[s]      each CTA: its own TMA bytes have landed
+//   peer_full[s] leader only: the peer's relay lane arrives remotely once the PEER's
+//                full[s] completed (no remote TMA signalling needed)
+//   empty[s]     each CTA: the leader's tcgen05.commit multicasts one arrival to both
+//   tfull[a]     each CTA: accumulator a complete (multicast commit)
+//   tempty[a]    leader only, count 8: the 4 epilogue warps of BOTH CTAs (peer: remote)
+// ---------------------------------------------------------------------------
+constexpr int kGemm2Stages = 6;
+constexpr uint32_t kGemm2HalfB = (kGemmBN / 2) * kGemmBK * 2;            // 16 KB: this CTA's 128 rows of the B tile
+constexpr uint32_t kGemm2StageBytes = kGemmABytes + kGemm2HalfB;          // 32 KB
+constexpr uint32_t kGemm2SmemBytes = kGemm2Stages * kGemm2StageBytes + 512 + 1024;
+
+struct Gemm2Barriers {
+    uint64_t full[kGemm2Stages];
+    uint64_t peer_full[kGemm2Stages];
+    uint64_t empty[kGemm2Stages];
+    uint64_t tfull[2];
+    uint64_t tempty[2];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+        "r"(rank)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// one arrival on the barrier at this offset in EVERY CTA of `mask`, once the MMAs issued so far retire
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"(mask)
+        : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+gemm_topk_kernel_2cta(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmX, const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    Gemm2Barriers* bars = reinterpret_cast<Gemm2Barriers*>(smem + kGemm2Stages * kGemm2StageBytes);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kGemm2Stages; s++) {
+            mbar_init(&bars->full[s], 1);
+            mbar_init(&bars->peer_full[s], 1);
+            mbar_init(&bars->empty[s], 1);
+        }
+        for (int a = 0; a < 2; a++) {
+            mbar_init(&bars->tfull[a], 1);
+            mbar_init(&bars->tempty[a], 8);   // 4 epilogue warps x 2 CTAs (waited on by the leader only)
+        }
+        mbar_fence_init();
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmX);
+    }
+    if (warp == 2) tmem_alloc2(&bars->tmem_base, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();   // both CTAs' barriers exist before anyone arrives remotely
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    const uint32_t n_rows = p.row1 - p.row0;
+    const uint32_t n_xt = (n_rows + kGemmBN - 1) / kGemmBN;
+    const uint32_t n_qb2 = uint32_t((p.nq + 2 * kGemmBM - 1) / (2 * kGemmBM));   // 256-query blocks
+    const uint32_t n_kb = uint32_t((p.d + kGemmBK - 1) / kGemmBK);
+    const uint64_t n_tiles = uint64_t(n_xt) * n_qb2;
+    const uint32_t n_pairs = gridDim.x / 2, pair = blockIdx.x / 2;
+    const uint32_t t_lo = uint32_t(n_tiles * pair / n_pairs);
+    const uint32_t t_hi = uint32_t(n_tiles * (pair + 1) / n_pairs);
+
+    if (warp == 0) {
+        if (lane == 0) {   // TMA producer: this CTA's halves of A and B
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t t = t_lo; t < t_hi; t++) {
+                const uint32_t xt = t / n_qb2, qb2 = t % n_qb2;
+                for (uint32_t kb = 0; kb < n_kb; kb++) {
+                    mbar_wait(&bars->empty[stage], phase ^ 1u);
+                    uint8_t* sA = smem + stage * kGemm2StageBytes;
+                    uint8_t* sB = sA + kGemmABytes;
+                    mbar_arrive_expect_tx(&bars->full[stage], kGemm2StageBytes);
+                    tma_load_2d(sA, &tmQ, int(kb * kGemmBK), int(qb2 * 2 * kGemmBM + rank * kGemmBM), &bars->full[stage]);
+                    tma_load_2d(sB, &tmX, int(kb * kGemmBK), int(p.row0 + xt * kGemmBN + rank * (kGemmBN / 2)), &bars->full[stage]);
+                    if (++stage == kGemm2Stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        if (lane == 0 && !leader) {   // relay: tell the leader that the peer's half of stage s is in place
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t t = t_lo; t < t_hi; t++)
+                for (uint32_t kb = 0; kb < n_kb; kb++) {
+                    mbar_wait(&bars->full[stage], phase);
+                    mbar_arrive_remote(&bars->peer_full[stage], 0);
+                    if (++stage == kGemm2Stages) { stage = 0; phase ^= 1u; }
+                }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {   // the pair's single MMA issuer
+            const uint32_t idesc = umma_idesc_bf16(2 * kGemmBM, kGemmBN);
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (uint32_t t = t_lo; t < t_hi; t++) {
+                mbar_wait(&bars->tempty[acc], acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * kGemmBN;
+                for (uint32_t kb = 0; kb < n_kb; kb++) {
+                    mbar_wait(&bars->full[stage], phase);
+                    mbar_wait(&bars->peer_full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + stage * kGemm2StageBytes);
+                    const uint64_t a_desc = umma_desc_sw128(a_addr);
+                    const uint64_t b_desc = umma_desc_sw128(a_addr + kGemmABytes);
+#pragma unroll
+                    for (uint32_t k = 0; k < kGemmBK / 16; k++)
+                        umma_bf16_2cta(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_commit_2cta(&bars->empty[stage], 0x3);   // frees the stage in both CTAs
+                    if (++stage == kGemm2Stages) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit_2cta(&bars->tfull[acc], 0x3);         // accumulator ready in both CTAs
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else if (warp >= 4) {
+        const uint32_t quad = uint32_t(warp - 4);
+        uint32_t acc = 0, acc_phase = 0;
+        uint32_t cur_xt = 0xFFFFFFFFu, tile_row0 = 0;
+        uint32_t adm[8];
+        for (uint32_t t = t_lo; t < t_hi; t++) {
+            const uint32_t xt = t / n_qb2, qb2 = t % n_qb2;
+            if (xt != cur_xt) {
+                cur_xt = xt;
+                tile_row0 = p.row0 + xt * kGemmBN;
+#pragma unroll
+                for (int w = 0; w < 8; w++) {
+                    const uint32_t r = tile_row0 + 32 * w;
+                    uint32_t bits = 0xFFFFFFFFu;
+                    if (r >= p.n_valid) bits = 0;
+                    else {
+                        if (p.n_valid - r < 32) bits = (1u << (p.n_valid - r)) - 1u;
+                        if (p.mask) bits &= p.mask[r >> 5];
+                        if (p.live) bits &= p.live[r >> 5];
+                    }
+                    adm[w] = bits;
+                }
+            }
+            const int64_t q = int64_t(qb2) * 2 * kGemmBM + rank * kGemmBM + quad * 32 + lane;
+            mbar_wait(&bars->tfull[acc], acc_phase);
+            tc_fence_after();
+            gemm_epilogue_tile(p, tmem_base + ((quad * 32u) << 16) + acc * kGemmBN, q, tile_row0, adm);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (leader) mbar_arrive(&bars->tempty[acc]);
+                else mbar_arrive_remote(&bars->tempty[acc], 0);
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();   // nobody leaves while the peer may still touch its shared memory / barriers
+    if (warp == 2) tmem_dealloc2(tmem_base, kTmemCols);
 }
 
 // ---------------------------------------------------------------------------

@@ -384,6 +384,7 @@ struct mvdb_index {
     int batch_mode = 1;            // 0 off, 1 exact (bf16 candidates + fp32 re-scoring), 2 bf16
     int batch_min_nq = 9;
     int gemm_l2_hint = 0;
+    int gemm_variant = 0;          // 0: one CTA per 128x256 tile; 1: CTA pairs (cta_group::2), 256x256 tiles
     int scan_variant = MVDB_SCAN_AUTO;
     int fused_k_max = 128;
     int grid_ctas = 0;
@@ -669,9 +670,12 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
     init_batch_state_kernel<<<unsigned((nq + 255) / 256), 256, 0, stream>>>(ws->b_thr, ws->b_cnt, ws->b_ovf, nq);
     LAUNCHED();
 
-    CUtensorMap tmQ, tmX;
+    CUtensorMap tmQ, tmX, tmQ2, tmX2;
     RC_OK(encode_bf16_map(&tmQ, ws->b_q16, uint64_t(nq), ix->d, ix->ld16, kGemmBM));
+    tmQ2 = tmQ;   // the pair kernel loads 128-query boxes too
+    tmX2 = tmQ;
     CU_OK(cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes)));
+    CU_OK(cudaFuncSetAttribute(gemm_topk_kernel_2cta, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemm2SmemBytes)));
     CU_OK(cudaFuncSetAttribute(cand_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kCandCap * 8)));
 
     // rigorous bound on |bf16 score - fp32 score| per unit |q|: inputs rounded to nearest
@@ -736,6 +740,7 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
         const uint32_t m = uint32_t((uint64_t(n) + S - 1) / S);   // sampled rows of this level
         const uint32_t words = (m + 31) / 32;
         RC_OK(encode_bf16_map(&tmX, ix->mat16.ptr(), m, ix->d, ix->ld16 * int64_t(S), kGemmBN));
+        if (ix->gemm_variant == 1) RC_OK(encode_bf16_map(&tmX2, ix->mat16.ptr(), m, ix->d, ix->ld16 * int64_t(S), kGemmBN / 2));
         gp.row_stride = S;
         gp.row0 = 0;
         gp.row1 = uint32_t(align_up(m, kGemmBN));
@@ -786,9 +791,16 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
         for (uint32_t hi : cuts) {
             gp.row0 = lo;
             gp.row1 = hi;
-            const uint64_t tiles = uint64_t((hi - lo) / kGemmBN) * n_qb;
-            const unsigned grid = unsigned(std::min<uint64_t>(uint64_t(ix->sm_count), tiles));
-            gemm_topk_kernel<<<grid, 256, kGemmSmemBytes, stream>>>(tmQ, tmX, gp);
+            if (ix->gemm_variant == 1 && nq > kGemmBM) {
+                // CTA pairs: 256-query x 256-row tiles, B operand split across the pair
+                const uint64_t tiles2 = uint64_t((hi - lo) / kGemmBN) * ((nq + 2 * kGemmBM - 1) / (2 * kGemmBM));
+                const unsigned pairs = unsigned(std::min<uint64_t>(uint64_t(ix->sm_count / 2), tiles2));
+                gemm_topk_kernel_2cta<<<2 * pairs, 256, kGemm2SmemBytes, stream>>>(tmQ2, tmX2, gp);
+            } else {
+                const uint64_t tiles = uint64_t((hi - lo) / kGemmBN) * n_qb;
+                const unsigned grid = unsigned(std::min<uint64_t>(uint64_t(ix->sm_count), tiles));
+                gemm_topk_kernel<<<grid, 256, kGemmSmemBytes, stream>>>(tmQ, tmX, gp);
+            }
             LAUNCHED();
             if (!dense_out) {
                 cand_update_kernel<<<unsigned(nq), 256, kCandCap * 8, stream>>>(ws->b_cand, ws->b_cnt, ws->b_thr, ws->b_ovf, kCandCap,
@@ -1193,6 +1205,9 @@ int mvdb_index_set_option(mvdb_index* ix, const char* name, int64_t value) {
     } else if (s == "batch_mode") {
         if (value < 0 || value > 2) return fail(MVDB_ERR_ARG, "batch_mode must be 0 (off), 1 (exact) or 2 (bf16)");
         ix->batch_mode = int(value);
+    } else if (s == "gemm_variant") {
+        if (value < 0 || value > 1) return fail(MVDB_ERR_ARG, "gemm_variant must be 0 or 1");
+        ix->gemm_variant = int(value);
     } else if (s == "gemm_l2_hint") {
         if (value < 0 || value > 2) return fail(MVDB_ERR_ARG, "gemm_l2_hint must be 0..2");
         ix->gemm_l2_hint = int(value);

@@ -153,3 +153,38 @@ def test_batched_adversarial_periodic_filter_overflows_and_falls_back(mv):
     Dr, Ir = O.search_masked(x, odd, q, k)
     assert O.classify_parity(x, q, I, D, Ir, Dr, admissible=odd)["ok"]
     eng.close()
+
+
+@pytest.mark.parametrize("n,d,nq", [(1000, 64, 256), (5000, 1000, 300), (4096, 1024, 512), (70_000, 384, 1000)])
+def test_tcgen05_2cta_gemm_matches_bf16_matmul(mv, n, d, nq):
+    """cta_group::2 variant (CTA pairs, 256 x 256 tiles): same raw scores as the bf16 matmul."""
+    import torch
+    x, q = _data(n, d, nq, seed=n + d + 1)
+    eng = mv.FlatIPEngine(d)
+    eng.set_option("gemm_variant", 1)
+    eng.add(x)
+    got = eng.debug_gemm_scores(q)
+    xb = torch.from_numpy(x).to(torch.bfloat16).to(torch.float64)
+    qb = torch.from_numpy(q).to(torch.bfloat16).to(torch.float64)
+    want = (qb @ xb.T).numpy()
+    err = np.abs(got - want).max()
+    assert err < 2e-5, err
+    eng.close()
+
+
+def test_batched_2cta_exact_is_bit_identical_to_the_scan(mv):
+    n, d, nq, k = 60_000, 384, 700, 10
+    x, q = _data(n, d, nq, seed=77)
+    eng = mv.FlatIPEngine(d)
+    eng.add(x)
+    adm = np.random.default_rng(0).random(n) < 0.5
+    eng.set_option("batch_mode", 0)
+    Ds, Is = eng.search(q[:64], k, mask=adm)
+    eng.set_option("batch_mode", 1)
+    eng.set_option("gemm_variant", 1)
+    Db, Ib = eng.search(q, k, mask=adm)
+    assert np.array_equal(Is, Ib[:64]) and np.array_equal(Ds, Db[:64])
+    eng.set_option("gemm_variant", 0)
+    D0, I0 = eng.search(q, k, mask=adm)
+    assert np.array_equal(I0, Ib) and np.array_equal(D0, Db)
+    eng.close()
