@@ -558,6 +558,147 @@ gemm_topk_kernel_2cta(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 }
 
 // ---------------------------------------------------------------------------
+// Multicast variant: a cluster of 2 CTAs works on the SAME X tile with two
+// different query blocks.  Each CTA fetches half of the X tile (128 rows) and TMA
+// multicasts it into both CTAs' shared memory, so every L2 read of X feeds two SMs:
+// L2 output per SM per k-block drops from 48 KB to 32 KB.  MMAs stay cta_group::1
+// (each CTA owns its 128 x 256 tile); the only coupling is the `empty` barrier, which
+// needs BOTH CTAs' MMA commits before either producer may overwrite the stage.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d_mc(void* dst_smem, const CUtensorMap* map, int c0, int c1, uint64_t* bar,
+                                               uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%2, %3}], [%4], %5;" ::"r"(smem_u32(dst_smem)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "h"(cta_mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"(mask)
+        : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+gemm_topk_kernel_mc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmXh, const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(smem + kGemmStages * kGemmStageBytes);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kGemmStages; s++) {
+            mbar_init(&bars->full[s], 1);
+            mbar_init(&bars->empty[s], 2);    // both CTAs' MMA commits
+        }
+        for (int a = 0; a < 2; a++) {
+            mbar_init(&bars->tfull[a], 1);
+            mbar_init(&bars->tempty[a], 4);
+        }
+        mbar_fence_init();
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmXh);
+    }
+    if (warp == 2) tmem_alloc(&bars->tmem_base, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    const uint32_t n_rows = p.row1 - p.row0;
+    const uint32_t n_xt = (n_rows + kGemmBN - 1) / kGemmBN;
+    const uint32_t n_qb2 = uint32_t((p.nq + 2 * kGemmBM - 1) / (2 * kGemmBM));   // pairs of query blocks
+    const uint32_t n_kb = uint32_t((p.d + kGemmBK - 1) / kGemmBK);
+    const uint64_t n_tiles = uint64_t(n_xt) * n_qb2;
+    const uint32_t n_pairs = gridDim.x / 2, pair = blockIdx.x / 2;
+    const uint32_t t_lo = uint32_t(n_tiles * pair / n_pairs);
+    const uint32_t t_hi = uint32_t(n_tiles * (pair + 1) / n_pairs);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t t = t_lo; t < t_hi; t++) {
+                const uint32_t xt = t / n_qb2, qb = (t % n_qb2) * 2 + rank;
+                for (uint32_t kb = 0; kb < n_kb; kb++) {
+                    mbar_wait(&bars->empty[stage], phase ^ 1u);   // freed by BOTH CTAs
+                    uint8_t* sA = smem + stage * kGemmStageBytes;
+                    uint8_t* sB = sA + kGemmABytes;
+                    mbar_arrive_expect_tx(&bars->full[stage], kGemmStageBytes);   // A + my half of B + the peer's half
+                    tma_load_2d(sA, &tmQ, int(kb * kGemmBK), int(qb * kGemmBM), &bars->full[stage]);
+                    tma_load_2d_mc(sB + rank * (kGemmBBytes / 2), &tmXh, int(kb * kGemmBK),
+                                   int(p.row0 + xt * kGemmBN + rank * (kGemmBN / 2)), &bars->full[stage], 0x3);
+                    if (++stage == kGemmStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(kGemmBM, kGemmBN);
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (uint32_t t = t_lo; t < t_hi; t++) {
+                mbar_wait(&bars->tempty[acc], acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * kGemmBN;
+                for (uint32_t kb = 0; kb < n_kb; kb++) {
+                    mbar_wait(&bars->full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + stage * kGemmStageBytes);
+                    const uint64_t a_desc = umma_desc_sw128(a_addr);
+                    const uint64_t b_desc = umma_desc_sw128(a_addr + kGemmABytes);
+#pragma unroll
+                    for (uint32_t k = 0; k < kGemmBK / 16; k++)
+                        umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_commit_mc(&bars->empty[stage], 0x3);   // one arrival in each CTA's empty[stage]
+                    if (++stage == kGemmStages) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(&bars->tfull[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else if (warp >= 4) {
+        const uint32_t quad = uint32_t(warp - 4);
+        uint32_t acc = 0, acc_phase = 0;
+        uint32_t cur_xt = 0xFFFFFFFFu, tile_row0 = 0;
+        uint32_t adm[8];
+        for (uint32_t t = t_lo; t < t_hi; t++) {
+            const uint32_t xt = t / n_qb2, qb = (t % n_qb2) * 2 + rank;
+            if (xt != cur_xt) {
+                cur_xt = xt;
+                tile_row0 = p.row0 + xt * kGemmBN;
+#pragma unroll
+                for (int w = 0; w < 8; w++) {
+                    const uint32_t r = tile_row0 + 32 * w;
+                    uint32_t bits = 0xFFFFFFFFu;
+                    if (r >= p.n_valid) bits = 0;
+                    else {
+                        if (p.n_valid - r < 32) bits = (1u << (p.n_valid - r)) - 1u;
+                        if (p.mask) bits &= p.mask[r >> 5];
+                        if (p.live) bits &= p.live[r >> 5];
+                    }
+                    adm[w] = bits;
+                }
+            }
+            const int64_t q = int64_t(qb) * kGemmBM + quad * 32 + lane;
+            mbar_wait(&bars->tfull[acc], acc_phase);
+            tc_fence_after();
+            gemm_epilogue_tile(p, tmem_base + ((quad * 32u) << 16) + acc * kGemmBN, q, tile_row0, adm);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------
 // helpers around the GEMM
 // ---------------------------------------------------------------------------
 // fp32 rows (pitch ld_in floats) -> bf16 rows (pitch ld_out), round to nearest, zero padding

@@ -384,7 +384,8 @@ struct mvdb_index {
     int batch_mode = 1;            // 0 off, 1 exact (bf16 candidates + fp32 re-scoring), 2 bf16
     int batch_min_nq = 9;
     int gemm_l2_hint = 0;
-    int gemm_variant = 0;          // 0: one CTA per 128x256 tile; 1: CTA pairs (cta_group::2), 256x256 tiles
+    int gemm_variant = 0;          // 0: one CTA per 128x256 tile; 1: CTA pairs (cta_group::2), 256x256 tiles;
+                                   // 2: cluster of 2 sharing the X tile through TMA multicast
     int scan_variant = MVDB_SCAN_AUTO;
     int fused_k_max = 128;
     int grid_ctas = 0;
@@ -676,6 +677,7 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
     tmX2 = tmQ;
     CU_OK(cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes)));
     CU_OK(cudaFuncSetAttribute(gemm_topk_kernel_2cta, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemm2SmemBytes)));
+    CU_OK(cudaFuncSetAttribute(gemm_topk_kernel_mc, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes)));
     CU_OK(cudaFuncSetAttribute(cand_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kCandCap * 8)));
 
     // rigorous bound on |bf16 score - fp32 score| per unit |q|: inputs rounded to nearest
@@ -740,7 +742,7 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
         const uint32_t m = uint32_t((uint64_t(n) + S - 1) / S);   // sampled rows of this level
         const uint32_t words = (m + 31) / 32;
         RC_OK(encode_bf16_map(&tmX, ix->mat16.ptr(), m, ix->d, ix->ld16 * int64_t(S), kGemmBN));
-        if (ix->gemm_variant == 1) RC_OK(encode_bf16_map(&tmX2, ix->mat16.ptr(), m, ix->d, ix->ld16 * int64_t(S), kGemmBN / 2));
+        if (ix->gemm_variant >= 1) RC_OK(encode_bf16_map(&tmX2, ix->mat16.ptr(), m, ix->d, ix->ld16 * int64_t(S), kGemmBN / 2));
         gp.row_stride = S;
         gp.row0 = 0;
         gp.row1 = uint32_t(align_up(m, kGemmBN));
@@ -791,7 +793,11 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
         for (uint32_t hi : cuts) {
             gp.row0 = lo;
             gp.row1 = hi;
-            if (ix->gemm_variant == 1 && nq > kGemmBM) {
+            if (ix->gemm_variant == 2 && nq > kGemmBM) {
+                const uint64_t tiles2 = uint64_t((hi - lo) / kGemmBN) * ((nq + 2 * kGemmBM - 1) / (2 * kGemmBM));
+                const unsigned pairs = unsigned(std::min<uint64_t>(uint64_t(ix->sm_count / 2), tiles2));
+                gemm_topk_kernel_mc<<<2 * pairs, 256, kGemmSmemBytes, stream>>>(tmQ2, tmX2, gp);
+            } else if (ix->gemm_variant == 1 && nq > kGemmBM) {
                 // CTA pairs: 256-query x 256-row tiles, B operand split across the pair
                 const uint64_t tiles2 = uint64_t((hi - lo) / kGemmBN) * ((nq + 2 * kGemmBM - 1) / (2 * kGemmBM));
                 const unsigned pairs = unsigned(std::min<uint64_t>(uint64_t(ix->sm_count / 2), tiles2));
@@ -1206,7 +1212,7 @@ int mvdb_index_set_option(mvdb_index* ix, const char* name, int64_t value) {
         if (value < 0 || value > 2) return fail(MVDB_ERR_ARG, "batch_mode must be 0 (off), 1 (exact) or 2 (bf16)");
         ix->batch_mode = int(value);
     } else if (s == "gemm_variant") {
-        if (value < 0 || value > 1) return fail(MVDB_ERR_ARG, "gemm_variant must be 0 or 1");
+        if (value < 0 || value > 2) return fail(MVDB_ERR_ARG, "gemm_variant must be 0, 1 or 2");
         ix->gemm_variant = int(value);
     } else if (s == "gemm_l2_hint") {
         if (value < 0 || value > 2) return fail(MVDB_ERR_ARG, "gemm_l2_hint must be 0..2");

@@ -1,0 +1,27 @@
+import os, sys, json
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import minivectordb_b200 as mv
+out = []
+for n, d, nq, k in ((2_000_000, 1024, 4096, 100), (1_000_000, 384, 4096, 10), (10_000_000, 1024, 4096, 100)):
+    eng = mv.FlatIPEngine(d); eng.add_synthetic(1234, 0, n, 0, True); ws = eng.workspace()
+    q = torch.randn(nq, d, device="cuda"); q = q / q.norm(dim=1, keepdim=True)
+    D = torch.empty(nq, k, device="cuda"); I = torch.empty(nq, k, dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    ref = None
+    for variant in (0, 2, 1, 0, 2):
+        eng.set_option("gemm_variant", variant)
+        eng.search_device(ws, q.data_ptr(), nq, k, D.data_ptr(), I.data_ptr(), stream=st); torch.cuda.synchronize()
+        ts = []
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); eng.search_device(ws, q.data_ptr(), nq, k, D.data_ptr(), I.data_ptr(), stream=st); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        t = sorted(ts)[1]
+        same = None
+        if ref is None: ref = (D.clone(), I.clone())
+        else: same = bool(torch.equal(ref[0], D) and torch.equal(ref[1], I))
+        rec = dict(n=n, d=d, nq=nq, k=k, variant=variant, ms=t, tflops=2.0 * nq * n * d / t / 1e9, same_as_first=same)
+        out.append(rec); print(json.dumps(rec), flush=True)
+    del ws; eng.close()
+json.dump(out, open("gpurun_out/gemm_variant_probe.json", "w"), indent=1)
