@@ -581,7 +581,9 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
         : "memory");
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+// CS = cluster size (2 or 4): CS query blocks share one X tile; each CTA fetches 1/CS of it.
+template <int CS>
+__global__ void __launch_bounds__(256, 1)
 gemm_topk_kernel_mc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmXh, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -592,7 +594,7 @@ gemm_topk_kernel_mc(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (threadIdx.x == 0) {
         for (int s = 0; s < kGemmStages; s++) {
             mbar_init(&bars->full[s], 1);
-            mbar_init(&bars->empty[s], 2);    // both CTAs' MMA commits
+            mbar_init(&bars->empty[s], CS);   // every CTA's MMA commit
         }
         for (int a = 0; a < 2; a++) {
             mbar_init(&bars->tfull[a], 1);
@@ -611,10 +613,10 @@ gemm_topk_kernel_mc(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
     const uint32_t n_rows = p.row1 - p.row0;
     const uint32_t n_xt = (n_rows + kGemmBN - 1) / kGemmBN;
-    const uint32_t n_qb2 = uint32_t((p.nq + 2 * kGemmBM - 1) / (2 * kGemmBM));   // pairs of query blocks
+    const uint32_t n_qb2 = uint32_t((p.nq + CS * kGemmBM - 1) / (CS * kGemmBM));   // groups of CS query blocks
     const uint32_t n_kb = uint32_t((p.d + kGemmBK - 1) / kGemmBK);
     const uint64_t n_tiles = uint64_t(n_xt) * n_qb2;
-    const uint32_t n_pairs = gridDim.x / 2, pair = blockIdx.x / 2;
+    const uint32_t n_pairs = gridDim.x / CS, pair = blockIdx.x / CS;
     const uint32_t t_lo = uint32_t(n_tiles * pair / n_pairs);
     const uint32_t t_hi = uint32_t(n_tiles * (pair + 1) / n_pairs);
 
@@ -622,15 +624,15 @@ gemm_topk_kernel_mc(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (uint32_t t = t_lo; t < t_hi; t++) {
-                const uint32_t xt = t / n_qb2, qb = (t % n_qb2) * 2 + rank;
+                const uint32_t xt = t / n_qb2, qb = (t % n_qb2) * CS + rank;
                 for (uint32_t kb = 0; kb < n_kb; kb++) {
                     mbar_wait(&bars->empty[stage], phase ^ 1u);   // freed by BOTH CTAs
                     uint8_t* sA = smem + stage * kGemmStageBytes;
                     uint8_t* sB = sA + kGemmABytes;
                     mbar_arrive_expect_tx(&bars->full[stage], kGemmStageBytes);   // A + my half of B + the peer's half
                     tma_load_2d(sA, &tmQ, int(kb * kGemmBK), int(qb * kGemmBM), &bars->full[stage]);
-                    tma_load_2d_mc(sB + rank * (kGemmBBytes / 2), &tmXh, int(kb * kGemmBK),
-                                   int(p.row0 + xt * kGemmBN + rank * (kGemmBN / 2)), &bars->full[stage], 0x3);
+                    tma_load_2d_mc(sB + rank * (kGemmBBytes / CS), &tmXh, int(kb * kGemmBK),
+                                   int(p.row0 + xt * kGemmBN + rank * (kGemmBN / CS)), &bars->full[stage], uint16_t((1u << CS) - 1u));
                     if (++stage == kGemmStages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -652,7 +654,7 @@ gemm_topk_kernel_mc(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
                     for (uint32_t k = 0; k < kGemmBK / 16; k++)
                         umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                    umma_commit_mc(&bars->empty[stage], 0x3);   // one arrival in each CTA's empty[stage]
+                    umma_commit_mc(&bars->empty[stage], uint16_t((1u << CS) - 1u));   // one arrival in each CTA's empty[stage]
                     if (++stage == kGemmStages) { stage = 0; phase ^= 1u; }
                 }
                 umma_commit(&bars->tfull[acc]);
@@ -665,7 +667,7 @@ gemm_topk_kernel_mc(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         uint32_t cur_xt = 0xFFFFFFFFu, tile_row0 = 0;
         uint32_t adm[8];
         for (uint32_t t = t_lo; t < t_hi; t++) {
-            const uint32_t xt = t / n_qb2, qb = (t % n_qb2) * 2 + rank;
+            const uint32_t xt = t / n_qb2, qb = (t % n_qb2) * CS + rank;
             if (xt != cur_xt) {
                 cur_xt = xt;
                 tile_row0 = p.row0 + xt * kGemmBN;

@@ -385,7 +385,7 @@ struct mvdb_index {
     int batch_min_nq = 9;
     int gemm_l2_hint = 0;
     int gemm_variant = 0;          // 0: one CTA per 128x256 tile; 1: CTA pairs (cta_group::2), 256x256 tiles;
-                                   // 2: cluster of 2 sharing the X tile through TMA multicast
+                                   // 2 / 3: cluster of 2 / 4 CTAs sharing the X tile through TMA multicast
     int scan_variant = MVDB_SCAN_AUTO;
     int fused_k_max = 128;
     int grid_ctas = 0;
@@ -671,13 +671,15 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
     init_batch_state_kernel<<<unsigned((nq + 255) / 256), 256, 0, stream>>>(ws->b_thr, ws->b_cnt, ws->b_ovf, nq);
     LAUNCHED();
 
-    CUtensorMap tmQ, tmX, tmQ2, tmX2;
+    CUtensorMap tmQ, tmX, tmQ2, tmX2, tmX4;
     RC_OK(encode_bf16_map(&tmQ, ws->b_q16, uint64_t(nq), ix->d, ix->ld16, kGemmBM));
     tmQ2 = tmQ;   // the pair kernel loads 128-query boxes too
     tmX2 = tmQ;
+    tmX4 = tmQ;
     CU_OK(cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes)));
     CU_OK(cudaFuncSetAttribute(gemm_topk_kernel_2cta, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemm2SmemBytes)));
-    CU_OK(cudaFuncSetAttribute(gemm_topk_kernel_mc, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes)));
+    CU_OK(cudaFuncSetAttribute(gemm_topk_kernel_mc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes)));
+    CU_OK(cudaFuncSetAttribute(gemm_topk_kernel_mc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes)));
     CU_OK(cudaFuncSetAttribute(cand_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kCandCap * 8)));
 
     // rigorous bound on |bf16 score - fp32 score| per unit |q|: inputs rounded to nearest
@@ -743,6 +745,7 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
         const uint32_t words = (m + 31) / 32;
         RC_OK(encode_bf16_map(&tmX, ix->mat16.ptr(), m, ix->d, ix->ld16 * int64_t(S), kGemmBN));
         if (ix->gemm_variant >= 1) RC_OK(encode_bf16_map(&tmX2, ix->mat16.ptr(), m, ix->d, ix->ld16 * int64_t(S), kGemmBN / 2));
+        if (ix->gemm_variant == 3) RC_OK(encode_bf16_map(&tmX4, ix->mat16.ptr(), m, ix->d, ix->ld16 * int64_t(S), kGemmBN / 4));
         gp.row_stride = S;
         gp.row0 = 0;
         gp.row1 = uint32_t(align_up(m, kGemmBN));
@@ -793,10 +796,25 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
         for (uint32_t hi : cuts) {
             gp.row0 = lo;
             gp.row1 = hi;
-            if (ix->gemm_variant == 2 && nq > kGemmBM) {
-                const uint64_t tiles2 = uint64_t((hi - lo) / kGemmBN) * ((nq + 2 * kGemmBM - 1) / (2 * kGemmBM));
-                const unsigned pairs = unsigned(std::min<uint64_t>(uint64_t(ix->sm_count / 2), tiles2));
-                gemm_topk_kernel_mc<<<2 * pairs, 256, kGemmSmemBytes, stream>>>(tmQ2, tmX2, gp);
+            if (ix->gemm_variant >= 2 && nq > kGemmBM) {
+                // clusters of CS CTAs share one X tile through TMA multicast (CS query blocks at once)
+                const int cs = (ix->gemm_variant == 3 && nq > 2 * kGemmBM) ? 4 : 2;
+                const uint64_t tiles2 = uint64_t((hi - lo) / kGemmBN) * ((nq + cs * kGemmBM - 1) / (cs * kGemmBM));
+                const unsigned clusters = unsigned(std::min<uint64_t>(uint64_t(ix->sm_count / cs), tiles2));
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(clusters * cs);
+                cfg.blockDim = dim3(256);
+                cfg.dynamicSmemBytes = kGemmSmemBytes;
+                cfg.stream = stream;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = unsigned(cs);
+                attr[0].val.clusterDim.y = 1;
+                attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr;
+                cfg.numAttrs = 1;
+                if (cs == 4) CU_OK(cudaLaunchKernelEx(&cfg, gemm_topk_kernel_mc<4>, tmQ2, tmX4, gp));
+                else CU_OK(cudaLaunchKernelEx(&cfg, gemm_topk_kernel_mc<2>, tmQ2, tmX2, gp));
             } else if (ix->gemm_variant == 1 && nq > kGemmBM) {
                 // CTA pairs: 256-query x 256-row tiles, B operand split across the pair
                 const uint64_t tiles2 = uint64_t((hi - lo) / kGemmBN) * ((nq + 2 * kGemmBM - 1) / (2 * kGemmBM));
@@ -1212,7 +1230,7 @@ int mvdb_index_set_option(mvdb_index* ix, const char* name, int64_t value) {
         if (value < 0 || value > 2) return fail(MVDB_ERR_ARG, "batch_mode must be 0 (off), 1 (exact) or 2 (bf16)");
         ix->batch_mode = int(value);
     } else if (s == "gemm_variant") {
-        if (value < 0 || value > 2) return fail(MVDB_ERR_ARG, "gemm_variant must be 0, 1 or 2");
+        if (value < 0 || value > 3) return fail(MVDB_ERR_ARG, "gemm_variant must be 0..3");
         ix->gemm_variant = int(value);
     } else if (s == "gemm_l2_hint") {
         if (value < 0 || value > 2) return fail(MVDB_ERR_ARG, "gemm_l2_hint must be 0..2");

@@ -155,7 +155,7 @@ def test_batched_adversarial_periodic_filter_overflows_and_falls_back(mv):
     eng.close()
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 @pytest.mark.parametrize("n,d,nq", [(1000, 64, 256), (5000, 1000, 300), (4096, 1024, 512), (70_000, 384, 1000)])
 def test_tcgen05_2cta_gemm_matches_bf16_matmul(mv, n, d, nq, variant):
     """cta_group::2 variant (CTA pairs, 256 x 256 tiles) and TMA-multicast variant (cluster of 2
@@ -186,7 +186,7 @@ def test_batched_2cta_exact_is_bit_identical_to_the_scan(mv):
     eng.set_option("gemm_variant", 0)
     D0, I0 = eng.search(q, k, mask=adm)
     assert np.array_equal(Is, I0[:64]) and np.array_equal(Ds, D0[:64])
-    for variant in (1, 2):
+    for variant in (1, 2, 3):
         eng.set_option("gemm_variant", variant)
         Db, Ib = eng.search(q, k, mask=adm)
         assert np.array_equal(I0, Ib) and np.array_equal(D0, Db), variant
