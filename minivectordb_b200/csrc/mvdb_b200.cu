@@ -384,7 +384,7 @@ struct mvdb_index {
     int batch_mode = 1;            // 0 off, 1 exact (bf16 candidates + fp32 re-scoring), 2 bf16
     int batch_min_nq = 9;
     int gemm_l2_hint = 0;
-    int gemm_variant = 0;          // 0: one CTA per 128x256 tile; 1: CTA pairs (cta_group::2), 256x256 tiles;
+    int gemm_variant = 2;          // 0: one CTA per 128x256 tile; 1: CTA pairs (cta_group::2), 256x256 tiles;
                                    // 2 / 3: cluster of 2 / 4 CTAs sharing the X tile through TMA multicast
     int scan_variant = MVDB_SCAN_AUTO;
     int fused_k_max = 128;
