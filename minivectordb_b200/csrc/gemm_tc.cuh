@@ -18,11 +18,12 @@
 //
 // Tile: 128 queries (UMMA M, one TMEM lane per query) x 256 rows (UMMA N, one
 // TMEM column per row) x 64 bf16 of K per stage (= 128 B, SWIZZLE_128B).
-// Warp roles (256 threads, 1 CTA/SM, persistent):
+// Warp roles (384 threads, 1 CTA/SM, persistent):
 //   warp 0  TMA producer   cp.async.bulk.tensor.2d -> 4-stage smem ring
 //   warp 1  MMA issuer     one elected lane, tcgen05.mma.cta_group::1.kind::f16
 //   warp 2  TMEM allocator 512 columns = 2 accumulator stages x 256
-//   warps 4-7 epilogue     tcgen05.ld 32x32b.x32: thread <-> query, columns <-> rows
+//   warps 4-11 epilogue    tcgen05.ld 32x32b.x32: thread <-> query, columns <-> rows; two warps per
+//                          TMEM lane quadrant, each taking 128 of the 256 columns
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -148,15 +149,17 @@ __device__ __forceinline__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
 // Epilogue of one 128 x 256 accumulator tile for the query owned by this thread (TMEM lane).
 // t_lane: TMEM address of this warp's lane quadrant and accumulator stage; tile_row0: first
 // (sampled) row of the tile; adm: admissible bits of the tile's 256 rows (common masks).
+// g_lo .. g_lo+3: the four 32-column groups (half of the tile) this warp handles -- two warps
+// share each TMEM lane quadrant and split the 256 columns between them.
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t t_lane, int64_t q, uint32_t tile_row0,
-                                                   const uint32_t (&adm)[8]) {
+                                                   const uint32_t (&adm)[8], int g_lo) {
     const bool q_ok = q < p.nq;
     const uint64_t thr = (q_ok && p.thr) ? p.thr[q] : kEmptyKey;
     const uint32_t* qm = (q_ok && p.qmask) ? p.qmask[q] : nullptr;   // this query's own filter
     const uint32_t qm_words = qm ? p.qmask_words[q] : 0u;
     if (p.dense) {
 #pragma unroll 1
-        for (int c0 = 0; c0 < kGemmBN; c0 += 32) {
+        for (int c0 = 32 * g_lo; c0 < 32 * g_lo + 128; c0 += 32) {
             uint32_t v[32];
             tmem_ld_32x32(t_lane + uint32_t(c0), v);
             if (q_ok) {
@@ -172,10 +175,10 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
         // work, branch-free, no memory operation inside a divergent region.  The
         // group loop is deliberately NOT unrolled: fully unrolled the epilogue is
         // ~200 KB of SASS and becomes instruction-fetch bound (measured: 10x slower).
-        uint32_t hit[8];
+        uint32_t hit[4];
         uint32_t total = 0;
 #pragma unroll 1
-        for (int g = 0; g < 8; g++) {
+        for (int g = g_lo; g < g_lo + 4; g++) {
             uint32_t v[32];
             tmem_ld_32x32(t_lane + uint32_t(32 * g), v);
             uint32_t m = 0;
@@ -193,7 +196,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
                 const uint32_t w = (tile_row0 >> 5) + uint32_t(g);
                 m &= (w < qm_words) ? qm[w] : 0u;
             }
-            hit[g] = m;
+            hit[g - g_lo] = m;
             total += __popc(m);
         }
         // One reservation per thread per tile, then (rarely) pass 2: re-read the groups
@@ -202,8 +205,8 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
         if (total) pos = atomicAdd(p.cand_cnt + q, total);
         if (__any_sync(0xFFFFFFFFu, total != 0u)) {
 #pragma unroll 1
-            for (int g = 0; g < 8; g++) {
-                uint32_t m = hit[g];
+            for (int g = g_lo; g < g_lo + 4; g++) {
+                uint32_t m = hit[g - g_lo];
                 if (!__any_sync(0xFFFFFFFFu, m != 0u)) continue;
                 uint32_t v[32];
                 tmem_ld_32x32(t_lane + uint32_t(32 * g), v);
@@ -229,7 +232,7 @@ struct GemmBarriers {
     uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmX, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -243,7 +246,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         for (int a = 0; a < 2; a++) {
             mbar_init(&bars->tfull[a], 1);
-            mbar_init(&bars->tempty[a], 4);   // one arrival per epilogue warp
+            mbar_init(&bars->tempty[a], 8);   // one arrival per epilogue warp
         }
         mbar_fence_init();
         tma_prefetch_desc(&tmQ);
@@ -311,7 +314,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 }
         }
     } else if (warp >= 4) {
-        const uint32_t quad = uint32_t(warp - 4);            // == warp % 4: the TMEM lane quadrant this warp may read
+        const uint32_t quad = uint32_t(warp & 3);            // the TMEM lane quadrant this warp may read (warp % 4)
+        const int g_lo = warp >= 8 ? 4 : 0;                   // warps 4-7: columns 0-127, warps 8-11: columns 128-255
         uint32_t acc = 0, acc_phase = 0;
         uint32_t cur_xt = 0xFFFFFFFFu, tile_row0 = 0;
         uint32_t adm[8];
@@ -338,7 +342,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 const int64_t q = int64_t(qb) * kGemmBM + quad * 32 + lane;
                 mbar_wait(&bars->tfull[acc], acc_phase);
                 tc_fence_after();
-                gemm_epilogue_tile(p, tmem_base + ((quad * 32u) << 16) + acc * kGemmBN, q, tile_row0, adm);
+                gemm_epilogue_tile(p, tmem_base + ((quad * 32u) << 16) + acc * kGemmBN, q, tile_row0, adm, g_lo);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->tempty[acc]);
@@ -425,7 +429,7 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar, uint16_t mask) {
         : "memory");
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 gemm_topk_kernel_2cta(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmX, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -442,7 +446,7 @@ gemm_topk_kernel_2cta(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         }
         for (int a = 0; a < 2; a++) {
             mbar_init(&bars->tfull[a], 1);
-            mbar_init(&bars->tempty[a], 8);   // 4 epilogue warps x 2 CTAs (waited on by the leader only)
+            mbar_init(&bars->tempty[a], 16);  // 8 epilogue warps x 2 CTAs (waited on by the leader only)
         }
         mbar_fence_init();
         tma_prefetch_desc(&tmQ);
@@ -516,7 +520,8 @@ gemm_topk_kernel_2cta(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             }
         }
     } else if (warp >= 4) {
-        const uint32_t quad = uint32_t(warp - 4);
+        const uint32_t quad = uint32_t(warp & 3);
+        const int g_lo = warp >= 8 ? 4 : 0;
         uint32_t acc = 0, acc_phase = 0;
         uint32_t cur_xt = 0xFFFFFFFFu, tile_row0 = 0;
         uint32_t adm[8];
@@ -541,7 +546,7 @@ gemm_topk_kernel_2cta(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             const int64_t q = int64_t(qb2) * 2 * kGemmBM + rank * kGemmBM + quad * 32 + lane;
             mbar_wait(&bars->tfull[acc], acc_phase);
             tc_fence_after();
-            gemm_epilogue_tile(p, tmem_base + ((quad * 32u) << 16) + acc * kGemmBN, q, tile_row0, adm);
+            gemm_epilogue_tile(p, tmem_base + ((quad * 32u) << 16) + acc * kGemmBN, q, tile_row0, adm, g_lo);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -583,7 +588,7 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
 
 // CS = cluster size (2 or 4): CS query blocks share one X tile; each CTA fetches 1/CS of it.
 template <int CS>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_topk_kernel_mc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmXh, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -598,7 +603,7 @@ gemm_topk_kernel_mc(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         for (int a = 0; a < 2; a++) {
             mbar_init(&bars->tfull[a], 1);
-            mbar_init(&bars->tempty[a], 4);
+            mbar_init(&bars->tempty[a], 8);
         }
         mbar_fence_init();
         tma_prefetch_desc(&tmQ);
@@ -662,7 +667,8 @@ gemm_topk_kernel_mc(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
         }
     } else if (warp >= 4) {
-        const uint32_t quad = uint32_t(warp - 4);
+        const uint32_t quad = uint32_t(warp & 3);
+        const int g_lo = warp >= 8 ? 4 : 0;
         uint32_t acc = 0, acc_phase = 0;
         uint32_t cur_xt = 0xFFFFFFFFu, tile_row0 = 0;
         uint32_t adm[8];
@@ -687,7 +693,7 @@ gemm_topk_kernel_mc(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             const int64_t q = int64_t(qb) * kGemmBM + quad * 32 + lane;
             mbar_wait(&bars->tfull[acc], acc_phase);
             tc_fence_after();
-            gemm_epilogue_tile(p, tmem_base + ((quad * 32u) << 16) + acc * kGemmBN, q, tile_row0, adm);
+            gemm_epilogue_tile(p, tmem_base + ((quad * 32u) << 16) + acc * kGemmBN, q, tile_row0, adm, g_lo);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->tempty[acc]);

@@ -803,7 +803,7 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
                 const unsigned clusters = unsigned(std::min<uint64_t>(uint64_t(ix->sm_count / cs), tiles2));
                 cudaLaunchConfig_t cfg = {};
                 cfg.gridDim = dim3(clusters * cs);
-                cfg.blockDim = dim3(256);
+                cfg.blockDim = dim3(384);
                 cfg.dynamicSmemBytes = kGemmSmemBytes;
                 cfg.stream = stream;
                 cudaLaunchAttribute attr[1];
@@ -819,11 +819,11 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
                 // CTA pairs: 256-query x 256-row tiles, B operand split across the pair
                 const uint64_t tiles2 = uint64_t((hi - lo) / kGemmBN) * ((nq + 2 * kGemmBM - 1) / (2 * kGemmBM));
                 const unsigned pairs = unsigned(std::min<uint64_t>(uint64_t(ix->sm_count / 2), tiles2));
-                gemm_topk_kernel_2cta<<<2 * pairs, 256, kGemm2SmemBytes, stream>>>(tmQ2, tmX2, gp);
+                gemm_topk_kernel_2cta<<<2 * pairs, 384, kGemm2SmemBytes, stream>>>(tmQ2, tmX2, gp);
             } else {
                 const uint64_t tiles = uint64_t((hi - lo) / kGemmBN) * n_qb;
                 const unsigned grid = unsigned(std::min<uint64_t>(uint64_t(ix->sm_count), tiles));
-                gemm_topk_kernel<<<grid, 256, kGemmSmemBytes, stream>>>(tmQ, tmX, gp);
+                gemm_topk_kernel<<<grid, 384, kGemmSmemBytes, stream>>>(tmQ, tmX, gp);
             }
             LAUNCHED();
             if (!dense_out) {
