@@ -155,6 +155,9 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
                                                    const uint32_t (&adm)[8], int g_lo) {
     const bool q_ok = q < p.nq;
     const uint64_t thr = (q_ok && p.thr) ? p.thr[q] : kEmptyKey;
+    // threshold as (score, ~row): an empty threshold admits every finite score
+    const float thr_score = thr == kEmptyKey ? -INFINITY : key_score(thr);
+    const uint32_t thr_low = thr == kEmptyKey ? 0xFFFFFFFFu : uint32_t(thr);
     const uint32_t* qm = (q_ok && p.qmask) ? p.qmask[q] : nullptr;   // this query's own filter
     const uint32_t qm_words = qm ? p.qmask_words[q] : 0u;
     if (p.dense) {
@@ -186,9 +189,10 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
             const uint32_t low0 = 0xFFFFFFFFu - (tile_row0 + 32 * g) * p.row_stride;
 #pragma unroll
             for (int j = 0; j < 32; j++) {
+                // key(s,row) > thr  <=>  s > t, or s == t and ~row > thr_low  (float compares: NaN never
+                // passes, -0 == +0 exactly as the key's canonicalisation has it)
                 const float s = __uint_as_float(v[j]);
-                const uint64_t key = (uint64_t(score_to_ord(s)) << 32) | uint64_t(low0 - uint32_t(j) * p.row_stride);
-                const uint32_t pass = uint32_t(key > thr) & uint32_t(s == s);   // NaN never passes
+                const uint32_t pass = uint32_t(s > thr_score) | (uint32_t(s == thr_score) & uint32_t((low0 - uint32_t(j) * p.row_stride) > thr_low));
                 m |= pass << j;
             }
             m &= q_ok ? adm[g] : 0u;
