@@ -38,6 +38,7 @@ using namespace mvdb;
 // errors
 // ---------------------------------------------------------------------------
 static thread_local std::string g_err;
+static thread_local bool tl_force_scan = false;   // overflow fallback of the batched path: stay on the fp32 scan
 static std::atomic<uint64_t> g_launches{0};
 
 static int fail(int code, const char* fmt, ...) {
@@ -380,6 +381,7 @@ struct mvdb_index {
     uint64_t shadow_rows = 0;
     std::mutex shadow_mu;
     int* max_norm2_bits = nullptr;  // device: bit pattern of the largest squared row norm stored
+    std::atomic<float> max_norm2_host{0.f};  // host copy, refreshed at the end of every add
     // options
     int batch_mode = 1;            // 0 off, 1 exact (bf16 candidates + fp32 re-scoring), 2 bf16
     int batch_min_nq = 9;
@@ -686,11 +688,7 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
     // bf16 (2^-9 relative each) + fp32 accumulation of d terms, times the largest row norm
     float slack_unit = 0.f;
     if (mode == 1 && !dense_out) {
-        int bits = 0;
-        CU_OK(cudaMemcpyAsync(&bits, ix->max_norm2_bits, sizeof bits, cudaMemcpyDeviceToHost, stream));
-        CU_OK(cudaStreamSynchronize(stream));
-        float max_norm2;
-        memcpy(&max_norm2, &bits, 4);
+        const float max_norm2 = ix->max_norm2_host.load(std::memory_order_acquire);
         const double eps_unit = (std::ldexp(1.0, -8) + std::ldexp(1.0, -18) + double(ix->d) * std::ldexp(1.0, -22)) * 1.01;
         slack_unit = float(2.0 * eps_unit * std::sqrt(std::max(double(max_norm2), 1e-30)) * 1.0001);
     }
@@ -731,12 +729,23 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
     // filtered-out prefix (time-ordered data with a date filter, churn that deletes the oldest
     // rows) cannot flood the candidate lists.  Extra flops: 1/16 + 1/256 + ... = 6.7 %.
     std::vector<uint32_t> strides;
+    // Small batches (one query block) on mid-size matrices are dominated by launch count, not by
+    // candidate volume: two levels are enough when the final level admits <= ~2048 rows per query
+    // (k * stride), and the final level then runs in one piece.
+    bool single_piece = false;
     {
-        uint32_t s0 = 1;
-        while (!dense_out && (uint64_t(n) + s0 - 1) / s0 > kFirstLevel) s0 *= 16;
-        for (uint32_t st_ = s0;; st_ /= 16) {
-            strides.push_back(st_);
-            if (st_ == 1) break;
+        uint32_t s2 = 1;
+        while ((uint64_t(n) + s2 - 1) / s2 > 8192 - 256) s2 *= 2;
+        if (!dense_out && nq <= kGemmBM && s2 > 1 && uint64_t(k) * s2 <= 2048) {
+            strides = {s2, 1};
+            single_piece = true;
+        } else {
+            uint32_t s0 = 1;
+            while (!dense_out && (uint64_t(n) + s0 - 1) / s0 > kFirstLevel) s0 *= 16;
+            for (uint32_t st_ = s0;; st_ /= 16) {
+                strides.push_back(st_);
+                if (st_ == 1) break;
+            }
         }
     }
     for (size_t lv = 0; lv < strides.size(); lv++) {
@@ -786,7 +795,7 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
         // query whatever the row order), the refreshes cut that to ~5 k.
         std::vector<uint32_t> cuts;
         const uint32_t rows_al = gp.row1;
-        if (S == 1 && strides.size() > 1 && rows_al >= 64 * kGemmBN) {
+        if (S == 1 && strides.size() > 1 && rows_al >= 64 * kGemmBN && !single_piece) {
             const uint32_t e = uint32_t(align_up(rows_al / 8, kGemmBN));
             cuts = {e, 2 * e, 4 * e, rows_al};
         } else {
@@ -852,14 +861,13 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
     std::vector<unsigned int> ovf(size_t(nq), 0u);
     CU_OK(cudaMemcpyAsync(ovf.data(), ws->b_ovf, size_t(nq) * 4, cudaMemcpyDeviceToHost, stream));
     CU_OK(cudaStreamSynchronize(stream));
-    const int saved = ix->batch_mode;
     int rc = MVDB_OK;
     for (int64_t q = 0; q < nq && rc == MVDB_OK; q++) {
         if (!ovf[size_t(q)]) continue;
-        ix->batch_mode = 0;
+        tl_force_scan = true;
         rc = run_search(ix, ws, q_dev + q * ix->d, 1, k, mask_dev, n, normalize_q, label_offset, D_dev + q * k, I_dev + q * k,
                         stream, nullptr, qmasks ? qmasks + q : nullptr);
-        ix->batch_mode = saved;
+        tl_force_scan = false;
     }
     return rc;
 }
@@ -911,7 +919,7 @@ static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, in
     // bf16 shadow is half the bytes of the fp32 matrix, so one shadow pass (+ ~0.5 ms of fixed
     // cost, + exact re-scoring) beats the fp32 multi-query scan once a pass costs ~1 ms.
     const bool big_matrix = uint64_t(n) * uint64_t(ix->ld) * 4 >= (uint64_t(6) << 30);
-    if (!xch && ix->batch_mode != 0 && (nq >= ix->batch_min_nq || (nq >= 2 && big_matrix)) && k <= 128 &&
+    if (!xch && !tl_force_scan && ix->batch_mode != 0 && (nq >= ix->batch_min_nq || (nq >= 2 && big_matrix)) && k <= 128 &&
         tensor_map_encoder() != nullptr)
         return run_batched(ix, ws, q_dev, nq, k, mask_dev, n, normalize_q, label_offset, D_dev, I_dev, stream,
                            ix->batch_mode, nullptr, any_qmask ? qmasks : nullptr);
@@ -1295,7 +1303,14 @@ static int add_common(mvdb_index* ix, const float* x_host, const float* x_dev, b
         LAUNCHED();
     }
     CU_OK(cudaGetLastError());
-    CU_OK(cudaStreamSynchronize(st));
+    {
+        int bits = 0;
+        CU_OK(cudaMemcpyAsync(&bits, ix->max_norm2_bits, sizeof bits, cudaMemcpyDeviceToHost, st));
+        CU_OK(cudaStreamSynchronize(st));
+        float f;
+        memcpy(&f, &bits, 4);
+        ix->max_norm2_host.store(f, std::memory_order_release);
+    }
     ix->live_host.resize((n0 + n + 31) / 32, 0u);
     for (uint64_t r = n0; r < n0 + n;) {
         if ((r & 31) == 0 && r + 32 <= n0 + n) {
