@@ -81,7 +81,8 @@ int mvdb_index_reset(mvdb_index* ix);
  *                   fp32 scan), 1 exact (bf16 tcgen05 GEMM selects a rigorous
  *                   candidate superset, survivors re-scored in fp32: same ids and
  *                   distances as the scan; default), 2 bf16 (scores of the bf16 GEMM)
- *   "batch_min_nq"  smallest nq routed to the batched path (default 9 = more than one 8-query scan pass; k <= 128) */
+ *   "batch_min_nq"  floor on the nq routed to the batched path (default 2; above it a cost model
+ *                   picks the cheaper of the fp32 scan passes and one bf16 shadow pass; k <= 128) */
 int mvdb_index_set_option(mvdb_index* ix, const char* name, int64_t value);
 
 /* ---- ingest -------------------------------------------------------------

@@ -384,7 +384,8 @@ struct mvdb_index {
     std::atomic<float> max_norm2_host{0.f};  // host copy, refreshed at the end of every add
     // options
     int batch_mode = 1;            // 0 off, 1 exact (bf16 candidates + fp32 re-scoring), 2 bf16
-    int batch_min_nq = 9;
+    int batch_min_nq = 2;
+    int batch_cost_model = 1;      // 0: every batch of >= batch_min_nq queries takes the tensor path (tests, probes)
     int gemm_l2_hint = 0;
     int gemm_variant = 2;          // 0: one CTA per 128x256 tile; 1: CTA pairs (cta_group::2), 256x256 tiles;
                                    // 2 / 3: cluster of 2 / 4 CTAs sharing the X tile through TMA multicast
@@ -915,11 +916,24 @@ static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, in
     if (qmasks)
         for (int64_t i = 0; i < nq; i++) any_qmask |= qmasks[i].dev != nullptr;
     if (any_qmask && k > ix->fused_k_max) return fail(MVDB_ERR_ARG, "per-query masks need k <= %d", ix->fused_k_max);
-    // Large batches always go to the tensor cores.  On big matrices even 2..8 queries do: the
-    // bf16 shadow is half the bytes of the fp32 matrix, so one shadow pass (+ ~0.5 ms of fixed
-    // cost, + exact re-scoring) beats the fp32 multi-query scan once a pass costs ~1 ms.
-    const bool big_matrix = uint64_t(n) * uint64_t(ix->ld) * 4 >= (uint64_t(6) << 30);
-    if (!xch && !tl_force_scan && ix->batch_mode != 0 && (nq >= ix->batch_min_nq || (nq >= 2 && big_matrix)) && k <= 128 &&
+    // Scan or tensor cores?  A measured cost model (B200): the fp32 scan serves 1/2/4/8 queries
+    // per pass at 1.0/1.08/1.2/2.3 x the stream time of the matrix plus ~40 us per launch; the
+    // batched path costs ~330 us of fixed work (levels, threshold refreshes, re-scoring) plus one
+    // pass over the half-size bf16 shadow plus the GEMM itself.  `batch_min_nq` is only a floor.
+    bool use_tc = false;
+    {
+        const double bytes32 = double(n) * double(ix->ld) * 4.0;
+        double t_scan = 0.0;
+        for (int64_t rem = nq; rem > 0;) {
+            const int g = rem >= 8 ? 8 : rem >= 4 ? 4 : rem >= 2 ? 2 : 1;
+            const double f = g == 8 ? 2.3 : g == 4 ? 1.2 : g == 2 ? 1.08 : 1.0;
+            t_scan += 40e-6 + f * bytes32 / 6.4e12;
+            rem -= g;
+        }
+        const double t_tc = 330e-6 + 1.07 * (bytes32 * 0.5) / 6.0e12 + 2.0 * double(nq) * double(n) * double(ix->d) / 900e12;
+        use_tc = nq >= ix->batch_min_nq && (ix->batch_cost_model ? (nq >= 2 && t_tc < t_scan) : true);
+    }
+    if (!xch && !tl_force_scan && ix->batch_mode != 0 && use_tc && k <= 128 &&
         tensor_map_encoder() != nullptr)
         return run_batched(ix, ws, q_dev, nq, k, mask_dev, n, normalize_q, label_offset, D_dev, I_dev, stream,
                            ix->batch_mode, nullptr, any_qmask ? qmasks : nullptr);
@@ -1243,6 +1257,8 @@ int mvdb_index_set_option(mvdb_index* ix, const char* name, int64_t value) {
     } else if (s == "gemm_l2_hint") {
         if (value < 0 || value > 2) return fail(MVDB_ERR_ARG, "gemm_l2_hint must be 0..2");
         ix->gemm_l2_hint = int(value);
+    } else if (s == "batch_cost_model") {
+        ix->batch_cost_model = value != 0;
     } else if (s == "batch_min_nq") {
         if (value < 1) return fail(MVDB_ERR_ARG, "batch_min_nq must be >= 1");
         ix->batch_min_nq = int(value);

@@ -32,6 +32,7 @@ def test_tcgen05_gemm_matches_bf16_matmul(mv, n, d, nq):
     import torch
     x, q = _data(n, d, nq, seed=n + d)
     eng = mv.FlatIPEngine(d)
+    eng.set_option("batch_cost_model", 0)   # always exercise the tensor path here
     eng.add(x)
     got = eng.debug_gemm_scores(q)
     xb = torch.from_numpy(x).to(torch.bfloat16).to(torch.float64)
@@ -48,6 +49,7 @@ def test_tcgen05_gemm_matches_bf16_matmul(mv, n, d, nq):
 def test_batched_exact_is_bit_identical_to_the_scan(mv, n, d, nq, k):
     x, q = _data(n, d, nq, seed=k + d)
     eng = mv.FlatIPEngine(d)
+    eng.set_option("batch_cost_model", 0)   # always exercise the tensor path here
     eng.add(x)
     rng = np.random.default_rng(0)
     dead = rng.choice(n, n // 10, replace=False)
@@ -75,6 +77,7 @@ def test_batched_bf16_mode_recall(mv):
     n, d, nq, k = 100_000, 384, 256, 10
     x, q = _data(n, d, nq, seed=3)
     eng = mv.FlatIPEngine(d)
+    eng.set_option("batch_cost_model", 0)   # always exercise the tensor path here
     eng.add(x)
     eng.set_option("batch_mode", 2)
     D, I = eng.search(q, k)
@@ -95,6 +98,7 @@ def test_batched_overflow_falls_back_to_the_scan(mv):
     order = np.argsort(x @ q[0])
     x = np.ascontiguousarray(x[order])
     eng = mv.FlatIPEngine(d)
+    eng.set_option("batch_cost_model", 0)   # always exercise the tensor path here
     eng.add(x)
     D, I = eng.search(q, k)
     Dr, Ir = O.search_flat_ip(x, q, k)
@@ -106,6 +110,7 @@ def test_batched_overflow_falls_back_to_the_scan(mv):
 def test_batched_path_follows_appends(mv):
     x, q = _data(20_000, 128, 64, seed=9)
     eng = mv.FlatIPEngine(128)
+    eng.set_option("batch_cost_model", 0)
     eng.add(x[:5000])
     eng.search(q, 10)              # builds the bf16 shadow for 5000 rows
     eng.add(x[5000:])              # shadow must be extended lazily
@@ -123,6 +128,7 @@ def test_batched_is_robust_to_row_order_and_dead_prefixes(mv):
     n, d, nq, k = 120_000, 128, 48, 10
     x, q = _data(n, d, nq, seed=31)
     eng = mv.FlatIPEngine(d)
+    eng.set_option("batch_cost_model", 0)   # always exercise the tensor path here
     eng.add(x)
     eng.remove_rows(np.arange(0, 70_000))             # the first 58 % of the rows are tombstones
     live = np.ones(n, dtype=bool)
@@ -147,6 +153,7 @@ def test_batched_adversarial_periodic_filter_overflows_and_falls_back(mv):
     n, d, nq, k = 40_000, 64, 40, 10
     x, q = _data(n, d, nq, seed=33)
     eng = mv.FlatIPEngine(d)
+    eng.set_option("batch_cost_model", 0)   # always exercise the tensor path here
     eng.add(x)
     odd = (np.arange(n) % 2) == 1
     D, I = eng.search(q, k, mask=odd)
@@ -163,6 +170,7 @@ def test_tcgen05_2cta_gemm_matches_bf16_matmul(mv, n, d, nq, variant):
     import torch
     x, q = _data(n, d, nq, seed=n + d + 1)
     eng = mv.FlatIPEngine(d)
+    eng.set_option("batch_cost_model", 0)   # always exercise the tensor path here
     eng.set_option("gemm_variant", variant)
     eng.add(x)
     got = eng.debug_gemm_scores(q)
@@ -178,6 +186,7 @@ def test_batched_2cta_exact_is_bit_identical_to_the_scan(mv):
     n, d, nq, k = 60_000, 384, 700, 10
     x, q = _data(n, d, nq, seed=77)
     eng = mv.FlatIPEngine(d)
+    eng.set_option("batch_cost_model", 0)   # always exercise the tensor path here
     eng.add(x)
     adm = np.random.default_rng(0).random(n) < 0.5
     eng.set_option("batch_mode", 0)

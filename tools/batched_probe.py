@@ -36,6 +36,7 @@ for n, d, nqs, k in configs:
         ref = None
         for mode in (1, 2, 0):
             eng.set_option("batch_min_nq", 1)
+            eng.set_option("batch_cost_model", 0)
             if mode == 0 and nq > 256:
                 continue  # fp32 scan of thousands of queries is only a sanity baseline
             eng.set_option("batch_mode", mode)
