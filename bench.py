@@ -277,9 +277,10 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "rows_per_gpu": n, "rows_total": n * world, "dim": d, "k": k,
                        "filter_keep": None if args.no_filter else float(adm.mean()),
-                       "l2": f"matrix {n * ld * 4 / 1e9:.2f} GB per GPU >> 126 MB L2 (no flush needed)",
+                       "l2": f"matrix {n * ld * 4 / 1e9:.2f} GB per GPU vs 126 MB L2; streamed with L2 evict_first, "
+                             "distinct query each step (no flush needed above ~0.3 GB)",
                        "unit_note": "value = shard scans/s over all ranks = n_gpus x global QPS "
-                                    "(each rank scans its own 1M x 384 shard per query)",
+                                    f"(each rank scans its own {n} x {d} shard per query)",
                        "parallelism": f"row-shard x{world}" + (f", exchange={index.exchange}" if world > 1 else "")},
             "qps_global": qps_global,
             "p50_latency_us": float(np.median(per_step) * 1e6),
