@@ -162,6 +162,22 @@ int mvdb_mask_destroy(mvdb_mask* m);
 int mvdb_index_search_with_mask(mvdb_index* ix, const float* q, int64_t nq, int64_t k, const mvdb_mask* m,
                                 int normalize_queries, float* D, int64_t* I);
 
+/* Device-side filter evaluation (the producer of the mask, vector_database.py:354-386).
+ * A numeric metadata column is kept in HBM row-aligned with the index (value + presence bit
+ * per row); predicates ($gt $gte $lt $lte $ne, equality: op 2 3 4 5 1 0) and the AND / OR /
+ * exclude combinators (how 0 / 1 / 2 = and-not) run as small kernels and yield a mask handle
+ * directly -- no per-row Python, no mask upload.  Rows lacking the key never match, as in
+ * the reference's inverted-index walk (vector_database.py:260). */
+typedef struct mvdb_column mvdb_column;
+int mvdb_column_create(mvdb_index* ix, mvdb_column** out);
+int mvdb_column_destroy(mvdb_column* c);
+/* rows [len, len+n): values[n] (double), present[n] (0/1 bytes) */
+int mvdb_column_append(mvdb_column* c, const double* values, const uint8_t* present, uint64_t n);
+int mvdb_mask_from_predicate(mvdb_index* ix, const mvdb_column* c, int op, double operand, mvdb_mask** out);
+int mvdb_mask_create_filled(mvdb_index* ix, uint64_t rows, mvdb_mask** out);   /* all rows admissible */
+int mvdb_mask_combine(mvdb_mask* dst, const mvdb_mask* src, int how);
+int mvdb_mask_count(const mvdb_mask* m, uint64_t* count);                     /* admissible AND live rows */
+
 /* Device-buffer flavour for callers that keep queries/results in HBM (the
  * sharded path and the bench's device-resident leg).  All pointers are device
  * pointers on the index's device; `stream` is a cudaStream_t (NULL = default

@@ -37,6 +37,8 @@ EXPORTS = [
     "mvdb_exchange_create", "mvdb_exchange_ipc_handle", "mvdb_exchange_connect", "mvdb_exchange_set_offsets",
     "mvdb_exchange_status", "mvdb_exchange_destroy", "mvdb_index_search_exchange", "mvdb_debug_gemm_scores",
     "mvdb_index_mask_create", "mvdb_mask_destroy", "mvdb_index_search_with_mask",
+    "mvdb_column_create", "mvdb_column_destroy", "mvdb_column_append", "mvdb_mask_from_predicate",
+    "mvdb_mask_create_filled", "mvdb_mask_combine", "mvdb_mask_count",
 ]
 
 
@@ -136,6 +138,13 @@ def lib():
             "mvdb_index_mask_create": (i, [c_vp, c_vp, u64, ctypes.POINTER(c_vp)]),
             "mvdb_mask_destroy": (i, [c_vp]),
             "mvdb_index_search_with_mask": (i, [c_vp, c_vp, i64, i64, c_vp, i, c_vp, c_vp]),
+            "mvdb_column_create": (i, [c_vp, ctypes.POINTER(c_vp)]),
+            "mvdb_column_destroy": (i, [c_vp]),
+            "mvdb_column_append": (i, [c_vp, c_vp, c_vp, u64]),
+            "mvdb_mask_from_predicate": (i, [c_vp, c_vp, i, ctypes.c_double, ctypes.POINTER(c_vp)]),
+            "mvdb_mask_create_filled": (i, [c_vp, u64, ctypes.POINTER(c_vp)]),
+            "mvdb_mask_combine": (i, [c_vp, c_vp, i]),
+            "mvdb_mask_count": (i, [c_vp, ctypes.POINTER(u64)]),
             "mvdb_index_search_exchange": (i, [c_vp, c_vp, c_vp, c_vp, i64, i64, c_vp, u64, i, c_vp, c_vp, c_vp]),
         }
         for name, (res, args) in sig.items():

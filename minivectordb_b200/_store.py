@@ -298,6 +298,21 @@ class GpuStore:
                     self._mask_cache.move_to_end(key)
                     count, jobs = hit[1], hit[2]
                     adm = False  # placeholder: "filtered"
+                elif (len(self._parts) == 1 and self._parts[0].engine is not None
+                      and hasattr(self._parts[0].engine, "column") and self._parts[0].flushed == n):
+                    # single GPU: the filter is evaluated ON the device (numeric predicates by a
+                    # kernel over HBM-resident columns, the rest uploaded once) and combined there
+                    part = self._parts[0]
+                    handle = self._filters.admissible_device(part.engine, n, metadata_filter, exclude_filter, or_filters)
+                    count = handle.count()
+                    if count == 0:
+                        return [], [], []
+                    jobs = [(part, part.gids, handle)]
+                    adm = False
+                    if key is not None:
+                        self._mask_cache[key] = (self._version, count, jobs)
+                        while len(self._mask_cache) > self.MASK_CACHE_ENTRIES:
+                            self._mask_cache.popitem(last=False)
                 else:
                     adm = self._filters.admissible(live, metadata_filter, exclude_filter, or_filters)
             else:

@@ -85,6 +85,62 @@ __global__ void clear_live_rows_kernel(uint32_t* live, const int64_t* rows, uint
     atomicAnd(live + (r >> 5), ~(1u << uint32_t(r & 31)));
 }
 
+// ---------------------------------------------------------------------------
+// Device-side filter evaluation: a numeric metadata column lives in
+// HBM next to the matrix (value + presence bit per row); a predicate becomes a bitmask without
+// touching the host.  Replaces the per-row Python loops of ref vector_database.py:157-352 for
+// the operators $gt $gte $lt $lte $ne and equality on numbers.  One thread per 32-row word.
+// ---------------------------------------------------------------------------
+enum { kOpEq = 0, kOpNe = 1, kOpGt = 2, kOpGe = 3, kOpLt = 4, kOpLe = 5 };
+__global__ void predicate_mask_kernel(const double* __restrict__ vals, const uint32_t* __restrict__ has, uint64_t n,
+                                      int op, double x, uint32_t* __restrict__ out, uint32_t words) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= words) return;
+    const uint32_t present = has[w];
+    uint32_t bits = 0;
+    for (int j = 0; j < 32; j++) {
+        const uint64_t r = uint64_t(w) * 32 + j;
+        if (r >= n) break;
+        if (!((present >> j) & 1u)) continue;   // only rows that HAVE the key can match (inverted index, VDB:260)
+        const double v = vals[r];
+        bool ok;
+        switch (op) {
+            case kOpEq: ok = v == x; break;
+            case kOpNe: ok = v != x; break;
+            case kOpGt: ok = v > x; break;
+            case kOpGe: ok = v >= x; break;
+            case kOpLt: ok = v < x; break;
+            default: ok = v <= x; break;
+        }
+        bits |= uint32_t(ok) << j;
+    }
+    out[w] = bits;
+}
+// dst = dst AND src (0) / dst OR src (1) / dst AND NOT src (2); words past src_words read as 0
+__global__ void combine_mask_kernel(uint32_t* dst, uint32_t dst_words, const uint32_t* __restrict__ src, uint32_t src_words,
+                                    int how) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= dst_words) return;
+    const uint32_t s = w < src_words ? src[w] : 0u;
+    const uint32_t d = dst[w];
+    dst[w] = how == 0 ? (d & s) : how == 1 ? (d | s) : (d & ~s);
+}
+__global__ void fill_mask_kernel(uint32_t* dst, uint64_t rows, uint32_t words) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= words) return;
+    const uint64_t lo = uint64_t(w) * 32;
+    dst[w] = rows >= lo + 32 ? 0xFFFFFFFFu : (rows > lo ? ((1u << uint32_t(rows - lo)) - 1u) : 0u);
+}
+// admissible AND live rows
+__global__ void count_mask_kernel(const uint32_t* __restrict__ mask, const uint32_t* __restrict__ live, uint32_t words,
+                                  unsigned long long* out) {
+    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int c = 0;
+    if (w < words) c = __popc(mask[w] & (live ? live[w] : 0xFFFFFFFFu));
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
+}
+
 // order-preserving compaction: scratch[i] = x[src_rows[i]] (whole padded rows)
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float4* __restrict__ x, float4* __restrict__ out,
                                                           const uint32_t* __restrict__ src_rows, uint64_t m,

@@ -342,6 +342,13 @@ struct mvdb_mask {         // device-resident filter, uploaded once, reusable by
     uint32_t words;
 };
 
+struct mvdb_column {       // one numeric metadata column, row-aligned with the index
+    mvdb_index* ix;
+    double* vals = nullptr;
+    uint32_t* has = nullptr;
+    uint64_t len = 0, cap = 0;   // rows
+};
+
 struct CoalesceReq {
     const float* q;
     int64_t k;
@@ -1735,6 +1742,146 @@ int mvdb_mask_destroy(mvdb_mask* m) {
 
 static int search_entry(mvdb_index* ix, const float* q, int64_t nq, int64_t k, const uint8_t* mask, uint64_t mask_rows,
                         const mvdb_mask* handle, int normalize_queries, float* D, int64_t* I);
+
+// ---- device-side filter evaluation -------------------------------------------------------
+int mvdb_column_create(mvdb_index* ix, mvdb_column** out) {
+    if (!ix || !out) return fail(MVDB_ERR_ARG, "null argument");
+    *out = new mvdb_column();
+    (*out)->ix = ix;
+    return MVDB_OK;
+}
+
+int mvdb_column_destroy(mvdb_column* c) {
+    if (!c) return MVDB_OK;
+    DeviceGuard guard(c->ix->device);
+    cudaFree(c->vals);
+    cudaFree(c->has);
+    delete c;
+    return MVDB_OK;
+}
+
+int mvdb_column_append(mvdb_column* c, const double* values, const uint8_t* present, uint64_t n) {
+    if (!c) return fail(MVDB_ERR_ARG, "null column");
+    if (n == 0) return MVDB_OK;
+    if (!values || !present) return fail(MVDB_ERR_ARG, "null data");
+    ENTER(c->ix);
+    const uint64_t need = c->len + n;
+    if (need > c->cap) {
+        const uint64_t ncap = align_up(std::max<uint64_t>(need, c->cap * 2), 1024);
+        double* nv = nullptr;
+        uint32_t* nh = nullptr;
+        CU_OK(cudaMalloc(&nv, ncap * 8));
+        cudaError_t e = cudaMalloc(&nh, ncap / 8 + 8);
+        if (e == cudaSuccess) e = cudaMemset(nh, 0, ncap / 8 + 8);
+        if (e == cudaSuccess && c->len) e = cudaMemcpy(nv, c->vals, c->len * 8, cudaMemcpyDeviceToDevice);
+        if (e == cudaSuccess && c->len) e = cudaMemcpy(nh, c->has, (c->len + 31) / 32 * 4, cudaMemcpyDeviceToDevice);
+        if (e != cudaSuccess) {
+            cudaFree(nv);
+            cudaFree(nh);
+            return fail(MVDB_ERR_CUDA, "column growth failed: %s", cudaGetErrorString(e));
+        }
+        cudaFree(c->vals);
+        cudaFree(c->has);
+        c->vals = nv;
+        c->has = nh;
+        c->cap = ncap;
+    }
+    CU_OK(cudaMemcpy(c->vals + c->len, values, n * 8, cudaMemcpyHostToDevice));
+    // presence bits: merge the partially filled first word on the host
+    const uint64_t w0 = c->len / 32, w1 = (need + 31) / 32;
+    std::vector<uint32_t> words(size_t(w1 - w0), 0u);
+    if (c->len % 32) CU_OK(cudaMemcpy(words.data(), c->has + w0, 4, cudaMemcpyDeviceToHost));
+    for (uint64_t i = 0; i < n; i++)
+        if (present[i]) {
+            const uint64_t r = c->len + i;
+            words[size_t(r / 32 - w0)] |= 1u << (r % 32);
+        }
+    CU_OK(cudaMemcpy(c->has + w0, words.data(), words.size() * 4, cudaMemcpyHostToDevice));
+    c->len = need;
+    return MVDB_OK;
+}
+
+static int new_mask(mvdb_index* ix, uint64_t rows, mvdb_mask** out) {
+    const size_t words = std::max<size_t>((rows + 31) / 32, 1);
+    mvdb_mask* m = new mvdb_mask{ix, nullptr, rows, uint32_t((rows + 31) / 32)};
+    cudaError_t e = cudaMalloc(&m->dev, words * 4);
+    if (e != cudaSuccess) {
+        delete m;
+        return fail(MVDB_ERR_OOM, "mask allocation failed: %s", cudaGetErrorString(e));
+    }
+    *out = m;
+    return MVDB_OK;
+}
+
+int mvdb_mask_from_predicate(mvdb_index* ix, const mvdb_column* c, int op, double operand, mvdb_mask** out) {
+    ENTER(ix);
+    if (!c || !out || c->ix != ix) return fail(MVDB_ERR_ARG, "bad column");
+    if (op < 0 || op > 5) return fail(MVDB_ERR_ARG, "bad operator");
+    *out = nullptr;
+    mvdb_mask* m = nullptr;
+    RC_OK(new_mask(ix, c->len, &m));
+    if (m->words) {
+        predicate_mask_kernel<<<(m->words + 255) / 256, 256>>>(c->vals, c->has, c->len, op, operand, m->dev, m->words);
+        LAUNCHED();
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        mvdb_mask_destroy(m);
+        return fail(MVDB_ERR_CUDA, "predicate kernel failed: %s", cudaGetErrorString(e));
+    }
+    *out = m;
+    return MVDB_OK;
+}
+
+int mvdb_mask_create_filled(mvdb_index* ix, uint64_t rows, mvdb_mask** out) {
+    ENTER(ix);
+    if (!out) return fail(MVDB_ERR_ARG, "null out");
+    *out = nullptr;
+    mvdb_mask* m = nullptr;
+    RC_OK(new_mask(ix, rows, &m));
+    if (m->words) {
+        fill_mask_kernel<<<(m->words + 255) / 256, 256>>>(m->dev, rows, m->words);
+        LAUNCHED();
+    }
+    *out = m;
+    return MVDB_OK;
+}
+
+int mvdb_mask_combine(mvdb_mask* dst, const mvdb_mask* src, int how) {
+    if (!dst || !src || dst->ix != src->ix) return fail(MVDB_ERR_ARG, "bad masks");
+    if (how < 0 || how > 2) return fail(MVDB_ERR_ARG, "bad combine mode");
+    ENTER(dst->ix);
+    if (dst->words) {
+        combine_mask_kernel<<<(dst->words + 255) / 256, 256>>>(dst->dev, dst->words, src->dev, src->words, how);
+        LAUNCHED();
+    }
+    CU_OK(cudaGetLastError());
+    return MVDB_OK;
+}
+
+int mvdb_mask_count(const mvdb_mask* m, uint64_t* count) {
+    if (!m || !count) return fail(MVDB_ERR_ARG, "null argument");
+    mvdb_index* ix = m->ix;
+    ENTER(ix);
+    unsigned long long* dev = nullptr;
+    CU_OK(cudaMalloc(&dev, 8));
+    cudaError_t e = cudaMemset(dev, 0, 8);
+    // rows of the mask that are still live; the live bitmask covers at least as many words
+    const uint64_t nt = ix->ntotal.load(std::memory_order_acquire);
+    const uint32_t words = uint32_t(std::min<uint64_t>(m->words, (nt + 31) / 32));
+    if (e == cudaSuccess && words) {
+        const uint32_t* live = ix->ndead.load(std::memory_order_acquire) ? static_cast<const uint32_t*>(ix->live.ptr()) : nullptr;
+        count_mask_kernel<<<(words + 255) / 256, 256>>>(m->dev, live, words, dev);
+        LAUNCHED();
+        e = cudaGetLastError();
+    }
+    unsigned long long v = 0;
+    if (e == cudaSuccess) e = cudaMemcpy(&v, dev, 8, cudaMemcpyDeviceToHost);
+    cudaFree(dev);
+    if (e != cudaSuccess) return fail(MVDB_ERR_CUDA, "mask count failed: %s", cudaGetErrorString(e));
+    *count = v;
+    return MVDB_OK;
+}
 
 int mvdb_index_search_with_mask(mvdb_index* ix, const float* q, int64_t nq, int64_t k, const mvdb_mask* m,
                                 int normalize_queries, float* D, int64_t* I) {

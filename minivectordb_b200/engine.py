@@ -41,25 +41,82 @@ def pack_mask(admissible: np.ndarray) -> np.ndarray:
 
 
 class MaskHandle:
-    """A filter bitmask uploaded once and kept in HBM (mvdb_index_mask_create).  Pass it as
-    `mask=` to FlatIPEngine.search: no mask bytes move per query, and concurrent single-query
-    searches carrying handles are coalesced into one tensor-core batch."""
+    """A filter bitmask kept in HBM (mvdb_index_mask_create / mvdb_mask_from_predicate).  Pass it
+    as `mask=` to FlatIPEngine.search: no mask bytes move per query, and concurrent single-query
+    searches carrying handles are coalesced into one tensor-core batch with per-query filters."""
 
-    def __init__(self, engine: "FlatIPEngine", admissible):
-        a = np.asarray(admissible)
-        if a.dtype == np.bool_:
-            self.rows = int(a.shape[0])
-            packed = pack_mask(a)
-        else:
-            raise TypeError("MaskHandle needs a bool[n] array of admissible rows")
+    def __init__(self, engine: "FlatIPEngine", admissible=None, _raw=None, _rows=0):
         self._engine = engine
         self._h = ctypes.c_void_p()
+        if _raw is not None:
+            self._h, self.rows = _raw, int(_rows)
+            return
+        a = np.asarray(admissible)
+        if a.dtype != np.bool_:
+            raise TypeError("MaskHandle needs a bool[n] array of admissible rows")
+        self.rows = int(a.shape[0])
+        packed = pack_mask(a)
         N.check(N.lib().mvdb_index_mask_create(engine.handle, packed.ctypes.data if packed.size else None, self.rows,
                                                ctypes.byref(self._h)))
+
+    # device-side combinators (in place): and / or / and-not
+    def iand(self, other: "MaskHandle") -> "MaskHandle":
+        N.check(N.lib().mvdb_mask_combine(self._h, other._h, 0))
+        return self
+
+    def ior(self, other: "MaskHandle") -> "MaskHandle":
+        N.check(N.lib().mvdb_mask_combine(self._h, other._h, 1))
+        return self
+
+    def iandnot(self, other: "MaskHandle") -> "MaskHandle":
+        N.check(N.lib().mvdb_mask_combine(self._h, other._h, 2))
+        return self
+
+    def count(self) -> int:
+        """Admissible rows that are still live."""
+        c = ctypes.c_uint64(0)
+        N.check(N.lib().mvdb_mask_count(self._h, ctypes.byref(c)))
+        return int(c.value)
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h.value:
             N.lib().mvdb_mask_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceColumn:
+    """A numeric metadata column resident in HBM, row-aligned with the index (value + presence
+    bit per row); predicates on it become mask handles without touching the host."""
+
+    OPS = {None: 0, "$ne": 1, "$gt": 2, "$gte": 3, "$lt": 4, "$lte": 5}
+
+    def __init__(self, engine: "FlatIPEngine"):
+        self._engine = engine
+        self._h = ctypes.c_void_p()
+        self.rows = 0
+        N.check(N.lib().mvdb_column_create(engine.handle, ctypes.byref(self._h)))
+
+    def append(self, values: np.ndarray, present: np.ndarray) -> None:
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        present = np.ascontiguousarray(present, dtype=np.uint8)
+        assert values.shape == present.shape
+        N.check(N.lib().mvdb_column_append(self._h, values.ctypes.data, present.ctypes.data, values.shape[0]))
+        self.rows += int(values.shape[0])
+
+    def predicate(self, op, operand: float) -> MaskHandle:
+        h = ctypes.c_void_p()
+        N.check(N.lib().mvdb_mask_from_predicate(self._engine.handle, self._h, self.OPS[op], float(operand), ctypes.byref(h)))
+        return MaskHandle(self._engine, _raw=h, _rows=self.rows)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            N.lib().mvdb_column_destroy(self._h)
             self._h = ctypes.c_void_p()
 
     def __del__(self):
@@ -198,6 +255,15 @@ class FlatIPEngine:
     def mask_handle(self, admissible) -> MaskHandle:
         """Upload a bool[n] filter once; reuse it across searches."""
         return MaskHandle(self, admissible)
+
+    def mask_filled(self, rows: int) -> MaskHandle:
+        """Device-resident mask admitting rows [0, rows)."""
+        h = ctypes.c_void_p()
+        N.check(N.lib().mvdb_mask_create_filled(self._h, int(rows), ctypes.byref(h)))
+        return MaskHandle(self, _raw=h, _rows=rows)
+
+    def column(self) -> DeviceColumn:
+        return DeviceColumn(self)
 
     def debug_gemm_scores(self, q) -> np.ndarray:
         """Raw bf16 tensor-core scores [nq, ntotal] (test hook for the tcgen05 GEMM)."""

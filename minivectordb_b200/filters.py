@@ -51,7 +51,7 @@ def _is_plain_number(v) -> bool:
 class Column:
     """All rows that carry one metadata key: parallel lists (row id, value)."""
 
-    __slots__ = ("rows", "vals", "_rows_np", "_vals_np", "_kind", "_built")
+    __slots__ = ("rows", "vals", "_rows_np", "_vals_np", "_kind", "_built", "_dev", "_dev_rows")
 
     def __init__(self):
         self.rows: List[int] = []
@@ -60,6 +60,8 @@ class Column:
         self._vals_np = None
         self._kind = None
         self._built = 0
+        self._dev = None        # DeviceColumn mirror (numeric columns only)
+        self._dev_rows = 0      # rows [0, _dev_rows) of the database are mirrored
 
     def append(self, row: int, value) -> None:
         self.rows.append(row)
@@ -81,6 +83,29 @@ class Column:
                 self._vals_np = None
             self._built = n
         return self._kind
+
+    def device_match(self, engine, nrows: int, op: Optional[str], operand):
+        """The clause as a device-resident mask (MaskHandle).  Numeric column + numeric operand:
+        evaluated by a CUDA kernel on the HBM-resident column (which is extended lazily with the
+        rows appended since the last filter); anything else: evaluated here and uploaded."""
+        kind = self._typed() if self.rows else None
+        if kind == "num" and _is_plain_number(operand) and op != "$in":
+            if self._dev is None:
+                self._dev, self._dev_rows = engine.column(), 0
+            if self._dev_rows < nrows:
+                lo = int(np.searchsorted(self._rows_np, self._dev_rows))
+                m = nrows - self._dev_rows
+                vals = np.zeros(m, dtype=np.float64)
+                present = np.zeros(m, dtype=np.uint8)
+                idx = self._rows_np[lo:] - self._dev_rows
+                keep = idx < m
+                vals[idx[keep]] = self._vals_np[lo:][keep]
+                present[idx[keep]] = 1
+                self._dev.append(vals, present)
+                self._dev_rows = nrows
+            return self._dev.predicate(op, float(operand))
+        self._dev = None   # the column stopped being purely numeric (or never was)
+        return engine.mask_handle(self.match(nrows, op, operand))
 
     def match(self, nrows: int, op: Optional[str], operand) -> np.ndarray:
         """bool[nrows]: rows of this column whose value satisfies the clause
@@ -133,6 +158,57 @@ class FilterIndex:
         if col is None:
             return np.zeros(nrows, dtype=bool)
         return col.match(nrows, op, operand)
+
+    def _clause_device(self, engine, nrows: int, key, value):
+        if isinstance(value, dict):
+            op = next(iter(value))
+            if op not in _OPS:
+                raise ValueError(f"Invalid operator: {op}")
+            operand = value[op]
+        else:
+            op, operand = None, value
+        col = self.columns.get(key)
+        if col is None:
+            return engine.mask_handle(np.zeros(nrows, dtype=bool))   # nothing carries this key (full-size: it may be OR-ed into)
+        return col.device_match(engine, nrows, op, operand)
+
+    def admissible_device(self, engine, nrows: int, metadata_filter, exclude_filter, or_filters):
+        """Same combinators as `admissible`, evaluated on the device: returns a MaskHandle over
+        rows [0, nrows) (tombstones are applied by the engine, not here)."""
+        cur = None
+        if isinstance(metadata_filter, dict):
+            metadata_filter = [metadata_filter]
+        if metadata_filter:
+            for clause_set in metadata_filter:
+                for key, value in clause_set.items():
+                    hit = self._clause_device(engine, nrows, key, value)
+                    cur = hit if cur is None else cur.iand(hit)
+        elif not metadata_filter:
+            cur = engine.mask_filled(nrows)
+        if or_filters:
+            if isinstance(or_filters, dict):
+                or_filters = [or_filters]
+            or_filters = [f for f in or_filters if f]
+            if or_filters:
+                union = None
+                for clause_set in or_filters:
+                    for key, value in clause_set.items():
+                        hit = self._clause_device(engine, nrows, key, value)
+                        union = hit if union is None else union.ior(hit)
+                cur = union if cur is None else cur.iand(union)
+        if exclude_filter:
+            if isinstance(exclude_filter, dict):
+                exclude_filter = [exclude_filter]
+            if cur is None:
+                raise TypeError("unsupported operand type(s) for -=: 'NoneType' and 'set'")
+            for clause_set in exclude_filter:
+                for key, value in clause_set.items():
+                    col = self.columns.get(key)
+                    if col is not None:
+                        cur.iandnot(col.device_match(engine, nrows, None, value))   # equality only (VDB:343)
+        if cur is None:
+            return engine.mask_filled(0)
+        return cur
 
     # -- combinators ----------------------------------------------------------
     def admissible(self, live: np.ndarray, metadata_filter, exclude_filter, or_filters) -> Optional[np.ndarray]:

@@ -119,3 +119,62 @@ def test_compaction_on_device(classes, tmp_path, monkeypatch):
     after = db.find_most_similar(embs[777], k=20, metadata_filter={"g": {"$ne": 0}})
     assert db._parts[0].engine.ntotal == 1500   # physically compacted
     assert before[0] == after[0] and np.array_equal(np.array(before[1]), np.array(after[1]))
+
+
+def test_device_filter_evaluation_matches_host_evaluation(classes, tmp_path):
+    """Numeric predicates are evaluated by CUDA kernels over HBM-resident metadata columns and
+    combined on the device; the admissible set must equal the host (numpy) evaluation for every
+    combinator, including keys that are missing, mixed-type columns and rows appended later."""
+    from minivectordb_b200.filters import FilterIndex
+    db = classes[0](storage_file=str(tmp_path / "dev.pkl"))
+    rng = np.random.default_rng(2)
+    n, d = 5000, 16
+    embs = rng.standard_normal((n, d)).astype(np.float32)
+    metas = []
+    for i in range(n):
+        m = {"tag": f"t{i % 7}"}
+        if i % 3:
+            m["value"] = int(rng.integers(0, 100))
+        if i % 5 == 0:
+            m["score"] = float(rng.random())
+        if i % 11 == 0:
+            m["mixed"] = i if i % 2 else str(i)
+        metas.append(m)
+    db.store_embeddings_batch(list(range(n)), list(embs), metas)
+    q = rng.standard_normal(d).astype(np.float32)
+    filters = [
+        dict(metadata_filter={"value": {"$gt": 49}}),
+        dict(metadata_filter={"value": {"$lte": 10}, "score": {"$lt": 0.5}}),
+        dict(metadata_filter={"value": {"$ne": 7}}),
+        dict(metadata_filter={"value": 42}),
+        dict(metadata_filter=[{"value": {"$gte": 20}}, {"tag": "t3"}]),
+        dict(or_filters=[{"value": {"$lt": 5}}, {"score": {"$gt": 0.9}}, {"nokey": 1}]),
+        dict(metadata_filter={"value": {"$gt": 10}}, or_filters={"tag": "t1", "score": {"$gt": 0.5}}),
+        dict(exclude_filter={"value": 42}),
+        dict(metadata_filter={"value": {"$gt": 30}}, exclude_filter=[{"tag": "t2"}, {"value": 77}]),
+        dict(metadata_filter={"mixed": {"$ne": 11}}),
+        dict(metadata_filter={"nokey": {"$gt": 1}}),
+    ]
+    db.find_most_similar(q, k=1)   # flush
+    db.delete_embedding(5)
+    db.delete_embedding(4242)
+
+    def check_all():
+        for f in filters:
+            got = db.find_most_similar(q, k=10_000, **f)
+            live = db._g_live[:db._g_n]
+            want = FilterIndex.admissible(db._filters, live, f.get("metadata_filter"), f.get("exclude_filter"),
+                                          f.get("or_filters"))
+            want_ids = set(np.flatnonzero(live if want is None else want).tolist())
+            assert set(db.inverse_id_map[u] for u in got[0]) == {int(np.sum(live[:g])) for g in want_ids}, f
+            # a repeat is served from the cached device-resident mask
+            again = db.find_most_similar(q, k=10_000, **f)
+            assert again[0] == got[0]
+
+    check_all()
+    # rows appended after the device columns were built extend them lazily
+    more = rng.standard_normal((300, d)).astype(np.float32)
+    db.store_embeddings_batch(list(range(n, n + 300)), list(more), [{"value": int(i % 100), "tag": "t3"} for i in range(300)])
+    check_all()
+    with pytest.raises(ValueError):
+        db.find_most_similar(q, metadata_filter={"value": {"$regex": 1}})
