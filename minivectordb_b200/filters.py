@@ -175,7 +175,9 @@ class FilterIndex:
     def admissible_device(self, engine, nrows: int, metadata_filter, exclude_filter, or_filters):
         """Same combinators as `admissible`, evaluated on the device: returns a MaskHandle over
         rows [0, nrows) (tombstones are applied by the engine, not here)."""
-        cur = None
+        # "no AND filter" is decided BEFORE a dict is wrapped into a list, exactly as the
+        # reference does (VDB:356-360): {} starts from every row, [{}] from nothing
+        cur = None if metadata_filter else engine.mask_filled(nrows)
         if isinstance(metadata_filter, dict):
             metadata_filter = [metadata_filter]
         if metadata_filter:
@@ -183,8 +185,6 @@ class FilterIndex:
                 for key, value in clause_set.items():
                     hit = self._clause_device(engine, nrows, key, value)
                     cur = hit if cur is None else cur.iand(hit)
-        elif not metadata_filter:
-            cur = engine.mask_filled(nrows)
         if or_filters:
             if isinstance(or_filters, dict):
                 or_filters = [or_filters]
