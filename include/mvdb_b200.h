@@ -154,7 +154,8 @@ int mvdb_index_search(mvdb_index* ix, const float* q, int64_t nq, int64_t k, con
  * referenced by handle; searches through a handle move no mask bytes, and
  * concurrent single-query calls that carry handles are coalesced into one
  * tensor-core batch with per-query filters.  Rows >= mask_rows (appended after
- * the handle was made) are not admissible through it. */
+ * the handle was made) are not admissible through it.  mvdb_index_compact renumbers rows and
+ * therefore invalidates every handle and column made before it. */
 typedef struct mvdb_mask mvdb_mask;
 int mvdb_index_mask_create(mvdb_index* ix, const uint8_t* mask, uint64_t mask_rows, mvdb_mask** out);
 int mvdb_mask_destroy(mvdb_mask* m);

@@ -400,6 +400,8 @@ struct mvdb_index {
     int fused_k_max = 128;
     int grid_ctas = 0;
     int consumer_warps = 0;
+    unsigned long long* count_dev = nullptr;   // scratch of mvdb_mask_count
+    std::mutex count_mu;
     // query coalescer: concurrent single-query host searches share one pass over the matrix
     int coalesce = 1;
     int coalesce_max = 64;
@@ -1212,6 +1214,7 @@ int mvdb_index_destroy(mvdb_index* ix) {
     ix->live.destroy();
     ix->mat16.destroy();
     cudaFree(ix->max_norm2_bits);
+    cudaFree(ix->count_dev);
     cudaFree(ix->stage_dev[0]);
     cudaFree(ix->stage_dev[1]);
     cudaFree(ix->rows_dev);
@@ -1863,8 +1866,10 @@ int mvdb_mask_count(const mvdb_mask* m, uint64_t* count) {
     if (!m || !count) return fail(MVDB_ERR_ARG, "null argument");
     mvdb_index* ix = m->ix;
     ENTER(ix);
-    unsigned long long* dev = nullptr;
-    CU_OK(cudaMalloc(&dev, 8));
+    // one 8-byte counter per index, serialised by a mutex (a cudaMalloc per count would dominate)
+    std::lock_guard<std::mutex> cg(ix->count_mu);
+    if (!ix->count_dev) CU_OK(cudaMalloc(&ix->count_dev, 8));
+    unsigned long long* dev = ix->count_dev;
     cudaError_t e = cudaMemset(dev, 0, 8);
     // rows of the mask that are still live; the live bitmask covers at least as many words
     const uint64_t nt = ix->ntotal.load(std::memory_order_acquire);
@@ -1877,7 +1882,6 @@ int mvdb_mask_count(const mvdb_mask* m, uint64_t* count) {
     }
     unsigned long long v = 0;
     if (e == cudaSuccess) e = cudaMemcpy(&v, dev, 8, cudaMemcpyDeviceToHost);
-    cudaFree(dev);
     if (e != cudaSuccess) return fail(MVDB_ERR_CUDA, "mask count failed: %s", cudaGetErrorString(e));
     *count = v;
     return MVDB_OK;
