@@ -236,6 +236,10 @@ int mvdb_index_search_exchange(mvdb_index* ix, mvdb_workspace* ws, mvdb_exchange
  * against an independent bf16 matmul; not used by the product path. */
 int mvdb_debug_gemm_scores(mvdb_index* ix, const float* q, int64_t nq, float* out);
 
+/* Test hook: with option "trace" = 1 the single-query scan kernel stamps %globaltimer at fixed
+ * points (slots 0-6: CTA 0, slots 8-13: the last CTA); reads the 16 stamps of the latest launch. */
+int mvdb_debug_read_trace(mvdb_index* ix, uint64_t* out16);
+
 /* Number of kernel launches issued by this library since load (bench.py's
  * "gpu_launches" claim is read from here). */
 uint64_t mvdb_launch_count(void);

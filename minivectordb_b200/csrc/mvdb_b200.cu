@@ -394,6 +394,8 @@ struct mvdb_index {
     int batch_min_nq = 2;
     int batch_cost_model = 1;      // 0: every batch of >= batch_min_nq queries takes the tensor path (tests, probes)
     int gemm_l2_hint = 0;
+    unsigned long long* trace_dev = nullptr;   // debug timeline of the scan kernel (option "trace")
+    int l2_pin_mb = 0;             // head of the matrix kept L2-resident across scans (evict_last), MB
     int gemm_variant = 2;          // 0: one CTA per 128x256 tile; 1: CTA pairs (cta_group::2), 256x256 tiles;
                                    // 2 / 3: cluster of 2 / 4 CTAs sharing the X tile through TMA multicast
     int scan_variant = MVDB_SCAN_AUTO;
@@ -957,6 +959,8 @@ static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, in
     p.d = ix->d;
     p.ld4 = ix->ld4;
     p.normalize_q = normalize_q;
+    p.trace = ix->trace_dev;
+    p.pin_tiles = uint32_t((uint64_t(ix->l2_pin_mb) << 20) / (uint64_t(kRowsPerTile) * ix->ld * 4));
 
     if (k <= ix->fused_k_max) {
         p.k = int(k);
@@ -1261,6 +1265,18 @@ int mvdb_index_set_option(mvdb_index* ix, const char* name, int64_t value) {
     } else if (s == "batch_mode") {
         if (value < 0 || value > 2) return fail(MVDB_ERR_ARG, "batch_mode must be 0 (off), 1 (exact) or 2 (bf16)");
         ix->batch_mode = int(value);
+    } else if (s == "trace") {
+        DeviceGuard guard(ix->device);
+        if (value && !ix->trace_dev) {
+            CU_OK(cudaMalloc(&ix->trace_dev, 16 * 8));
+            CU_OK(cudaMemset(ix->trace_dev, 0, 16 * 8));
+        } else if (!value && ix->trace_dev) {
+            cudaFree(ix->trace_dev);
+            ix->trace_dev = nullptr;
+        }
+    } else if (s == "l2_pin_mb") {
+        if (value < 0 || value > 120) return fail(MVDB_ERR_ARG, "l2_pin_mb must be 0..120");
+        ix->l2_pin_mb = int(value);
     } else if (s == "gemm_variant") {
         if (value < 0 || value > 3) return fail(MVDB_ERR_ARG, "gemm_variant must be 0..3");
         ix->gemm_variant = int(value);
@@ -2066,6 +2082,14 @@ int mvdb_debug_gemm_scores(mvdb_index* ix, const float* q, int64_t nq, float* ou
     cudaFree(q_dev);
     cudaFree(o_dev);
     return rc;
+}
+
+int mvdb_debug_read_trace(mvdb_index* ix, uint64_t* out16) {
+    ENTER(ix);
+    if (!out16 || !ix->trace_dev) return fail(MVDB_ERR_STATE, "tracing is off (set option \"trace\" = 1)");
+    CU_OK(cudaDeviceSynchronize());
+    CU_OK(cudaMemcpy(out16, ix->trace_dev, 16 * 8, cudaMemcpyDeviceToHost));
+    return MVDB_OK;
 }
 
 int mvdb_normalize_L2(float* x, uint64_t n, int d, int device) {

@@ -51,6 +51,9 @@ struct ScanParams {
     uint32_t stage_bytes;  // 8 * ld * 4 rounded to 128
     uint32_t sel_off, q_off, stage_off;  // byte offsets into dynamic shared memory
     uint32_t merge_off, merge_bytes;     // scratch for the last-CTA merge (the idle TMA ring, or a tail region)
+    unsigned long long* trace;   // debug: globaltimer stamps of one consumer warp (nullptr in production)
+    uint32_t pin_tiles;          // tiles [0, pin_tiles) are loaded with L2 evict_last: the head of the matrix stays
+                                 // L2-resident across queries, the rest streams through with evict_first
     const uint32_t* qmask[8];    // per-query admissible bitmasks (coalesced searches; nullptr = none); multi kernel only
     uint32_t qmask_bytes[8];     // bytes available behind qmask[i]; rows past them are not admissible
     int has_qmask;
@@ -207,27 +210,41 @@ __device__ __forceinline__ WarpSelect merge_cta_lists(SmemHeader* hdr, uint64_t*
 // Called by all consumer warps once their tiles are done.  `sel_cnt[qi]` must
 // already be compacted lists in selbuf[(cw*nq+qi)*cap ..].
 // bar_id/bar_threads: named barrier covering exactly the consumer warps.
+// debug timeline: consumer warp 0 lane 0 of CTA 0 stamps slots 0-7, of the LAST CTA slots 8-15
+__device__ __forceinline__ void trace_stamp(const ScanParams& p, int slot, int cw, int lane) {
+    if (p.trace && cw == 0 && lane == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[slot] = t;
+    }
+}
+
 __device__ __forceinline__ void finish_scan(const ScanParams& p, uint8_t* smem_base, SmemHeader* hdr,
                                             uint64_t* selbuf, int cw, int ncw, int lane, int bar_id,
                                             int bar_threads) {
     const int nq = p.nq, k = p.k, cap = p.cap;
     const int G = gridDim.x;
     named_bar_sync(bar_id, bar_threads);
+    if (blockIdx.x == 0) trace_stamp(p, 3, cw, lane);
     // ---- CTA merge: warp (qi % ncw) owns query qi -------------------------
     for (int qi = cw; qi < nq; qi += ncw) {
         WarpSelect m = merge_cta_lists(hdr, selbuf, nq, qi, cw, ncw, cap, k, lane);
         uint64_t* dst = p.partials + (size_t(qi) * G + blockIdx.x) * k;
         for (int i = lane; i < k; i += kWarp) dst[i] = (i < m.cnt) ? m.buf[i] : kEmptyKey;
     }
+    if (blockIdx.x == 0) trace_stamp(p, 4, cw, lane);
     __threadfence();
     named_bar_sync(bar_id, bar_threads);
+    if (blockIdx.x == 0) trace_stamp(p, 5, cw, lane);
     if (cw == 0 && lane == 0) {
         unsigned t = atomicAdd(p.ticket, 1u);
         hdr->last_flag = (t == unsigned(G - 1));
     }
     named_bar_sync(bar_id, bar_threads);
+    if (blockIdx.x == 0) trace_stamp(p, 6, cw, lane);
     if (!hdr->last_flag) return;
     // ---- last CTA: merge the G partial lists of every query ---------------
+    trace_stamp(p, 8, cw, lane);
     __threadfence();
     // Every CTA list is sorted best-first, so the lists are streamed COLUMN by
     // column (all heads, then all second entries, ...): the threshold rises
@@ -247,6 +264,7 @@ __device__ __forceinline__ void finish_scan(const ScanParams& p, uint8_t* smem_b
             for (int i = cw * kWarp + lane; i < G * k; i += bar_threads) mbuf[i] = __ldcg(src + i);
             named_bar_sync(bar_id, bar_threads);
             src = mbuf;
+            if (qi == 0) trace_stamp(p, 9, cw, lane);
         }
         for (int col = 0; col < k; col++) {
             bool any = false;
@@ -258,17 +276,21 @@ __device__ __forceinline__ void finish_scan(const ScanParams& p, uint8_t* smem_b
             }
             if (!any) break;
         }
+        if (qi == 0) trace_stamp(p, 10, cw, lane);
         f.compact(lane);
         if (lane == 0) hdr->cnts[cw * nq + qi] = f.cnt;
     }
     named_bar_sync(bar_id, bar_threads);
+    trace_stamp(p, 11, cw, lane);
     for (int qi = cw; qi < nq; qi += ncw) {
         WarpSelect m = merge_cta_lists(hdr, selbuf, nq, qi, cw, ncw, cap, k, lane);
         __syncwarp();
+        if (qi == 0) trace_stamp(p, 12, cw, lane);
         if (p.xchg) xchg_send(p.xchg, p.xchg_seq, qi, m.buf, m.cnt, k, lane);
         else write_results(m.buf, m.cnt, k, p.outD + size_t(qi) * k, p.outI + size_t(qi) * k, p.label_offset, lane);
     }
     if (cw == 0 && lane == 0) *p.ticket = 0u;  // ready for the next launch on this workspace
+    trace_stamp(p, 13, cw, lane);
     if (!p.xchg) return;
     // ---- fused exchange: all lists are on their way to every rank -----------
     named_bar_sync(bar_id, bar_threads);
@@ -363,7 +385,7 @@ __global__ void __launch_bounds__(kTma ? 288 : 256, kTma ? 1 : 2) scan_q1_kernel
         __syncthreads();
         if (warp == 0) {
             if (lane == 0) {
-                const uint64_t pol = policy_evict_first();
+                const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
                 const uint32_t row_bytes = uint32_t(p.ld4) * 16u;
                 int s = 0;
                 uint32_t ph = 0;
@@ -375,7 +397,8 @@ __global__ void __launch_bounds__(kTma ? 288 : 256, kTma ? 1 : 2) scan_q1_kernel
                     uint32_t bytes = rows * row_bytes;
                     mbar_arrive_expect_tx(&hdr->full[s], bytes);
                     bulk_g2s(smem + p.stage_off + size_t(s) * p.stage_bytes,
-                             p.x + size_t(row0) * size_t(p.ld4) * 4, bytes, &hdr->full[s], pol);
+                             p.x + size_t(row0) * size_t(p.ld4) * 4, bytes, &hdr->full[s],
+                             tile < p.pin_tiles ? pol_keep : pol_stream);
                     if (++s == S) {
                         s = 0;
                         ph ^= 1u;
@@ -386,8 +409,10 @@ __global__ void __launch_bounds__(kTma ? 288 : 256, kTma ? 1 : 2) scan_q1_kernel
         }
     }
 
+    if (blockIdx.x == 0) trace_stamp(p, 0, cw, lane);
     float4 qr[D4];
     load_query_regs<D4>(p.q, p.d, p.ld4, p.normalize_q, lane, qr);
+    if (blockIdx.x == 0) trace_stamp(p, 1, cw, lane);
 
     WarpSelect sel;
     sel.init(selbuf + size_t(cw) * p.cap, p.cap, p.k);
@@ -447,6 +472,7 @@ __global__ void __launch_bounds__(kTma ? 288 : 256, kTma ? 1 : 2) scan_q1_kernel
         }
     }
     if (p.all_ord) return;
+    if (blockIdx.x == 0) trace_stamp(p, 2, cw, lane);
     sel.compact(lane);
     if (lane == 0) hdr->cnts[cw] = sel.cnt;
     finish_scan(p, smem, hdr, selbuf, cw, ncw, lane, 1, ncw * 32);
@@ -483,7 +509,7 @@ __global__ void __launch_bounds__(kTma ? 288 : 256, (kTma || NQ >= 8) ? 1 : 2) s
         __syncthreads();
         if (warp == 0) {
             if (lane == 0) {
-                const uint64_t pol = policy_evict_first();
+                const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
                 const uint32_t row_bytes = uint32_t(ld4) * 16u;
                 int s = 0;
                 uint32_t ph = 0;
@@ -495,7 +521,8 @@ __global__ void __launch_bounds__(kTma ? 288 : 256, (kTma || NQ >= 8) ? 1 : 2) s
                     uint32_t bytes = rows * row_bytes;
                     mbar_arrive_expect_tx(&hdr->full[s], bytes);
                     bulk_g2s(smem + p.stage_off + size_t(s) * p.stage_bytes,
-                             p.x + size_t(row0) * size_t(ld4) * 4, bytes, &hdr->full[s], pol);
+                             p.x + size_t(row0) * size_t(ld4) * 4, bytes, &hdr->full[s],
+                             tile < p.pin_tiles ? pol_keep : pol_stream);
                     if (++s == S) {
                         s = 0;
                         ph ^= 1u;
