@@ -77,6 +77,9 @@ int mvdb_index_reset(mvdb_index* ix);
  *   "scan_variant"  MVDB_SCAN_*          "fused_k_max"  largest k served by the fused select
  *   "grid_ctas"     CTAs of the scan kernel (0 = one per SM)
  *   "consumer_warps" consumer warps per CTA of the TMA scan (0 = auto)
+ *   "dyn_tiles"     percentage (0..100, default 15) of the tiles the TMA scan claims from a
+ *                   global counter instead of the static round-robin split, to level the
+ *                   finishing times of the SMs; results are identical for every value
  *   "batch_mode"    large query batches on the tensor cores: 0 off (always the
  *                   fp32 scan), 1 exact (bf16 tcgen05 GEMM selects a rigorous
  *                   candidate superset, survivors re-scored in fp32: same ids and

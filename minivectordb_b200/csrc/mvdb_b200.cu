@@ -316,16 +316,12 @@ struct mvdb_workspace {
     size_t q_cap = 0;
     uint32_t* mask_dev = nullptr;
     size_t mask_cap = 0;
-    float* D_dev = nullptr;
-    size_t D_cap = 0;
-    int64_t* I_dev = nullptr;
+    int64_t* I_dev = nullptr;   // [labels | distances] of a host-buffer search (one D2H transfer)
     size_t I_cap = 0;
     float* q_pin = nullptr;
     size_t q_pin_cap = 0;
     uint32_t* mask_pin = nullptr;
     size_t mask_pin_cap = 0;
-    float* D_pin = nullptr;
-    size_t D_pin_cap = 0;
     int64_t* I_pin = nullptr;
     size_t I_pin_cap = 0;
 };
@@ -395,6 +391,7 @@ struct mvdb_index {
     int batch_cost_model = 1;      // 0: every batch of >= batch_min_nq queries takes the tensor path (tests, probes)
     int gemm_l2_hint = 0;
     unsigned long long* trace_dev = nullptr;   // debug timeline of the scan kernel (option "trace")
+    int dyn_tiles = 15;            // % of the tiles the TMA scan claims from a global counter (rest: static round-robin)
     int l2_pin_mb = 0;             // head of the matrix kept L2-resident across scans (evict_last), MB
     int gemm_variant = 2;          // 0: one CTA per 128x256 tile; 1: CTA pairs (cta_group::2), 256x256 tiles;
                                    // 2 / 3: cluster of 2 / 4 CTAs sharing the X tile through TMA multicast
@@ -480,6 +477,7 @@ static ScanKernel multi_kernel(int nq) {
 struct ScanPlan {
     ScanKernel fn = nullptr;
     bool tma = false;
+    bool q1 = false;
     int grid = 0, threads = 0;
     size_t smem = 0;
 };
@@ -559,6 +557,7 @@ static int plan_scan(mvdb_index* ix, ScanParams& p, int nq, ScanPlan* plan) {
             p.merge_bytes = uint32_t(size_t(stages) * p.stage_bytes);
         }
     }
+    plan->q1 = use_q1;
     if (tma) {
         plan->tma = true;
         plan->threads = 32 * (1 + ncw_tma);
@@ -609,8 +608,9 @@ __global__ void fill_empty_results_kernel(float* D, int64_t* I, int64_t total) {
 
 static int ws_scratch(mvdb_workspace* ws) {
     if (!ws->ticket) {
-        CU_OK(cudaMalloc(&ws->ticket, sizeof(unsigned int)));
-        CU_OK(cudaMemset(ws->ticket, 0, sizeof(unsigned int)));
+        // ticket at +0, the dynamic scheduler's tile counter at +128 (its own L2 line)
+        CU_OK(cudaMalloc(&ws->ticket, 256));
+        CU_OK(cudaMemset(ws->ticket, 0, 256));
     }
     return MVDB_OK;
 }
@@ -1005,6 +1005,17 @@ static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, in
             p.outD = D_dev + done * k;
             p.outI = I_dev + done * k;
             p.all_ord = nullptr;
+            p.tile_ctr = nullptr;
+            if (ix->dyn_tiles > 0 && plan.tma) {
+                // the first (100 - dyn_tiles)% of every CTA's share is a static round-robin, the
+                // rest is claimed from a counter in chunks aligned to one 32-row mask word
+                const uint32_t tiles = (p.n + kRowsPerTile - 1) / kRowsPerTile;
+                uint32_t st = uint32_t(uint64_t(tiles / uint32_t(plan.grid)) * uint32_t(100 - ix->dyn_tiles) / 100u);
+                if (plan.grid & 3) st &= ~3u;
+                p.static_iters = st;
+                p.dyn_tile0 = st * uint32_t(plan.grid);
+                p.tile_ctr = ws->ticket + 32;
+            }
             plan.fn<<<plan.grid, plan.threads, plan.smem, stream>>>(p);
             LAUNCHED();
             CU_OK(cudaGetLastError());
@@ -1088,11 +1099,9 @@ static void ws_free(mvdb_workspace* ws) {
     cudaFree(ws->b_lqwords);
     cudaFree(ws->q_dev);
     cudaFree(ws->mask_dev);
-    cudaFree(ws->D_dev);
     cudaFree(ws->I_dev);
     cudaFreeHost(ws->q_pin);
     cudaFreeHost(ws->mask_pin);
-    cudaFreeHost(ws->D_pin);
     cudaFreeHost(ws->I_pin);
     if (ws->stream) cudaStreamDestroy(ws->stream);
     delete ws;
@@ -1274,6 +1283,9 @@ int mvdb_index_set_option(mvdb_index* ix, const char* name, int64_t value) {
             cudaFree(ix->trace_dev);
             ix->trace_dev = nullptr;
         }
+    } else if (s == "dyn_tiles") {
+        if (value < 0 || value > 100) return fail(MVDB_ERR_ARG, "dyn_tiles is a percentage, 0..100");
+        ix->dyn_tiles = int(value);
     } else if (s == "l2_pin_mb") {
         if (value < 0 || value > 120) return fail(MVDB_ERR_ARG, "l2_pin_mb must be 0..120");
         ix->l2_pin_mb = int(value);
@@ -1555,10 +1567,12 @@ static int search_host_direct(mvdb_index* ix, const float* q, int64_t nq, int64_
     const size_t qn = size_t(nq) * ix->d, on = size_t(nq) * k;
     RC_OK(grow_dev(&ws->q_dev, &ws->q_cap, qn));
     RC_OK(grow_pin(&ws->q_pin, &ws->q_pin_cap, qn));
-    RC_OK(grow_dev(&ws->D_dev, &ws->D_cap, on));
-    RC_OK(grow_dev(&ws->I_dev, &ws->I_cap, on));
-    RC_OK(grow_pin(&ws->D_pin, &ws->D_pin_cap, on));
-    RC_OK(grow_pin(&ws->I_pin, &ws->I_pin_cap, on));
+    // labels and distances share one buffer ([I | D]) so that the results come back in ONE transfer
+    const size_t out_elems = on + (on + 1) / 2;
+    RC_OK(grow_dev(&ws->I_dev, &ws->I_cap, out_elems));
+    RC_OK(grow_pin(&ws->I_pin, &ws->I_pin_cap, out_elems));
+    float* const D_dev = reinterpret_cast<float*>(ws->I_dev + on);
+    const float* const D_pin = reinterpret_cast<const float*>(ws->I_pin + on);
     memcpy(ws->q_pin, q, qn * 4);
     CU_OK(cudaMemcpyAsync(ws->q_dev, ws->q_pin, qn * 4, cudaMemcpyHostToDevice, st));
     const uint32_t* mask_dev = nullptr;
@@ -1579,11 +1593,10 @@ static int search_host_direct(mvdb_index* ix, const float* q, int64_t nq, int64_
         }
         mask_dev = ws->mask_dev;
     }
-    RC_OK(run_search(ix, ws, ws->q_dev, nq, k, mask_dev, mask_rows, normalize_queries, 0, ws->D_dev, ws->I_dev, st, nullptr));
-    CU_OK(cudaMemcpyAsync(ws->D_pin, ws->D_dev, on * 4, cudaMemcpyDeviceToHost, st));
-    CU_OK(cudaMemcpyAsync(ws->I_pin, ws->I_dev, on * 8, cudaMemcpyDeviceToHost, st));
+    RC_OK(run_search(ix, ws, ws->q_dev, nq, k, mask_dev, mask_rows, normalize_queries, 0, D_dev, ws->I_dev, st, nullptr));
+    CU_OK(cudaMemcpyAsync(ws->I_pin, ws->I_dev, on * 12, cudaMemcpyDeviceToHost, st));
     CU_OK(cudaStreamSynchronize(st));
-    memcpy(D, ws->D_pin, on * 4);
+    memcpy(D, D_pin, on * 4);
     memcpy(I, ws->I_pin, on * 8);
     return MVDB_OK;
 }
@@ -1617,10 +1630,11 @@ static int exec_coalesced(mvdb_index* ix, std::vector<CoalesceReq*>& batch) {
     }
     RC_OK(grow_dev(&ws->q_dev, &ws->q_cap, qn));
     RC_OK(grow_pin(&ws->q_pin, &ws->q_pin_cap, qn));
-    RC_OK(grow_dev(&ws->D_dev, &ws->D_cap, on));
-    RC_OK(grow_dev(&ws->I_dev, &ws->I_cap, on));
-    RC_OK(grow_pin(&ws->D_pin, &ws->D_pin_cap, on));
-    RC_OK(grow_pin(&ws->I_pin, &ws->I_pin_cap, on));
+    const size_t out_elems = on + (on + 1) / 2;   // [I | D] in one buffer: one D2H transfer
+    RC_OK(grow_dev(&ws->I_dev, &ws->I_cap, out_elems));
+    RC_OK(grow_pin(&ws->I_pin, &ws->I_pin_cap, out_elems));
+    float* const D_dev = reinterpret_cast<float*>(ws->I_dev + on);
+    const float* const D_pin = reinterpret_cast<const float*>(ws->I_pin + on);
     if (n_masked) {
         RC_OK(grow_dev(&ws->mask_dev, &ws->mask_cap, std::max<size_t>(words * n_masked, 1)));
         RC_OK(grow_pin(&ws->mask_pin, &ws->mask_pin_cap, std::max<size_t>(words * n_masked, 1)));
@@ -1647,13 +1661,12 @@ static int exec_coalesced(mvdb_index* ix, std::vector<CoalesceReq*>& batch) {
     CU_OK(cudaMemcpyAsync(ws->q_dev, ws->q_pin, qn * 4, cudaMemcpyHostToDevice, st));
     if (n_masked && words)
         CU_OK(cudaMemcpyAsync(ws->mask_dev, ws->mask_pin, words * 4 * n_masked, cudaMemcpyHostToDevice, st));
-    RC_OK(run_search(ix, ws, ws->q_dev, B, k, nullptr, 0, batch[0]->normalize, 0, ws->D_dev, ws->I_dev, st, nullptr,
+    RC_OK(run_search(ix, ws, ws->q_dev, B, k, nullptr, 0, batch[0]->normalize, 0, D_dev, ws->I_dev, st, nullptr,
                      any_filter ? qmasks.data() : nullptr));
-    CU_OK(cudaMemcpyAsync(ws->D_pin, ws->D_dev, on * 4, cudaMemcpyDeviceToHost, st));
-    CU_OK(cudaMemcpyAsync(ws->I_pin, ws->I_dev, on * 8, cudaMemcpyDeviceToHost, st));
+    CU_OK(cudaMemcpyAsync(ws->I_pin, ws->I_dev, on * 12, cudaMemcpyDeviceToHost, st));
     CU_OK(cudaStreamSynchronize(st));
     for (int64_t i = 0; i < B; i++) {
-        memcpy(batch[size_t(i)]->D, ws->D_pin + i * k, size_t(k) * 4);
+        memcpy(batch[size_t(i)]->D, D_pin + i * k, size_t(k) * 4);
         memcpy(batch[size_t(i)]->I, ws->I_pin + i * k, size_t(k) * 8);
     }
     return MVDB_OK;

@@ -36,6 +36,9 @@ struct ScanParams {
     const uint32_t* mask;  // admissible-row bitmask or nullptr (no filter)
     uint64_t* partials;    // [nq][gridDim.x][k] keys
     unsigned int* ticket;  // zero before launch; reset by the last CTA
+    unsigned int* tile_ctr;  // dynamic tile scheduler (NULL = static round-robin); zero before launch, reset by the last CTA
+    uint32_t static_iters;   // ... iterations of every CTA served by the static round-robin first
+    uint32_t dyn_tile0;      // ... first tile of the dynamically claimed remainder (= static_iters * grid, multiple of kDynChunk)
     float* outD;           // [nq][k]
     int64_t* outI;         // [nq][k]
     uint32_t* all_ord;     // large-k mode: [nq][n] score images (0 = not admissible); else nullptr
@@ -170,6 +173,8 @@ struct SmemHeader {
     uint64_t empty[16];
     int cnts[64];      // [warp][query] list lengths for the CTA merge
     int last_flag;
+    uint32_t tile_of[16];  // dynamic tile scheduler: tile held by ring stage s (kNoTile = stop)
+    uint32_t adm_of[16];   // ... and its admissible byte (mask & live)
 };
 static_assert(sizeof(SmemHeader) <= 1024, "header too large");
 
@@ -289,7 +294,10 @@ __device__ __forceinline__ void finish_scan(const ScanParams& p, uint8_t* smem_b
         if (p.xchg) xchg_send(p.xchg, p.xchg_seq, qi, m.buf, m.cnt, k, lane);
         else write_results(m.buf, m.cnt, k, p.outD + size_t(qi) * k, p.outI + size_t(qi) * k, p.label_offset, lane);
     }
-    if (cw == 0 && lane == 0) *p.ticket = 0u;  // ready for the next launch on this workspace
+    if (cw == 0 && lane == 0) {  // ready for the next launch on this workspace
+        *p.ticket = 0u;
+        if (p.tile_ctr) *p.tile_ctr = 0u;
+    }
     trace_stamp(p, 13, cw, lane);
     if (!p.xchg) return;
     // ---- fused exchange: all lists are on their way to every rank -----------
@@ -321,11 +329,14 @@ template <int D4>
 __device__ __forceinline__ void load_query_regs(const float* q, int d, int ld4, int normalize,
                                                 int lane, float4 (&qr)[D4]) {
     float nr = 0.f;
+    const bool vec = ((d & 3) == 0) && ((reinterpret_cast<uintptr_t>(q) & 15) == 0);
 #pragma unroll
     for (int j = 0; j < D4; j++) {
         int c = lane + 32 * j;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c < ld4) {
+        if (vec) {
+            if (4 * c < d) v = reinterpret_cast<const float4*>(q)[c];
+        } else if (c < ld4) {
             int b = 4 * c;
             if (b + 0 < d) v.x = q[b + 0];
             if (b + 1 < d) v.y = q[b + 1];
@@ -350,11 +361,98 @@ __device__ __forceinline__ void load_query_regs(const float* q, int d, int ld4, 
     }
 }
 
+// dynamic scheduler: tiles are claimed kDynChunk at a time = one 32-row word of the bitmasks
+constexpr uint32_t kDynChunk = 4;
+constexpr uint32_t kNoTile = 0xFFFFFFFFu;
+__device__ __forceinline__ uint32_t admissible_word(const ScanParams& p, uint32_t chunk) {
+    uint32_t adm = 0xFFFFFFFFu;
+    if (p.mask) adm &= p.mask[chunk];
+    if (p.live) adm &= p.live[chunk];
+    return adm;
+}
+
 __device__ __forceinline__ uint32_t admissible_byte(const ScanParams& p, uint32_t tile) {
     uint32_t adm = 0xFFu;
     if (p.mask) adm &= reinterpret_cast<const uint8_t*>(p.mask)[tile];
     if (p.live) adm &= reinterpret_cast<const uint8_t*>(p.live)[tile];
     return adm;
+}
+
+// ---------------------------------------------------------------------------
+// Producer of the TMA ring (one thread).  Tiles come from two schedules:
+//   * static: iteration `it` < n_static of CTA b is tile b + it*G, as a plain round-robin;
+//   * dynamic (p.tile_ctr != NULL): the remaining tiles [p.dyn_tile0, T) are claimed from a
+//     global counter in chunks of kDynChunk consecutive tiles.  A purely static split leaves
+//     the slowest SM ~15% behind the fastest (far-die / channel contention) and that tail is
+//     idle HBM; a purely dynamic one pays the claim latency before the first byte moves.
+//     Claims run two ahead (the first two are issued before the static phase), so neither the
+//     atomic's nor the mask word's latency is ever waited on.
+// The producer publishes (tile, admissible byte) of a dynamic stage in the header before it
+// arms the full barrier, and ends with one stop marker per consumer warp (warp w owns the
+// stages s with s % ncw == w).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void scan_producer(const ScanParams& p, SmemHeader* hdr, uint8_t* smem, int ncw,
+                                              uint32_t iters, uint32_t T) {
+    const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
+    const uint32_t row_bytes = uint32_t(p.ld4) * 16u;
+    const uint32_t G = gridDim.x;
+    const int S = p.stages;
+    const bool dyn = p.tile_ctr != nullptr;
+    const uint32_t n_static = dyn ? p.static_iters : iters;
+    const uint32_t nchunks = dyn ? (T - p.dyn_tile0 + kDynChunk - 1) / kDynChunk : 0u;
+    const uint32_t word0 = p.dyn_tile0 / kDynChunk;
+    uint32_t c0 = 0, c1 = 0;
+    if (dyn) {  // both issued unconditionally: nothing here waits on the first one's result
+        c0 = atomicAdd(p.tile_ctr, 1u);
+        c1 = atomicAdd(p.tile_ctr, 1u);
+    }
+    int s = 0;
+    uint32_t ph = 0;
+    auto issue = [&](uint32_t tile) {
+        const uint32_t row0 = tile * kRowsPerTile;
+        const uint32_t bytes = min(uint32_t(kRowsPerTile), p.n - row0) * row_bytes;
+        mbar_arrive_expect_tx(&hdr->full[s], bytes);
+        bulk_g2s(smem + p.stage_off + size_t(s) * p.stage_bytes, p.x + size_t(row0) * size_t(p.ld4) * 4, bytes,
+                 &hdr->full[s], tile < p.pin_tiles ? pol_keep : pol_stream);
+        if (++s == S) {
+            s = 0;
+            ph ^= 1u;
+        }
+    };
+    for (uint32_t it = 0; it < n_static; it++) {
+        mbar_wait(&hdr->empty[s], ph ^ 1u);
+        issue(blockIdx.x + it * G);
+    }
+    if (!dyn) return;
+    uint32_t a0 = (c0 < nchunks) ? admissible_word(p, word0 + c0) : 0u;
+    while (c0 < nchunks) {
+        // every claim's result is consumed before this loop ends, so none is in flight when
+        // the last CTA resets the counter
+        const uint32_t c2 = (c1 < nchunks) ? atomicAdd(p.tile_ctr, 1u) : nchunks;
+        const uint32_t a1 = (c1 < nchunks) ? admissible_word(p, word0 + c1) : 0u;
+#pragma unroll
+        for (uint32_t t = 0; t < kDynChunk; t++) {
+            const uint32_t tile = p.dyn_tile0 + c0 * kDynChunk + t;
+            if (tile >= T) break;
+            mbar_wait(&hdr->empty[s], ph ^ 1u);
+            hdr->tile_of[s] = tile;
+            hdr->adm_of[s] = (a0 >> (8 * t)) & 0xFFu;
+            issue(tile);
+        }
+        c0 = c1;
+        c1 = c2;
+        a0 = a1;
+    }
+    asm volatile("" ::"r"(c1));  // the second claim has returned even when the loop never ran
+    for (int i = 0; i < ncw; i++) {
+        mbar_wait(&hdr->empty[s], ph ^ 1u);
+        hdr->tile_of[s] = kNoTile;
+        mbar_arrive(&hdr->full[s]);
+        if (++s == S) {
+            s = 0;
+            ph ^= 1u;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -384,27 +482,7 @@ __global__ void __launch_bounds__(kTma ? 288 : 256, kTma ? 1 : 2) scan_q1_kernel
         }
         __syncthreads();
         if (warp == 0) {
-            if (lane == 0) {
-                const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
-                const uint32_t row_bytes = uint32_t(p.ld4) * 16u;
-                int s = 0;
-                uint32_t ph = 0;
-                for (uint32_t it = 0; it < iters; it++) {
-                    mbar_wait(&hdr->empty[s], ph ^ 1u);
-                    uint32_t tile = blockIdx.x + it * G;
-                    uint32_t row0 = tile * kRowsPerTile;
-                    uint32_t rows = min(uint32_t(kRowsPerTile), p.n - row0);
-                    uint32_t bytes = rows * row_bytes;
-                    mbar_arrive_expect_tx(&hdr->full[s], bytes);
-                    bulk_g2s(smem + p.stage_off + size_t(s) * p.stage_bytes,
-                             p.x + size_t(row0) * size_t(p.ld4) * 4, bytes, &hdr->full[s],
-                             tile < p.pin_tiles ? pol_keep : pol_stream);
-                    if (++s == S) {
-                        s = 0;
-                        ph ^= 1u;
-                    }
-                }
-            }
+            if (lane == 0) scan_producer(p, hdr, smem, ncw, iters, T);
             return;
         }
     }
@@ -420,17 +498,29 @@ __global__ void __launch_bounds__(kTma ? 288 : 256, kTma ? 1 : 2) scan_q1_kernel
     const bool leader = (lane & 3) == 0;
     const int ld4 = p.ld4;
 
-    for (uint32_t it = cw; it < iters; it += ncw) {
-        const uint32_t tile = blockIdx.x + it * G;
+    const bool dyn = kTma && p.tile_ctr != nullptr;
+    const uint32_t n_static = dyn ? p.static_iters : iters;
+    for (uint32_t it = cw;; it += ncw) {
+        uint32_t tile, adm;
+        if (it < n_static) {
+            tile = blockIdx.x + it * G;
+            adm = admissible_byte(p, tile);  // issued before the data wait
+            if (kTma) mbar_wait(&hdr->full[it % S], (it / S) & 1u);
+        } else if (dyn) {
+            const int s = it % S;
+            mbar_wait(&hdr->full[s], (it / S) & 1u);
+            tile = hdr->tile_of[s];
+            if (tile == kNoTile) break;
+            adm = hdr->adm_of[s];
+        } else {
+            break;
+        }
         const uint32_t row0 = tile * kRowsPerTile;
-        const uint32_t adm = admissible_byte(p, tile);  // issued before the data wait
         float acc[8];
 #pragma unroll
         for (int r = 0; r < 8; r++) acc[r] = 0.f;
         if (kTma) {
             const int s = it % S;
-            const uint32_t ph = (it / S) & 1u;
-            mbar_wait(&hdr->full[s], ph);
             const float4* st = reinterpret_cast<const float4*>(smem + p.stage_off + size_t(s) * p.stage_bytes);
 #pragma unroll
             for (int j = 0; j < D4; j++) {
@@ -508,27 +598,7 @@ __global__ void __launch_bounds__(kTma ? 288 : 256, (kTma || NQ >= 8) ? 1 : 2) s
         }
         __syncthreads();
         if (warp == 0) {
-            if (lane == 0) {
-                const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
-                const uint32_t row_bytes = uint32_t(ld4) * 16u;
-                int s = 0;
-                uint32_t ph = 0;
-                for (uint32_t it = 0; it < iters; it++) {
-                    mbar_wait(&hdr->empty[s], ph ^ 1u);
-                    uint32_t tile = blockIdx.x + it * G;
-                    uint32_t row0 = tile * kRowsPerTile;
-                    uint32_t rows = min(uint32_t(kRowsPerTile), p.n - row0);
-                    uint32_t bytes = rows * row_bytes;
-                    mbar_arrive_expect_tx(&hdr->full[s], bytes);
-                    bulk_g2s(smem + p.stage_off + size_t(s) * p.stage_bytes,
-                             p.x + size_t(row0) * size_t(ld4) * 4, bytes, &hdr->full[s],
-                             tile < p.pin_tiles ? pol_keep : pol_stream);
-                    if (++s == S) {
-                        s = 0;
-                        ph ^= 1u;
-                    }
-                }
-            }
+            if (lane == 0) scan_producer(p, hdr, smem, ncw, iters, T);
             return;
         }
     }
@@ -567,10 +637,23 @@ __global__ void __launch_bounds__(kTma ? 288 : 256, (kTma || NQ >= 8) ? 1 : 2) s
     const int my_row = tile_row_of_lane(lane);
     const bool leader = (lane & 3) == 0;
 
-    for (uint32_t it = cw; it < iters; it += ncw) {
-        const uint32_t tile = blockIdx.x + it * G;
+    const bool dyn = kTma && p.tile_ctr != nullptr;
+    const uint32_t n_static = dyn ? p.static_iters : iters;
+    for (uint32_t it = cw;; it += ncw) {
+        uint32_t tile, adm;
+        if (it < n_static) {
+            tile = blockIdx.x + it * G;
+            adm = admissible_byte(p, tile);
+            if (kTma) mbar_wait(&hdr->full[it % S], (it / S) & 1u);
+        } else if (dyn) {
+            mbar_wait(&hdr->full[it % S], (it / S) & 1u);
+            tile = hdr->tile_of[it % S];
+            if (tile == kNoTile) break;
+            adm = hdr->adm_of[it % S];
+        } else {
+            break;
+        }
         const uint32_t row0 = tile * kRowsPerTile;
-        const uint32_t adm = admissible_byte(p, tile);
         float acc[NQ][8];
 #pragma unroll
         for (int qi = 0; qi < NQ; qi++)
@@ -582,8 +665,6 @@ __global__ void __launch_bounds__(kTma ? 288 : 256, (kTma || NQ >= 8) ? 1 : 2) s
         int s = 0;
         if (kTma) {
             s = it % S;
-            const uint32_t ph = (it / S) & 1u;
-            mbar_wait(&hdr->full[s], ph);
             st = reinterpret_cast<const float4*>(smem + p.stage_off + size_t(s) * p.stage_bytes);
         } else {
             st = reinterpret_cast<const float4*>(p.x) + size_t(row0) * ld4;

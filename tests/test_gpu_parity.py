@@ -347,6 +347,42 @@ def test_tma_ring_any_consumer_warp_count(mv, d):
     eng.close()
 
 
+@pytest.mark.parametrize("n,d,grid", [(120_000, 384, 0), (99_991, 512, 0), (120_000, 200, 37), (5_000, 768, 0),
+                                      (131, 64, 0), (64_123, 1536, 146)])
+def test_dynamic_tile_schedule_is_result_neutral(mv, n, d, grid):
+    """The TMA scan serves part of the tiles from a global counter ("dyn_tiles" = that percentage).
+    Which CTA scans which tile must not show in the results: every percentage, with masks,
+    tombstones, 1/2/4 queries per launch, ragged last tile/word and a grid that is not a multiple
+    of 4, returns exactly what the static split (0) and the oracle return."""
+    eng = mv.FlatIPEngine(d)
+    eng.add_synthetic(21, 0, n, dist=0, normalize=True)
+    eng.set_option("batch_mode", 0)
+    eng.set_option("scan_variant", 1)
+    if grid:
+        eng.set_option("grid_ctas", grid)
+    eng.remove_rows(np.arange(3, n, 11))
+    adm = np.random.default_rng(22).random(n) < 0.5
+    q = O.synth_rows(23, 0, 4, d)
+    O.normalize_L2(q)
+    x = O.synth_rows(21, 0, n, d)
+    O.normalize_L2(x)
+    live = np.ones(n, dtype=bool)
+    live[np.arange(3, n, 11)] = False
+    ref = {}
+    for pct in (0, 15, 50, 100):
+        eng.set_option("dyn_tiles", pct)
+        for nq in (1, 2, 4):
+            for mask in (None, adm):
+                for rep in range(2):   # the counter must come back to zero after every launch
+                    D, I = eng.search(q[:nq], 10, mask=mask)
+                    key = (nq, mask is None)
+                    if key not in ref:
+                        ref[key] = (D, I)
+                        _check(x, q[:nq], 10, D, I, live if mask is None else (live & adm))
+                    assert np.array_equal(I, ref[key][1]) and np.array_equal(D, ref[key][0]), (pct, nq, mask is None, rep)
+    eng.close()
+
+
 def test_coalesced_concurrent_searches_equal_direct_ones(mv):
     """Concurrent single-query calls are coalesced into shared passes (<= 8 per scan launch with
     per-query filters, tensor-core batch when unfiltered); every caller must get exactly what a
