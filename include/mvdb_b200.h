@@ -242,6 +242,10 @@ int mvdb_debug_gemm_scores(mvdb_index* ix, const float* q, int64_t nq, float* ou
 /* Test hook: with option "trace" = 1 the single-query scan kernel stamps %globaltimer at fixed
  * points (slots 0-6: CTA 0, slots 8-13: the last CTA); reads the 16 stamps of the latest launch. */
 int mvdb_debug_read_trace(mvdb_index* ix, uint64_t* out16);
+/* Test hook: with option "gemm_prof" = 1 the cluster GEMM kernels count, per CTA, the cycles their
+ * producer / MMA / epilogue threads spend blocked on each barrier (8 counters per CTA, layout at
+ * GemmParams::prof in csrc/gemm_tc.cuh); reads the counters of the most recent launch. */
+int mvdb_debug_read_gemm_prof(mvdb_index* ix, uint64_t* out, int ctas);
 
 /* Number of kernel launches issued by this library since load (bench.py's
  * "gpu_launches" claim is read from here). */

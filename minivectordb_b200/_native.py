@@ -38,7 +38,7 @@ EXPORTS = [
     "mvdb_exchange_status", "mvdb_exchange_destroy", "mvdb_index_search_exchange", "mvdb_debug_gemm_scores",
     "mvdb_index_mask_create", "mvdb_mask_destroy", "mvdb_index_search_with_mask",
     "mvdb_column_create", "mvdb_column_destroy", "mvdb_column_append", "mvdb_mask_from_predicate",
-    "mvdb_mask_create_filled", "mvdb_mask_combine", "mvdb_mask_count", "mvdb_debug_read_trace",
+    "mvdb_mask_create_filled", "mvdb_mask_combine", "mvdb_mask_count", "mvdb_debug_read_trace", "mvdb_debug_read_gemm_prof",
 ]
 
 
@@ -146,6 +146,7 @@ def lib():
             "mvdb_mask_combine": (i, [c_vp, c_vp, i]),
             "mvdb_mask_count": (i, [c_vp, ctypes.POINTER(u64)]),
             "mvdb_debug_read_trace": (i, [c_vp, c_vp]),
+            "mvdb_debug_read_gemm_prof": (i, [c_vp, c_vp, ctypes.c_int]),
             "mvdb_index_search_exchange": (i, [c_vp, c_vp, c_vp, c_vp, i64, i64, c_vp, u64, i, c_vp, c_vp, c_vp]),
         }
         for name, (res, args) in sig.items():

@@ -65,7 +65,25 @@ struct GemmParams {
     // debug: dense scores [nq][n_total] (nullptr in production)
     float* dense;
     int64_t dense_ld;
+    // debug: per-CTA cycle counters [gridDim.x][8] (nullptr in production): 0 MMA thread total, 1 its wait
+    // for operands (full), 2 its wait for a drained accumulator (tempty), 3 producer total, 4 producer wait
+    // for a free stage (empty), 5 epilogue warp 4 total, 6 its wait for an accumulator (tfull)
+    // 7 wall time of the MMA thread in ns (globaltimer)
+    unsigned long long* prof;
+    int debug;   // experiments, results are garbage: 1 = no operand loads (barriers only), 2 = no epilogue work, 4 = epilogue reads TMEM but skips the reduction,
+                 // 8 = MMA thread never waits for operands (use with 1)
 };
+
+// mbar_wait that adds the cycles it blocked to `acc` when profiling
+__device__ __forceinline__ void mbar_wait_prof(uint64_t* bar, uint32_t parity, bool on, long long& acc) {
+    if (on) {
+        const long long a = clock64();
+        mbar_wait(bar, parity);
+        acc += clock64() - a;
+    } else {
+        mbar_wait(bar, parity);
+    }
+}
 
 // ---- PTX wrappers ------------------------------------------------------------
 __device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -110,6 +128,81 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
+}
+// One k-block (4 x K=16) of single-CTA MMAs with two barrier PEEKS folded in: mbarrier.test_wait
+// (non-blocking) on `peek0` / `peek1` is issued BEFORE the MMAs and its predicate is only read
+// AFTER them, so the issuing thread never sits between two tcgen05.mma waiting for shared memory.
+// Returns bit 0 = peek0 complete, bit 1 = peek1 complete (a peek that is switched off reads as 0).
+__device__ __forceinline__ uint32_t umma_bf16_x4_peek(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                      uint32_t accumulate_first, uint64_t* peek0, uint32_t parity0,
+                                                      uint32_t do0, uint64_t* peek1, uint32_t parity1, uint32_t do1) {
+    uint32_t tok;
+    asm volatile(
+        "{\n\t.reg .pred p0, p1, pa, pt, d0, d1;\n\t"
+        ".reg .b32 t0, t1;\n\t"
+        ".reg .b64 a, b;\n\t"
+        "setp.ne.b32 d0, %8, 0;\n\t"
+        "setp.ne.b32 d1, %11, 0;\n\t"
+        "setp.ne.b32 p0, 0, 0;\n\t"
+        "setp.ne.b32 p1, 0, 0;\n\t"
+        "@d0 mbarrier.test_wait.parity.shared::cta.b64 p0, [%6], %7;\n\t"
+        "@d1 mbarrier.test_wait.parity.shared::cta.b64 p1, [%9], %10;\n\t"
+        "setp.ne.b32 pa, %5, 0;\n\t"
+        "setp.eq.b32 pt, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %3, %4, pa;\n\t"
+        "add.u64 a, %2, 2;\n\t"
+        "add.u64 b, %3, 2;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, pt;\n\t"
+        "add.u64 a, %2, 4;\n\t"
+        "add.u64 b, %3, 4;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, pt;\n\t"
+        "add.u64 a, %2, 6;\n\t"
+        "add.u64 b, %3, 6;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, pt;\n\t"
+        "selp.u32 t0, 1, 0, p0;\n\t"
+        "selp.u32 t1, 2, 0, p1;\n\t"
+        "or.b32 %0, t0, t1;\n\t}"
+        : "=r"(tok)
+        : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate_first), "r"(smem_u32(peek0)), "r"(parity0),
+          "r"(do0), "r"(smem_u32(peek1)), "r"(parity1), "r"(do1)
+        : "memory");
+    return tok;
+}
+// same for a CTA pair (issued by the leader CTA only)
+__device__ __forceinline__ uint32_t umma_bf16_x4_peek_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                      uint32_t accumulate_first, uint64_t* peek0, uint32_t parity0,
+                                                      uint32_t do0, uint64_t* peek1, uint32_t parity1, uint32_t do1) {
+    uint32_t tok;
+    asm volatile(
+        "{\n\t.reg .pred p0, p1, pa, pt, d0, d1;\n\t"
+        ".reg .b32 t0, t1;\n\t"
+        ".reg .b64 a, b;\n\t"
+        "setp.ne.b32 d0, %8, 0;\n\t"
+        "setp.ne.b32 d1, %11, 0;\n\t"
+        "setp.ne.b32 p0, 0, 0;\n\t"
+        "setp.ne.b32 p1, 0, 0;\n\t"
+        "@d0 mbarrier.test_wait.parity.shared::cta.b64 p0, [%6], %7;\n\t"
+        "@d1 mbarrier.test_wait.parity.shared::cta.b64 p1, [%9], %10;\n\t"
+        "setp.ne.b32 pa, %5, 0;\n\t"
+        "setp.eq.b32 pt, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%1], %2, %3, %4, pa;\n\t"
+        "add.u64 a, %2, 2;\n\t"
+        "add.u64 b, %3, 2;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%1], a, b, %4, pt;\n\t"
+        "add.u64 a, %2, 4;\n\t"
+        "add.u64 b, %3, 4;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%1], a, b, %4, pt;\n\t"
+        "add.u64 a, %2, 6;\n\t"
+        "add.u64 b, %3, 6;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%1], a, b, %4, pt;\n\t"
+        "selp.u32 t0, 1, 0, p0;\n\t"
+        "selp.u32 t1, 2, 0, p1;\n\t"
+        "or.b32 %0, t0, t1;\n\t}"
+        : "=r"(tok)
+        : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate_first), "r"(smem_u32(peek0)), "r"(parity0),
+          "r"(do0), "r"(smem_u32(peek1)), "r"(parity1), "r"(do1)
+        : "memory");
+    return tok;
 }
 // 32 lanes x 32 consecutive 32-bit columns: thread t of the warp receives lane (base_lane + t)
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -185,20 +278,45 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
             uint32_t v[32];
             tmem_ld_32x32(t_lane + uint32_t(32 * g), v);
             uint32_t m = 0;
-            // ~row of column 0 of this group; column j is index row (tile_row0 + 32g + j) * stride
-            const uint32_t low0 = 0xFFFFFFFFu - (tile_row0 + 32 * g) * p.row_stride;
+            // Common case first: once the thresholds are warm almost no group holds a candidate,
+            // so reduce the 32 scores to their maximum (16 FMNMX3) and compare ONCE.  The epilogue
+            // warps share their schedulers with the MMA-issuing thread: every instruction saved
+            // here is an issue slot it gets sooner (measured: the per-element test cost the
+            // tensor pipe 17% at d = 1024 and 40% at d = 384).  fmaxf drops NaNs, which never pass.
+            float sub[4];
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-                // key(s,row) > thr  <=>  s > t, or s == t and ~row > thr_low  (float compares: NaN never
-                // passes, -0 == +0 exactly as the key's canonicalisation has it)
-                const float s = __uint_as_float(v[j]);
-                const uint32_t pass = uint32_t(s > thr_score) | (uint32_t(s == thr_score) & uint32_t((low0 - uint32_t(j) * p.row_stride) > thr_low));
-                m |= pass << j;
+            for (int b = 0; b < 4; b++) {
+                float t = __uint_as_float(v[8 * b]);
+#pragma unroll
+                for (int j = 1; j < 8; j++) t = fmaxf(t, __uint_as_float(v[8 * b + j]));
+                sub[b] = t;
             }
-            m &= q_ok ? adm[g] : 0u;
-            if (qm) {
-                const uint32_t w = (tile_row0 >> 5) + uint32_t(g);
-                m &= (w < qm_words) ? qm[w] : 0u;
+            float mx = fmaxf(fmaxf(sub[0], sub[1]), fmaxf(sub[2], sub[3]));
+            if (p.debug & 4) mx = __uint_as_float(v[0] & v[31]);   // experiment: TMEM reads only, no reduction
+            if (q_ok && mx >= thr_score) {
+                // ~row of column 0 of this group; column j is index row (tile_row0 + 32g + j) * stride
+                const uint32_t low0 = 0xFFFFFFFFu - (tile_row0 + 32 * g) * p.row_stride;
+                // rare path, still kept short: only the 8-score blocks whose own maximum passes are
+                // examined score by score (hits are sparse, so that is nearly always one of the four)
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    if (sub[b] >= thr_score) {
+#pragma unroll
+                        for (int j = 8 * b; j < 8 * b + 8; j++) {
+                            // key(s,row) > thr  <=>  s > t, or s == t and ~row > thr_low  (float compares: NaN never
+                            // passes, -0 == +0 exactly as the key's canonicalisation has it)
+                            const float sc = __uint_as_float(v[j]);
+                            const uint32_t pass = uint32_t(sc > thr_score) |
+                                                  (uint32_t(sc == thr_score) & uint32_t((low0 - uint32_t(j) * p.row_stride) > thr_low));
+                            m |= pass << j;
+                        }
+                    }
+                }
+                m &= adm[g];
+                if (qm) {
+                    const uint32_t w = (tile_row0 >> 5) + uint32_t(g);
+                    m &= (w < qm_words) ? qm[w] : 0u;
+                }
             }
             hit[g - g_lo] = m;
             total += __popc(m);
@@ -295,27 +413,32 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_bf16(kGemmBM, kGemmBN);
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            // barrier peeks folded into the MMA issue: see gemm_topk_kernel_mc
+            uint32_t tok_full = 0, tok_acc = 0;
             for (uint32_t t = t_lo; t < t_hi; t++) {
-                    mbar_wait(&bars->tempty[acc], acc_phase ^ 1u);   // epilogue has drained this accumulator
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + acc * kGemmBN;
-                    for (uint32_t kb = 0; kb < n_kb; kb++) {
-                        mbar_wait(&bars->full[stage], phase);
-                        tc_fence_after();
-                        const uint32_t a_addr = smem_u32(smem + stage * kGemmStageBytes);
-                        const uint64_t a_desc = umma_desc_sw128(a_addr);
-                        const uint64_t b_desc = umma_desc_sw128(a_addr + kGemmABytes);
-#pragma unroll
-                        for (uint32_t k = 0; k < kGemmBK / 16; k++) {
-                            // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in (addr >> 4)
-                            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                        }
-                        umma_commit(&bars->empty[stage]);   // frees the smem slot when these MMAs retire
-                        if (++stage == kGemmStages) { stage = 0; phase ^= 1u; }
-                    }
-                    umma_commit(&bars->tfull[acc]);         // accumulator complete -> epilogue
-                    if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                if (!tok_acc) mbar_wait(&bars->tempty[acc], acc_phase ^ 1u);   // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * kGemmBN;
+                for (uint32_t kb = 0; kb < n_kb; kb++) {
+                    if (!tok_full) mbar_wait(&bars->full[stage], phase);
+                    const uint32_t a_addr = smem_u32(smem + stage * kGemmStageBytes);
+                    const uint64_t a_desc = umma_desc_sw128(a_addr);
+                    const uint64_t b_desc = umma_desc_sw128(a_addr + kGemmABytes);
+                    const uint32_t cur = stage;
+                    if (++stage == kGemmStages) { stage = 0; phase ^= 1u; }
+                    const bool last_kb = kb + 1 == n_kb;
+                    const bool more = !(last_kb && t + 1 == t_hi);
+                    const uint32_t tok = umma_bf16_x4_peek(d_tmem, a_desc, b_desc, idesc, kb != 0 ? 1u : 0u,
+                                                           &bars->full[stage], phase, more ? 1u : 0u,
+                                                           &bars->tempty[acc ^ 1u], acc_phase ^ (acc ^ 1u),
+                                                           (more && last_kb) ? 1u : 0u);
+                    tok_full = tok & 1u;
+                    if (last_kb) tok_acc = tok >> 1;
+                    umma_commit(&bars->empty[cur]);   // frees the smem slot when these MMAs retire
                 }
+                umma_commit(&bars->tfull[acc]);       // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
         }
     } else if (warp >= 4) {
         const uint32_t quad = uint32_t(warp & 3);            // the TMEM lane quadrant this warp may read (warp % 4)
@@ -367,22 +490,23 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 // CTAs' shared memory and writes a 128 x 256 accumulator into each CTA's TMEM.
 // Per SM this halves the B-operand traffic from L2 and makes room for a 6-stage ring.
 //
-// Synchronisation (every barrier is local to the CTA that waits on it):
-//   full[s]      each CTA: its own TMA bytes have landed
-//   peer_full[s] leader only: the peer's relay lane arrives remotely once the PEER's
-//                full[s] completed (no remote TMA signalling needed)
+// Synchronisation:
+//   full[s]      LEADER only: armed by the leader's producer with the bytes of BOTH CTAs' halves;
+//                the peer's TMA loads complete their transaction bytes on the leader's barrier
+//                directly (cp.async.bulk.tensor ... .cta_group::2 with the leader's barrier
+//                address), so the MMA thread waits on ONE barrier and no relay is needed
 //   empty[s]     each CTA: the leader's tcgen05.commit multicasts one arrival to both
 //   tfull[a]     each CTA: accumulator a complete (multicast commit)
-//   tempty[a]    leader only, count 8: the 4 epilogue warps of BOTH CTAs (peer: remote)
+//   tempty[a]    leader only, count 16: the 8 epilogue warps of BOTH CTAs (peer: remote arrive)
 // ---------------------------------------------------------------------------
-constexpr int kGemm2Stages = 6;
+constexpr int kGemm2Stages = 7;
 constexpr uint32_t kGemm2HalfB = (kGemmBN / 2) * kGemmBK * 2;            // 16 KB: this CTA's 128 rows of the B tile
 constexpr uint32_t kGemm2StageBytes = kGemmABytes + kGemm2HalfB;          // 32 KB
 constexpr uint32_t kGemm2SmemBytes = kGemm2Stages * kGemm2StageBytes + 512 + 1024;
+static_assert(kGemm2SmemBytes <= 232448, "2-CTA ring exceeds the 227 KB shared-memory opt-in");
 
 struct Gemm2Barriers {
     uint64_t full[kGemm2Stages];
-    uint64_t peer_full[kGemm2Stages];
     uint64_t empty[kGemm2Stages];
     uint64_t tfull[2];
     uint64_t tempty[2];
@@ -405,6 +529,22 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
         "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
         "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
         "r"(rank)
+        : "memory");
+}
+// shared::cluster address of `ptr`'s offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(const void* ptr, uint32_t rank) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(ptr)), "r"(rank));
+    return ra;
+}
+// TMA load of a CTA pair: data lands in THIS CTA's shared memory, the transaction bytes complete
+// on `bar_cluster_addr`, which may be a barrier of the peer CTA (shared::cluster address)
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst_smem, const CUtensorMap* map, int c0, int c1,
+                                                uint32_t bar_cluster_addr) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst_smem)),
+        "l"(map), "r"(c0), "r"(c1), "r"(bar_cluster_addr)
         : "memory");
 }
 __device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
@@ -445,7 +585,6 @@ gemm_topk_kernel_2cta(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     if (threadIdx.x == 0) {
         for (int s = 0; s < kGemm2Stages; s++) {
             mbar_init(&bars->full[s], 1);
-            mbar_init(&bars->peer_full[s], 1);
             mbar_init(&bars->empty[s], 1);
         }
         for (int a = 0; a < 2; a++) {
@@ -473,54 +612,76 @@ gemm_topk_kernel_2cta(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const uint32_t t_hi = uint32_t(n_tiles * (pair + 1) / n_pairs);
 
     if (warp == 0) {
-        if (lane == 0) {   // TMA producer: this CTA's halves of A and B
+        if (lane == 0) {   // TMA producer: this CTA's halves of A and B, signalled on the LEADER's barrier
             uint32_t stage = 0, phase = 0;
+            const bool prof = p.prof != nullptr;
+            long long w_empty = 0;
+            const long long t_begin = clock64();
             for (uint32_t t = t_lo; t < t_hi; t++) {
                 const uint32_t xt = t / n_qb2, qb2 = t % n_qb2;
                 for (uint32_t kb = 0; kb < n_kb; kb++) {
-                    mbar_wait(&bars->empty[stage], phase ^ 1u);
+                    mbar_wait_prof(&bars->empty[stage], phase ^ 1u, prof, w_empty);
                     uint8_t* sA = smem + stage * kGemm2StageBytes;
                     uint8_t* sB = sA + kGemmABytes;
-                    mbar_arrive_expect_tx(&bars->full[stage], kGemm2StageBytes);
-                    tma_load_2d(sA, &tmQ, int(kb * kGemmBK), int(qb2 * 2 * kGemmBM + rank * kGemmBM), &bars->full[stage]);
-                    tma_load_2d(sB, &tmX, int(kb * kGemmBK), int(p.row0 + xt * kGemmBN + rank * (kGemmBN / 2)), &bars->full[stage]);
+                    const uint32_t full0 = mapa_u32(&bars->full[stage], 0);
+                    if (p.debug & 1) {   // experiment: synchronisation only, no operand traffic
+                        if (leader) mbar_arrive(&bars->full[stage]);
+                        if (++stage == kGemm2Stages) { stage = 0; phase ^= 1u; }
+                        continue;
+                    }
+                    if (leader) mbar_arrive_expect_tx(&bars->full[stage], 2 * kGemm2StageBytes);
+                    tma_load_2d_2sm(sA, &tmQ, int(kb * kGemmBK), int(qb2 * 2 * kGemmBM + rank * kGemmBM), full0);
+                    tma_load_2d_2sm(sB, &tmX, int(kb * kGemmBK), int(p.row0 + xt * kGemmBN + rank * (kGemmBN / 2)), full0);
                     if (++stage == kGemm2Stages) { stage = 0; phase ^= 1u; }
                 }
             }
-        }
-    } else if (warp == 3) {
-        if (lane == 0 && !leader) {   // relay: tell the leader that the peer's half of stage s is in place
-            uint32_t stage = 0, phase = 0;
-            for (uint32_t t = t_lo; t < t_hi; t++)
-                for (uint32_t kb = 0; kb < n_kb; kb++) {
-                    mbar_wait(&bars->full[stage], phase);
-                    mbar_arrive_remote(&bars->peer_full[stage], 0);
-                    if (++stage == kGemm2Stages) { stage = 0; phase ^= 1u; }
-                }
+            if (prof) {
+                p.prof[blockIdx.x * 8 + 3] = (unsigned long long)(clock64() - t_begin);
+                p.prof[blockIdx.x * 8 + 4] = (unsigned long long)w_empty;
+            }
         }
     } else if (warp == 1) {
         if (lane == 0 && leader) {   // the pair's single MMA issuer
             const uint32_t idesc = umma_idesc_bf16(2 * kGemmBM, kGemmBN);
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            const bool prof = p.prof != nullptr;
+            long long w_full = 0, w_tempty = 0;
+            const long long t_begin = clock64();
+            unsigned long long g_begin;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_begin));
+            // barrier peeks folded into the MMA issue: see gemm_topk_kernel_mc
+            uint32_t tok_full = 0, tok_acc = 0;
             for (uint32_t t = t_lo; t < t_hi; t++) {
-                mbar_wait(&bars->tempty[acc], acc_phase ^ 1u);
+                if (!tok_acc) mbar_wait_prof(&bars->tempty[acc], acc_phase ^ 1u, prof, w_tempty);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * kGemmBN;
                 for (uint32_t kb = 0; kb < n_kb; kb++) {
-                    mbar_wait(&bars->full[stage], phase);
-                    mbar_wait(&bars->peer_full[stage], phase);
-                    tc_fence_after();
+                    if (!tok_full && !(p.debug & 8)) mbar_wait_prof(&bars->full[stage], phase, prof, w_full);
                     const uint32_t a_addr = smem_u32(smem + stage * kGemm2StageBytes);
                     const uint64_t a_desc = umma_desc_sw128(a_addr);
                     const uint64_t b_desc = umma_desc_sw128(a_addr + kGemmABytes);
-#pragma unroll
-                    for (uint32_t k = 0; k < kGemmBK / 16; k++)
-                        umma_bf16_2cta(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                    umma_commit_2cta(&bars->empty[stage], 0x3);   // frees the stage in both CTAs
+                    const uint32_t cur = stage;
                     if (++stage == kGemm2Stages) { stage = 0; phase ^= 1u; }
+                    const bool last_kb = kb + 1 == n_kb;
+                    const bool more = !(last_kb && t + 1 == t_hi);
+                    const uint32_t tok = umma_bf16_x4_peek_2cta(d_tmem, a_desc, b_desc, idesc, kb != 0 ? 1u : 0u,
+                                                                &bars->full[stage], phase, more ? 1u : 0u,
+                                                                &bars->tempty[acc ^ 1u], acc_phase ^ (acc ^ 1u),
+                                                                (more && last_kb) ? 1u : 0u);
+                    tok_full = tok & 1u;
+                    if (last_kb) tok_acc = tok >> 1;
+                    umma_commit_2cta(&bars->empty[cur], 0x3);   // frees the stage in both CTAs
                 }
-                umma_commit_2cta(&bars->tfull[acc], 0x3);         // accumulator ready in both CTAs
+                umma_commit_2cta(&bars->tfull[acc], 0x3);       // accumulator ready in both CTAs
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+            if (prof) {
+                p.prof[blockIdx.x * 8 + 0] = (unsigned long long)(clock64() - t_begin);
+                p.prof[blockIdx.x * 8 + 1] = (unsigned long long)w_full;
+                p.prof[blockIdx.x * 8 + 2] = (unsigned long long)w_tempty;
+                unsigned long long g_end;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_end));
+                p.prof[blockIdx.x * 8 + 7] = g_end - g_begin;
             }
         }
     } else if (warp >= 4) {
@@ -529,6 +690,9 @@ gemm_topk_kernel_2cta(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         uint32_t acc = 0, acc_phase = 0;
         uint32_t cur_xt = 0xFFFFFFFFu, tile_row0 = 0;
         uint32_t adm[8];
+        const bool prof = p.prof != nullptr;
+        long long w_tfull = 0;
+        const long long t_begin = clock64();
         for (uint32_t t = t_lo; t < t_hi; t++) {
             const uint32_t xt = t / n_qb2, qb2 = t % n_qb2;
             if (xt != cur_xt) {
@@ -548,9 +712,9 @@ gemm_topk_kernel_2cta(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 }
             }
             const int64_t q = int64_t(qb2) * 2 * kGemmBM + rank * kGemmBM + quad * 32 + lane;
-            mbar_wait(&bars->tfull[acc], acc_phase);
+            mbar_wait_prof(&bars->tfull[acc], acc_phase, prof, w_tfull);
             tc_fence_after();
-            gemm_epilogue_tile(p, tmem_base + ((quad * 32u) << 16) + acc * kGemmBN, q, tile_row0, adm, g_lo);
+            if (!(p.debug & 2)) gemm_epilogue_tile(p, tmem_base + ((quad * 32u) << 16) + acc * kGemmBN, q, tile_row0, adm, g_lo);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -558,6 +722,10 @@ gemm_topk_kernel_2cta(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 else mbar_arrive_remote(&bars->tempty[acc], 0);
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+        if (prof && warp == 4 && lane == 0) {
+            p.prof[blockIdx.x * 8 + 5] = (unsigned long long)(clock64() - t_begin);
+            p.prof[blockIdx.x * 8 + 6] = (unsigned long long)w_tfull;
         }
     }
     tc_fence_before();
@@ -632,12 +800,20 @@ gemm_topk_kernel_mc(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (warp == 0) {
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
+            const bool prof = p.prof != nullptr;
+            long long w_empty = 0;
+            const long long t_begin = clock64();
             for (uint32_t t = t_lo; t < t_hi; t++) {
                 const uint32_t xt = t / n_qb2, qb = (t % n_qb2) * CS + rank;
                 for (uint32_t kb = 0; kb < n_kb; kb++) {
-                    mbar_wait(&bars->empty[stage], phase ^ 1u);   // freed by BOTH CTAs
+                    mbar_wait_prof(&bars->empty[stage], phase ^ 1u, prof, w_empty);   // freed by BOTH CTAs
                     uint8_t* sA = smem + stage * kGemmStageBytes;
                     uint8_t* sB = sA + kGemmABytes;
+                    if (p.debug & 1) {   // experiment: synchronisation only, no operand traffic
+                        mbar_arrive(&bars->full[stage]);
+                        if (++stage == kGemmStages) { stage = 0; phase ^= 1u; }
+                        continue;
+                    }
                     mbar_arrive_expect_tx(&bars->full[stage], kGemmStageBytes);   // A + my half of B + the peer's half
                     tma_load_2d(sA, &tmQ, int(kb * kGemmBK), int(qb * kGemmBM), &bars->full[stage]);
                     tma_load_2d_mc(sB + rank * (kGemmBBytes / CS), &tmXh, int(kb * kGemmBK),
@@ -645,29 +821,59 @@ gemm_topk_kernel_mc(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     if (++stage == kGemmStages) { stage = 0; phase ^= 1u; }
                 }
             }
+            if (prof) {
+                p.prof[blockIdx.x * 8 + 3] = (unsigned long long)(clock64() - t_begin);
+                p.prof[blockIdx.x * 8 + 4] = (unsigned long long)w_empty;
+            }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_bf16(kGemmBM, kGemmBN);
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            const bool prof = p.prof != nullptr;
+            long long w_full = 0, w_tempty = 0;
+            const long long t_begin = clock64();
+            unsigned long long g_begin;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_begin));
+            // Any latency this thread spends between two tcgen05.mma is a bubble in the tensor pipe
+            // (measured: a try_wait on an ALREADY complete barrier at every k-block boundary cost
+            // ~90 of every 600 cycles; the pipe reaches 100% with the wait removed).  So the barrier
+            // of the NEXT k-block (and, at a tile boundary, the next tile's drained accumulator) is
+            // only PEEKED with a non-blocking test_wait issued ahead of the current k-block's MMAs
+            // and read after them (umma_bf16_x4_peek); the blocking loop runs only if a peek failed.
+            static_assert(kGemmBK == 64, "umma_bf16_x4_peek issues exactly four K=16 MMAs");
+            uint32_t tok_full = 0, tok_acc = 0;
             for (uint32_t t = t_lo; t < t_hi; t++) {
-                mbar_wait(&bars->tempty[acc], acc_phase ^ 1u);
+                if (!tok_acc) mbar_wait_prof(&bars->tempty[acc], acc_phase ^ 1u, prof, w_tempty);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * kGemmBN;
                 for (uint32_t kb = 0; kb < n_kb; kb++) {
-                    mbar_wait(&bars->full[stage], phase);
-                    tc_fence_after();
+                    if (!tok_full && !(p.debug & 8)) mbar_wait_prof(&bars->full[stage], phase, prof, w_full);
                     const uint32_t a_addr = smem_u32(smem + stage * kGemmStageBytes);
                     const uint64_t a_desc = umma_desc_sw128(a_addr);
                     const uint64_t b_desc = umma_desc_sw128(a_addr + kGemmABytes);
-#pragma unroll
-                    for (uint32_t k = 0; k < kGemmBK / 16; k++)
-                        umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                    umma_commit_mc(&bars->empty[stage], uint16_t((1u << CS) - 1u));   // one arrival in each CTA's empty[stage]
+                    const uint32_t cur = stage;
                     if (++stage == kGemmStages) { stage = 0; phase ^= 1u; }
+                    const bool last_kb = kb + 1 == n_kb;
+                    const bool more = !(last_kb && t + 1 == t_hi);
+                    const uint32_t tok = umma_bf16_x4_peek(d_tmem, a_desc, b_desc, idesc, kb != 0 ? 1u : 0u,
+                                                           &bars->full[stage], phase, more ? 1u : 0u,
+                                                           &bars->tempty[acc ^ 1u], acc_phase ^ (acc ^ 1u),
+                                                           (more && last_kb) ? 1u : 0u);
+                    tok_full = tok & 1u;
+                    if (last_kb) tok_acc = tok >> 1;
+                    umma_commit_mc(&bars->empty[cur], uint16_t((1u << CS) - 1u));   // one arrival in each CTA's empty[cur]
                 }
                 umma_commit(&bars->tfull[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+            if (prof) {
+                p.prof[blockIdx.x * 8 + 0] = (unsigned long long)(clock64() - t_begin);
+                p.prof[blockIdx.x * 8 + 1] = (unsigned long long)w_full;
+                p.prof[blockIdx.x * 8 + 2] = (unsigned long long)w_tempty;
+                unsigned long long g_end;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_end));
+                p.prof[blockIdx.x * 8 + 7] = g_end - g_begin;
             }
         }
     } else if (warp >= 4) {
@@ -676,6 +882,9 @@ gemm_topk_kernel_mc(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         uint32_t acc = 0, acc_phase = 0;
         uint32_t cur_xt = 0xFFFFFFFFu, tile_row0 = 0;
         uint32_t adm[8];
+        const bool prof = p.prof != nullptr;
+        long long w_tfull = 0;
+        const long long t_begin = clock64();
         for (uint32_t t = t_lo; t < t_hi; t++) {
             const uint32_t xt = t / n_qb2, qb = (t % n_qb2) * CS + rank;
             if (xt != cur_xt) {
@@ -695,13 +904,17 @@ gemm_topk_kernel_mc(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 }
             }
             const int64_t q = int64_t(qb) * kGemmBM + quad * 32 + lane;
-            mbar_wait(&bars->tfull[acc], acc_phase);
+            mbar_wait_prof(&bars->tfull[acc], acc_phase, prof, w_tfull);
             tc_fence_after();
-            gemm_epilogue_tile(p, tmem_base + ((quad * 32u) << 16) + acc * kGemmBN, q, tile_row0, adm, g_lo);
+            if (!(p.debug & 2)) gemm_epilogue_tile(p, tmem_base + ((quad * 32u) << 16) + acc * kGemmBN, q, tile_row0, adm, g_lo);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->tempty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+        if (prof && warp == 4 && lane == 0) {
+            p.prof[blockIdx.x * 8 + 5] = (unsigned long long)(clock64() - t_begin);
+            p.prof[blockIdx.x * 8 + 6] = (unsigned long long)w_tfull;
         }
     }
     tc_fence_before();

@@ -391,6 +391,8 @@ struct mvdb_index {
     int batch_cost_model = 1;      // 0: every batch of >= batch_min_nq queries takes the tensor path (tests, probes)
     int gemm_l2_hint = 0;
     unsigned long long* trace_dev = nullptr;   // debug timeline of the scan kernel (option "trace")
+    int gemm_debug = 0;            // GemmParams::debug experiments (results are garbage when non-zero)
+    unsigned long long* gemm_prof_dev = nullptr;   // debug wait-cycle counters of the GEMM kernels (option "gemm_prof"), [256][8]
     int dyn_tiles = 15;            // % of the tiles the TMA scan claims from a global counter (rest: static round-robin)
     int l2_pin_mb = 0;             // head of the matrix kept L2-resident across scans (evict_last), MB
     int gemm_variant = 2;          // 0: one CTA per 128x256 tile; 1: CTA pairs (cta_group::2), 256x256 tiles;
@@ -729,6 +731,8 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
     gp.cand_cnt = ws->b_cnt;
     gp.cand_cap = kCandCap;
     gp.dense = dense_out;
+    gp.prof = ix->gemm_prof_dev;
+    gp.debug = ix->gemm_debug;
     gp.dense_ld = n;
     const uint32_t n_qb = uint32_t((nq + kGemmBM - 1) / kGemmBM);
 
@@ -1274,6 +1278,16 @@ int mvdb_index_set_option(mvdb_index* ix, const char* name, int64_t value) {
     } else if (s == "batch_mode") {
         if (value < 0 || value > 2) return fail(MVDB_ERR_ARG, "batch_mode must be 0 (off), 1 (exact) or 2 (bf16)");
         ix->batch_mode = int(value);
+    } else if (s == "gemm_debug") {
+        ix->gemm_debug = int(value);
+    } else if (s == "gemm_prof") {
+        if (value && !ix->gemm_prof_dev) {
+            CU_OK(cudaMalloc(&ix->gemm_prof_dev, 256 * 8 * 8));
+            CU_OK(cudaMemset(ix->gemm_prof_dev, 0, 256 * 8 * 8));
+        } else if (!value && ix->gemm_prof_dev) {
+            cudaFree(ix->gemm_prof_dev);
+            ix->gemm_prof_dev = nullptr;
+        }
     } else if (s == "trace") {
         DeviceGuard guard(ix->device);
         if (value && !ix->trace_dev) {
@@ -1573,9 +1587,9 @@ static int search_host_direct(mvdb_index* ix, const float* q, int64_t nq, int64_
     RC_OK(grow_pin(&ws->I_pin, &ws->I_pin_cap, out_elems));
     float* const D_dev = reinterpret_cast<float*>(ws->I_dev + on);
     const float* const D_pin = reinterpret_cast<const float*>(ws->I_pin + on);
-    memcpy(ws->q_pin, q, qn * 4);
-    CU_OK(cudaMemcpyAsync(ws->q_dev, ws->q_pin, qn * 4, cudaMemcpyHostToDevice, st));
     const uint32_t* mask_dev = nullptr;
+    const float* q_dev = ws->q_dev;
+    bool q_sent = false;
     if (handle) {
         mask_dev = handle->dev;      // already resident: no per-query upload
         mask_rows = handle->rows;
@@ -1583,17 +1597,26 @@ static int search_host_direct(mvdb_index* ix, const float* q, int64_t nq, int64_
         const uint64_t rows = std::min<uint64_t>(mask_rows, ix->ntotal.load(std::memory_order_acquire));
         mask_rows = rows;
         const size_t words = (rows + 31) / 32, bytes = (rows + 7) / 8;
-        RC_OK(grow_dev(&ws->mask_dev, &ws->mask_cap, std::max<size_t>(words, 1)));
-        RC_OK(grow_pin(&ws->mask_pin, &ws->mask_pin_cap, std::max<size_t>(words, 1)));
+        // the filter and the queries travel as ONE transfer: [mask words | pad to 128 B | q]
+        const size_t q_at = align_up(words * 4, 128) / 4;
+        RC_OK(grow_dev(&ws->mask_dev, &ws->mask_cap, q_at + qn));
+        RC_OK(grow_pin(&ws->mask_pin, &ws->mask_pin_cap, q_at + qn));
         if (words) {
             ws->mask_pin[words - 1] = 0;
             memcpy(ws->mask_pin, mask, bytes);
             if (rows & 7) reinterpret_cast<uint8_t*>(ws->mask_pin)[bytes - 1] &= uint8_t((1u << (rows & 7)) - 1u);
-            CU_OK(cudaMemcpyAsync(ws->mask_dev, ws->mask_pin, words * 4, cudaMemcpyHostToDevice, st));
         }
+        memcpy(ws->mask_pin + q_at, q, qn * 4);
+        CU_OK(cudaMemcpyAsync(ws->mask_dev, ws->mask_pin, (q_at + qn) * 4, cudaMemcpyHostToDevice, st));
         mask_dev = ws->mask_dev;
+        q_dev = reinterpret_cast<const float*>(ws->mask_dev + q_at);
+        q_sent = true;
     }
-    RC_OK(run_search(ix, ws, ws->q_dev, nq, k, mask_dev, mask_rows, normalize_queries, 0, D_dev, ws->I_dev, st, nullptr));
+    if (!q_sent) {
+        memcpy(ws->q_pin, q, qn * 4);
+        CU_OK(cudaMemcpyAsync(ws->q_dev, ws->q_pin, qn * 4, cudaMemcpyHostToDevice, st));
+    }
+    RC_OK(run_search(ix, ws, q_dev, nq, k, mask_dev, mask_rows, normalize_queries, 0, D_dev, ws->I_dev, st, nullptr));
     CU_OK(cudaMemcpyAsync(ws->I_pin, ws->I_dev, on * 12, cudaMemcpyDeviceToHost, st));
     CU_OK(cudaStreamSynchronize(st));
     memcpy(D, D_pin, on * 4);
@@ -2095,6 +2118,15 @@ int mvdb_debug_gemm_scores(mvdb_index* ix, const float* q, int64_t nq, float* ou
     cudaFree(q_dev);
     cudaFree(o_dev);
     return rc;
+}
+
+int mvdb_debug_read_gemm_prof(mvdb_index* ix, uint64_t* out, int ctas) {
+    ENTER(ix);
+    if (!out || ctas <= 0 || ctas > 256 || !ix->gemm_prof_dev)
+        return fail(MVDB_ERR_STATE, "GEMM profiling is off (set option \"gemm_prof\" = 1) or bad arguments");
+    CU_OK(cudaDeviceSynchronize());
+    CU_OK(cudaMemcpy(out, ix->gemm_prof_dev, size_t(ctas) * 8 * 8, cudaMemcpyDeviceToHost));
+    return MVDB_OK;
 }
 
 int mvdb_debug_read_trace(mvdb_index* ix, uint64_t* out16) {

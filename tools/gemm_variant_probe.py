@@ -3,13 +3,13 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import minivectordb_b200 as mv
 out = []
-for n, d, nq, k in ((2_000_000, 1024, 4096, 100), (1_000_000, 384, 4096, 10), (10_000_000, 1024, 4096, 100)):
+for n, d, nq, k in [((2_000_000, 1024, 4096, 100), (1_000_000, 384, 4096, 10), (10_000_000, 1024, 4096, 100))[int(c)] for c in os.environ.get("CASES", "0,1,2").split(",")]:
     eng = mv.FlatIPEngine(d); eng.add_synthetic(1234, 0, n, 0, True); ws = eng.workspace()
     q = torch.randn(nq, d, device="cuda"); q = q / q.norm(dim=1, keepdim=True)
     D = torch.empty(nq, k, device="cuda"); I = torch.empty(nq, k, dtype=torch.int64, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
     ref = None
-    for variant in (0, 2, 3, 2, 3):
+    for variant in [int(v) for v in os.environ.get("VARIANTS", "2,1,2,1").split(",")]:
         eng.set_option("gemm_variant", variant)
         eng.search_device(ws, q.data_ptr(), nq, k, D.data_ptr(), I.data_ptr(), stream=st); torch.cuda.synchronize()
         ts = []
