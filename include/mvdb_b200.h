@@ -83,7 +83,9 @@ int mvdb_index_reset(mvdb_index* ix);
  *   "batch_mode"    large query batches on the tensor cores: 0 off (always the
  *                   fp32 scan), 1 exact (bf16 tcgen05 GEMM selects a rigorous
  *                   candidate superset, survivors re-scored in fp32: same ids and
- *                   distances as the scan; default), 2 bf16 (scores of the bf16 GEMM)
+ *                   distances as the scan; default), 2 bf16 (scores of the bf16 GEMM), 3 tf32
+ *                   (scores of a tcgen05 kind::tf32 GEMM over the fp32 matrix itself: no shadow
+ *                   copy, 10-bit mantissa operands, half the tensor rate)
  *   "batch_min_nq"  floor on the nq routed to the batched path (default 2; above it a cost model
  *                   picks the cheaper of the fp32 scan passes and one bf16 shadow pass; k <= 128) */
 int mvdb_index_set_option(mvdb_index* ix, const char* name, int64_t value);

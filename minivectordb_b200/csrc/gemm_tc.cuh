@@ -129,81 +129,51 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
-// One k-block (4 x K=16) of single-CTA MMAs with two barrier PEEKS folded in: mbarrier.test_wait
+// One k-block (4 MMAs, 32 B of K each) with two barrier PEEKS folded in: mbarrier.test_wait
 // (non-blocking) on `peek0` / `peek1` is issued BEFORE the MMAs and its predicate is only read
 // AFTER them, so the issuing thread never sits between two tcgen05.mma waiting for shared memory.
 // Returns bit 0 = peek0 complete, bit 1 = peek1 complete (a peek that is switched off reads as 0).
-__device__ __forceinline__ uint32_t umma_bf16_x4_peek(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                                      uint32_t accumulate_first, uint64_t* peek0, uint32_t parity0,
-                                                      uint32_t do0, uint64_t* peek1, uint32_t parity1, uint32_t do1) {
-    uint32_t tok;
-    asm volatile(
-        "{\n\t.reg .pred p0, p1, pa, pt, d0, d1;\n\t"
-        ".reg .b32 t0, t1;\n\t"
-        ".reg .b64 a, b;\n\t"
-        "setp.ne.b32 d0, %8, 0;\n\t"
-        "setp.ne.b32 d1, %11, 0;\n\t"
-        "setp.ne.b32 p0, 0, 0;\n\t"
-        "setp.ne.b32 p1, 0, 0;\n\t"
-        "@d0 mbarrier.test_wait.parity.shared::cta.b64 p0, [%6], %7;\n\t"
-        "@d1 mbarrier.test_wait.parity.shared::cta.b64 p1, [%9], %10;\n\t"
-        "setp.ne.b32 pa, %5, 0;\n\t"
-        "setp.eq.b32 pt, 0, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %3, %4, pa;\n\t"
-        "add.u64 a, %2, 2;\n\t"
-        "add.u64 b, %3, 2;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, pt;\n\t"
-        "add.u64 a, %2, 4;\n\t"
-        "add.u64 b, %3, 4;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, pt;\n\t"
-        "add.u64 a, %2, 6;\n\t"
-        "add.u64 b, %3, 6;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, pt;\n\t"
-        "selp.u32 t0, 1, 0, p0;\n\t"
-        "selp.u32 t1, 2, 0, p1;\n\t"
-        "or.b32 %0, t0, t1;\n\t}"
-        : "=r"(tok)
-        : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate_first), "r"(smem_u32(peek0)), "r"(parity0),
-          "r"(do0), "r"(smem_u32(peek1)), "r"(parity1), "r"(do1)
-        : "memory");
-    return tok;
-}
-// same for a CTA pair (issued by the leader CTA only)
-__device__ __forceinline__ uint32_t umma_bf16_x4_peek_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                                      uint32_t accumulate_first, uint64_t* peek0, uint32_t parity0,
-                                                      uint32_t do0, uint64_t* peek1, uint32_t parity1, uint32_t do1) {
-    uint32_t tok;
-    asm volatile(
-        "{\n\t.reg .pred p0, p1, pa, pt, d0, d1;\n\t"
-        ".reg .b32 t0, t1;\n\t"
-        ".reg .b64 a, b;\n\t"
-        "setp.ne.b32 d0, %8, 0;\n\t"
-        "setp.ne.b32 d1, %11, 0;\n\t"
-        "setp.ne.b32 p0, 0, 0;\n\t"
-        "setp.ne.b32 p1, 0, 0;\n\t"
-        "@d0 mbarrier.test_wait.parity.shared::cta.b64 p0, [%6], %7;\n\t"
-        "@d1 mbarrier.test_wait.parity.shared::cta.b64 p1, [%9], %10;\n\t"
-        "setp.ne.b32 pa, %5, 0;\n\t"
-        "setp.eq.b32 pt, 0, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%1], %2, %3, %4, pa;\n\t"
-        "add.u64 a, %2, 2;\n\t"
-        "add.u64 b, %3, 2;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%1], a, b, %4, pt;\n\t"
-        "add.u64 a, %2, 4;\n\t"
-        "add.u64 b, %3, 4;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%1], a, b, %4, pt;\n\t"
-        "add.u64 a, %2, 6;\n\t"
-        "add.u64 b, %3, 6;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%1], a, b, %4, pt;\n\t"
-        "selp.u32 t0, 1, 0, p0;\n\t"
-        "selp.u32 t1, 2, 0, p1;\n\t"
-        "or.b32 %0, t0, t1;\n\t}"
-        : "=r"(tok)
-        : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate_first), "r"(smem_u32(peek0)), "r"(parity0),
-          "r"(do0), "r"(smem_u32(peek1)), "r"(parity1), "r"(do1)
-        : "memory");
-    return tok;
-}
+// Generated for: one CTA / bf16, CTA pair / bf16 (issued by the leader only), one CTA / tf32.
+#define MVDB_DEFINE_UMMA_X4_PEEK(NAME, GROUP, KIND)                                                                      \
+    __device__ __forceinline__ uint32_t NAME(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,          \
+                                             uint32_t accumulate_first, uint64_t* peek0, uint32_t parity0, uint32_t do0, \
+                                             uint64_t* peek1, uint32_t parity1, uint32_t do1) {                          \
+        uint32_t tok;                                                                                                    \
+        asm volatile(                                                                                                    \
+            "{\n\t.reg .pred p0, p1, pa, pt, d0, d1;\n\t"                                                                \
+            ".reg .b32 t0, t1;\n\t"                                                                                      \
+            ".reg .b64 a, b;\n\t"                                                                                        \
+            "setp.ne.b32 d0, %8, 0;\n\t"                                                                                 \
+            "setp.ne.b32 d1, %11, 0;\n\t"                                                                                \
+            "setp.ne.b32 p0, 0, 0;\n\t"                                                                                  \
+            "setp.ne.b32 p1, 0, 0;\n\t"                                                                                  \
+            "@d0 mbarrier.test_wait.parity.shared::cta.b64 p0, [%6], %7;\n\t"                                            \
+            "@d1 mbarrier.test_wait.parity.shared::cta.b64 p1, [%9], %10;\n\t"                                           \
+            "setp.ne.b32 pa, %5, 0;\n\t"                                                                                 \
+            "setp.eq.b32 pt, 0, 0;\n\t"                                                                                  \
+            "tcgen05.mma.cta_group::" GROUP ".kind::" KIND " [%1], %2, %3, %4, pa;\n\t"                                  \
+            "add.u64 a, %2, 2;\n\t"                                                                                      \
+            "add.u64 b, %3, 2;\n\t"                                                                                      \
+            "tcgen05.mma.cta_group::" GROUP ".kind::" KIND " [%1], a, b, %4, pt;\n\t"                                    \
+            "add.u64 a, %2, 4;\n\t"                                                                                      \
+            "add.u64 b, %3, 4;\n\t"                                                                                      \
+            "tcgen05.mma.cta_group::" GROUP ".kind::" KIND " [%1], a, b, %4, pt;\n\t"                                    \
+            "add.u64 a, %2, 6;\n\t"                                                                                      \
+            "add.u64 b, %3, 6;\n\t"                                                                                      \
+            "tcgen05.mma.cta_group::" GROUP ".kind::" KIND " [%1], a, b, %4, pt;\n\t"                                    \
+            "selp.u32 t0, 1, 0, p0;\n\t"                                                                                 \
+            "selp.u32 t1, 2, 0, p1;\n\t"                                                                                 \
+            "or.b32 %0, t0, t1;\n\t}"                                                                                    \
+            : "=r"(tok)                                                                                                  \
+            : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate_first), "r"(smem_u32(peek0)),            \
+              "r"(parity0), "r"(do0), "r"(smem_u32(peek1)), "r"(parity1), "r"(do1)                                       \
+            : "memory");                                                                                                 \
+        return tok;                                                                                                      \
+    }
+MVDB_DEFINE_UMMA_X4_PEEK(umma_bf16_x4_peek, "1", "f16")
+MVDB_DEFINE_UMMA_X4_PEEK(umma_bf16_x4_peek_2cta, "2", "f16")
+MVDB_DEFINE_UMMA_X4_PEEK(umma_tf32_x4_peek, "1", "tf32")
+#undef MVDB_DEFINE_UMMA_X4_PEEK
 // 32 lanes x 32 consecutive 32-bit columns: thread t of the warp receives lane (base_lane + t)
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -238,6 +208,19 @@ __device__ __forceinline__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
            | (uint32_t(N >> 3) << 17)
            | (uint32_t(M >> 4) << 24);
 }
+
+// kind::tf32: A/B are fp32 words in shared memory of which the tensor core uses the upper 19 bits
+// (sign, 8 exponent, 10 mantissa bits: truncation), K = 8 per instruction (32 B, like bf16's K = 16)
+__device__ __forceinline__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+    return (1u << 4)                 // c_format  = F32
+           | (2u << 7)               // a_format  = TF32
+           | (2u << 10)              // b_format  = TF32
+           | (uint32_t(N >> 3) << 17)
+           | (uint32_t(M >> 4) << 24);
+}
+// elements of K in one 128-byte k-block
+template <bool kTf32>
+__device__ __forceinline__ constexpr int gemm_bk() { return kTf32 ? 32 : 64; }
 
 // Epilogue of one 128 x 256 accumulator tile for the query owned by this thread (TMEM lane).
 // t_lane: TMEM address of this warp's lane quadrant and accumulator stage; tile_row0: first
@@ -354,8 +337,10 @@ struct GemmBarriers {
     uint32_t tmem_base;
 };
 
+template <bool kTf32>
 __global__ void __launch_bounds__(384, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmX, const GemmParams p) {
+    constexpr int kBK = gemm_bk<kTf32>();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(smem + kGemmStages * kGemmStageBytes);
@@ -383,7 +368,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t n_rows = p.row1 - p.row0;
     const uint32_t n_xt = (n_rows + kGemmBN - 1) / kGemmBN;
     const uint32_t n_qb = uint32_t((p.nq + kGemmBM - 1) / kGemmBM);
-    const uint32_t n_kb = uint32_t((p.d + kGemmBK - 1) / kGemmBK);
+    const uint32_t n_kb = uint32_t((p.d + kBK - 1) / kBK);
     // tile t = xt * n_qb + qb; CTA c owns the contiguous range [t_lo, t_hi): consecutive
     // tiles share the X tile (L2 reuse) and small row chunks still fill the grid.
     const uint64_t n_tiles = uint64_t(n_xt) * n_qb;
@@ -401,17 +386,17 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                         uint8_t* sA = smem + stage * kGemmStageBytes;
                         uint8_t* sB = sA + kGemmABytes;
                         mbar_arrive_expect_tx(&bars->full[stage], kGemmStageBytes);
-                        if (p.l2_hint >= 2) tma_load_2d_hint(sA, &tmQ, int(kb * kGemmBK), int(qb * kGemmBM), &bars->full[stage], keep);
-                        else tma_load_2d(sA, &tmQ, int(kb * kGemmBK), int(qb * kGemmBM), &bars->full[stage]);
-                        if (p.l2_hint >= 1) tma_load_2d_hint(sB, &tmX, int(kb * kGemmBK), int(p.row0 + xt * kGemmBN), &bars->full[stage], keep);
-                        else tma_load_2d(sB, &tmX, int(kb * kGemmBK), int(p.row0 + xt * kGemmBN), &bars->full[stage]);
+                        if (p.l2_hint >= 2) tma_load_2d_hint(sA, &tmQ, int(kb * kBK), int(qb * kGemmBM), &bars->full[stage], keep);
+                        else tma_load_2d(sA, &tmQ, int(kb * kBK), int(qb * kGemmBM), &bars->full[stage]);
+                        if (p.l2_hint >= 1) tma_load_2d_hint(sB, &tmX, int(kb * kBK), int(p.row0 + xt * kGemmBN), &bars->full[stage], keep);
+                        else tma_load_2d(sB, &tmX, int(kb * kBK), int(p.row0 + xt * kGemmBN), &bars->full[stage]);
                         if (++stage == kGemmStages) { stage = 0; phase ^= 1u; }
                     }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(kGemmBM, kGemmBN);
+            const uint32_t idesc = kTf32 ? umma_idesc_tf32(kGemmBM, kGemmBN) : umma_idesc_bf16(kGemmBM, kGemmBN);
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
             // barrier peeks folded into the MMA issue: see gemm_topk_kernel_mc
             uint32_t tok_full = 0, tok_acc = 0;
@@ -428,7 +413,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     if (++stage == kGemmStages) { stage = 0; phase ^= 1u; }
                     const bool last_kb = kb + 1 == n_kb;
                     const bool more = !(last_kb && t + 1 == t_hi);
-                    const uint32_t tok = umma_bf16_x4_peek(d_tmem, a_desc, b_desc, idesc, kb != 0 ? 1u : 0u,
+                    const uint32_t tok = (kTf32 ? umma_tf32_x4_peek : umma_bf16_x4_peek)(d_tmem, a_desc, b_desc, idesc, kb != 0 ? 1u : 0u,
                                                            &bars->full[stage], phase, more ? 1u : 0u,
                                                            &bars->tempty[acc ^ 1u], acc_phase ^ (acc ^ 1u),
                                                            (more && last_kb) ? 1u : 0u);
@@ -759,9 +744,10 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
 }
 
 // CS = cluster size (2 or 4): CS query blocks share one X tile; each CTA fetches 1/CS of it.
-template <int CS>
+template <int CS, bool kTf32>
 __global__ void __launch_bounds__(384, 1)
 gemm_topk_kernel_mc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmXh, const GemmParams p) {
+    constexpr int kBK = gemm_bk<kTf32>();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(smem + kGemmStages * kGemmStageBytes);
@@ -791,7 +777,7 @@ gemm_topk_kernel_mc(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t n_rows = p.row1 - p.row0;
     const uint32_t n_xt = (n_rows + kGemmBN - 1) / kGemmBN;
     const uint32_t n_qb2 = uint32_t((p.nq + CS * kGemmBM - 1) / (CS * kGemmBM));   // groups of CS query blocks
-    const uint32_t n_kb = uint32_t((p.d + kGemmBK - 1) / kGemmBK);
+    const uint32_t n_kb = uint32_t((p.d + kBK - 1) / kBK);
     const uint64_t n_tiles = uint64_t(n_xt) * n_qb2;
     const uint32_t n_pairs = gridDim.x / CS, pair = blockIdx.x / CS;
     const uint32_t t_lo = uint32_t(n_tiles * pair / n_pairs);
@@ -815,8 +801,8 @@ gemm_topk_kernel_mc(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                         continue;
                     }
                     mbar_arrive_expect_tx(&bars->full[stage], kGemmStageBytes);   // A + my half of B + the peer's half
-                    tma_load_2d(sA, &tmQ, int(kb * kGemmBK), int(qb * kGemmBM), &bars->full[stage]);
-                    tma_load_2d_mc(sB + rank * (kGemmBBytes / CS), &tmXh, int(kb * kGemmBK),
+                    tma_load_2d(sA, &tmQ, int(kb * kBK), int(qb * kGemmBM), &bars->full[stage]);
+                    tma_load_2d_mc(sB + rank * (kGemmBBytes / CS), &tmXh, int(kb * kBK),
                                    int(p.row0 + xt * kGemmBN + rank * (kGemmBN / CS)), &bars->full[stage], uint16_t((1u << CS) - 1u));
                     if (++stage == kGemmStages) { stage = 0; phase ^= 1u; }
                 }
@@ -828,7 +814,7 @@ gemm_topk_kernel_mc(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(kGemmBM, kGemmBN);
+            const uint32_t idesc = kTf32 ? umma_idesc_tf32(kGemmBM, kGemmBN) : umma_idesc_bf16(kGemmBM, kGemmBN);
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
             const bool prof = p.prof != nullptr;
             long long w_full = 0, w_tempty = 0;
@@ -841,7 +827,7 @@ gemm_topk_kernel_mc(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             // of the NEXT k-block (and, at a tile boundary, the next tile's drained accumulator) is
             // only PEEKED with a non-blocking test_wait issued ahead of the current k-block's MMAs
             // and read after them (umma_bf16_x4_peek); the blocking loop runs only if a peek failed.
-            static_assert(kGemmBK == 64, "umma_bf16_x4_peek issues exactly four K=16 MMAs");
+            static_assert(kGemmBK == 64, "the x4_peek helpers issue exactly four 32-byte K steps per 128-byte k-block");
             uint32_t tok_full = 0, tok_acc = 0;
             for (uint32_t t = t_lo; t < t_hi; t++) {
                 if (!tok_acc) mbar_wait_prof(&bars->tempty[acc], acc_phase ^ 1u, prof, w_tempty);
@@ -856,7 +842,7 @@ gemm_topk_kernel_mc(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     if (++stage == kGemmStages) { stage = 0; phase ^= 1u; }
                     const bool last_kb = kb + 1 == n_kb;
                     const bool more = !(last_kb && t + 1 == t_hi);
-                    const uint32_t tok = umma_bf16_x4_peek(d_tmem, a_desc, b_desc, idesc, kb != 0 ? 1u : 0u,
+                    const uint32_t tok = (kTf32 ? umma_tf32_x4_peek : umma_bf16_x4_peek)(d_tmem, a_desc, b_desc, idesc, kb != 0 ? 1u : 0u,
                                                            &bars->full[stage], phase, more ? 1u : 0u,
                                                            &bars->tempty[acc ^ 1u], acc_phase ^ (acc ^ 1u),
                                                            (more && last_kb) ? 1u : 0u);

@@ -386,7 +386,7 @@ struct mvdb_index {
     int* max_norm2_bits = nullptr;  // device: bit pattern of the largest squared row norm stored
     std::atomic<float> max_norm2_host{0.f};  // host copy, refreshed at the end of every add
     // options
-    int batch_mode = 1;            // 0 off, 1 exact (bf16 candidates + fp32 re-scoring), 2 bf16
+    int batch_mode = 1;            // 0 off, 1 exact (bf16 candidates + fp32 re-scoring), 2 bf16, 3 tf32
     int batch_min_nq = 2;
     int batch_cost_model = 1;      // 0: every batch of >= batch_min_nq queries takes the tensor path (tests, probes)
     int gemm_l2_hint = 0;
@@ -622,16 +622,19 @@ static int ws_scratch(mvdb_workspace* ws) {
 // batched tensor-core path (gemm_tc.cuh)
 // ---------------------------------------------------------------------------
 // rows x d bf16 matrix whose consecutive (sampled) rows are ld_elems elements apart
-static int encode_bf16_map(CUtensorMap* tm, const void* base, uint64_t rows, int d, int64_t ld_elems, uint32_t box_rows) {
+// tf32 = false: bf16 elements, 64 per 128-byte box row; tf32 = true: fp32 elements, 32 per box row
+static int encode_gemm_map(CUtensorMap* tm, const void* base, uint64_t rows, int d, int64_t ld_elems, uint32_t box_rows,
+                           bool tf32 = false) {
     TensorMapEncodeTiledFn enc = tensor_map_encoder();
     if (!enc) return fail(MVDB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const unsigned esize = tf32 ? 4u : 2u;
     cuuint64_t gdim[2] = {cuuint64_t(d), cuuint64_t(std::max<uint64_t>(rows, 1))};
-    cuuint64_t gstride[1] = {cuuint64_t(ld_elems) * 2};
-    cuuint32_t box[2] = {cuuint32_t(kGemmBK), box_rows};
+    cuuint64_t gstride[1] = {cuuint64_t(ld_elems) * esize};
+    cuuint32_t box[2] = {cuuint32_t(128u / esize), box_rows};
     cuuint32_t estride[2] = {1, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estride,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(tm, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base),
+                     gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(MVDB_ERR_CUDA, "cuTensorMapEncodeTiled failed: %d", int(r));
     return MVDB_OK;
 }
@@ -669,7 +672,10 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
                        const uint32_t* mask_dev, uint32_t n, int normalize_q, int64_t label_offset, float* D_dev,
                        int64_t* I_dev, cudaStream_t stream, int mode, float* dense_out,
                        const QMaskRef* qmasks = nullptr) {
-    RC_OK(ensure_shadow(ix, n));
+    // mode 1 exact (bf16 candidates + fp32 re-score), 2 bf16 scores, 3 tf32 scores (fp32 operands
+    // straight from the master matrix: no shadow copy, half the tensor rate, twice the bytes)
+    const bool tf32 = mode == 3;
+    if (!tf32) RC_OK(ensure_shadow(ix, n));
     RC_OK(grow_dev(&ws->b_qn, &ws->b_qn_cap, size_t(nq) * ix->ld));
     RC_OK(grow_dev(&ws->b_qnorm, &ws->b_qnorm_cap, size_t(nq)));
     RC_OK(grow_dev(&ws->b_q16, &ws->b_q16_cap, size_t(nq) * ix->ld16));
@@ -681,21 +687,29 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
     prep_queries_kernel<<<unsigned((nq * 32 + 255) / 256), 256, 0, stream>>>(q_dev, ws->b_qn, ws->b_qnorm, nq, ix->d, ix->ld,
                                                                             normalize_q);
     LAUNCHED();
-    to_bf16_rows_kernel<<<unsigned(std::min<int64_t>((nq * 32 + 255) / 256, 4096)), 256, 0, stream>>>(
-        ws->b_qn, ws->b_q16, uint64_t(nq), ix->d, ix->ld, ix->ld16);
-    LAUNCHED();
+    if (!tf32) {
+        to_bf16_rows_kernel<<<unsigned(std::min<int64_t>((nq * 32 + 255) / 256, 4096)), 256, 0, stream>>>(
+            ws->b_qn, ws->b_q16, uint64_t(nq), ix->d, ix->ld, ix->ld16);
+        LAUNCHED();
+    }
     init_batch_state_kernel<<<unsigned((nq + 255) / 256), 256, 0, stream>>>(ws->b_thr, ws->b_cnt, ws->b_ovf, nq);
     LAUNCHED();
 
     CUtensorMap tmQ, tmX, tmQ2, tmX2, tmX4;
-    RC_OK(encode_bf16_map(&tmQ, ws->b_q16, uint64_t(nq), ix->d, ix->ld16, kGemmBM));
+    const void* const x_base = tf32 ? ix->mat.ptr() : ix->mat16.ptr();
+    const int64_t x_ld = tf32 ? int64_t(ix->ld) : int64_t(ix->ld16);
+    const int variant = tf32 ? (ix->gemm_variant >= 2 ? 2 : 0) : ix->gemm_variant;   // tf32: single CTA or cluster-2 multicast
+    if (tf32) RC_OK(encode_gemm_map(&tmQ, ws->b_qn, uint64_t(nq), ix->d, ix->ld, kGemmBM, true));
+    else RC_OK(encode_gemm_map(&tmQ, ws->b_q16, uint64_t(nq), ix->d, ix->ld16, kGemmBM));
     tmQ2 = tmQ;   // the pair kernel loads 128-query boxes too
     tmX2 = tmQ;
     tmX4 = tmQ;
-    CU_OK(cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes)));
+    CU_OK(cudaFuncSetAttribute(gemm_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes)));
+    CU_OK(cudaFuncSetAttribute(gemm_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes)));
     CU_OK(cudaFuncSetAttribute(gemm_topk_kernel_2cta, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemm2SmemBytes)));
-    CU_OK(cudaFuncSetAttribute(gemm_topk_kernel_mc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes)));
-    CU_OK(cudaFuncSetAttribute(gemm_topk_kernel_mc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes)));
+    CU_OK(cudaFuncSetAttribute(gemm_topk_kernel_mc<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes)));
+    CU_OK(cudaFuncSetAttribute(gemm_topk_kernel_mc<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes)));
+    CU_OK(cudaFuncSetAttribute(gemm_topk_kernel_mc<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes)));
     CU_OK(cudaFuncSetAttribute(cand_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kCandCap * 8)));
 
     // rigorous bound on |bf16 score - fp32 score| per unit |q|: inputs rounded to nearest
@@ -768,9 +782,9 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
         const uint32_t S = strides[lv];
         const uint32_t m = uint32_t((uint64_t(n) + S - 1) / S);   // sampled rows of this level
         const uint32_t words = (m + 31) / 32;
-        RC_OK(encode_bf16_map(&tmX, ix->mat16.ptr(), m, ix->d, ix->ld16 * int64_t(S), kGemmBN));
-        if (ix->gemm_variant >= 1) RC_OK(encode_bf16_map(&tmX2, ix->mat16.ptr(), m, ix->d, ix->ld16 * int64_t(S), kGemmBN / 2));
-        if (ix->gemm_variant == 3) RC_OK(encode_bf16_map(&tmX4, ix->mat16.ptr(), m, ix->d, ix->ld16 * int64_t(S), kGemmBN / 4));
+        RC_OK(encode_gemm_map(&tmX, x_base, m, ix->d, x_ld * int64_t(S), kGemmBN, tf32));
+        if (variant >= 1) RC_OK(encode_gemm_map(&tmX2, x_base, m, ix->d, x_ld * int64_t(S), kGemmBN / 2, tf32));
+        if (variant == 3) RC_OK(encode_gemm_map(&tmX4, x_base, m, ix->d, x_ld * int64_t(S), kGemmBN / 4, tf32));
         gp.row_stride = S;
         gp.row0 = 0;
         gp.row1 = uint32_t(align_up(m, kGemmBN));
@@ -821,9 +835,9 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
         for (uint32_t hi : cuts) {
             gp.row0 = lo;
             gp.row1 = hi;
-            if (ix->gemm_variant >= 2 && nq > kGemmBM) {
+            if (variant >= 2 && nq > kGemmBM) {
                 // clusters of CS CTAs share one X tile through TMA multicast (CS query blocks at once)
-                const int cs = (ix->gemm_variant == 3 && nq > 2 * kGemmBM) ? 4 : 2;
+                const int cs = (variant == 3 && nq > 2 * kGemmBM) ? 4 : 2;
                 const uint64_t tiles2 = uint64_t((hi - lo) / kGemmBN) * ((nq + cs * kGemmBM - 1) / (cs * kGemmBM));
                 const unsigned clusters = unsigned(std::min<uint64_t>(uint64_t(ix->sm_count / cs), tiles2));
                 cudaLaunchConfig_t cfg = {};
@@ -838,9 +852,10 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
                 attr[0].val.clusterDim.z = 1;
                 cfg.attrs = attr;
                 cfg.numAttrs = 1;
-                if (cs == 4) CU_OK(cudaLaunchKernelEx(&cfg, gemm_topk_kernel_mc<4>, tmQ2, tmX4, gp));
-                else CU_OK(cudaLaunchKernelEx(&cfg, gemm_topk_kernel_mc<2>, tmQ2, tmX2, gp));
-            } else if (ix->gemm_variant == 1 && nq > kGemmBM) {
+                if (cs == 4) CU_OK(cudaLaunchKernelEx(&cfg, gemm_topk_kernel_mc<4, false>, tmQ2, tmX4, gp));
+                else if (tf32) CU_OK(cudaLaunchKernelEx(&cfg, gemm_topk_kernel_mc<2, true>, tmQ2, tmX2, gp));
+                else CU_OK(cudaLaunchKernelEx(&cfg, gemm_topk_kernel_mc<2, false>, tmQ2, tmX2, gp));
+            } else if (variant == 1 && nq > kGemmBM) {
                 // CTA pairs: 256-query x 256-row tiles, B operand split across the pair
                 const uint64_t tiles2 = uint64_t((hi - lo) / kGemmBN) * ((nq + 2 * kGemmBM - 1) / (2 * kGemmBM));
                 const unsigned pairs = unsigned(std::min<uint64_t>(uint64_t(ix->sm_count / 2), tiles2));
@@ -848,7 +863,8 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
             } else {
                 const uint64_t tiles = uint64_t((hi - lo) / kGemmBN) * n_qb;
                 const unsigned grid = unsigned(std::min<uint64_t>(uint64_t(ix->sm_count), tiles));
-                gemm_topk_kernel<<<grid, 384, kGemmSmemBytes, stream>>>(tmQ, tmX, gp);
+                if (tf32) gemm_topk_kernel<true><<<grid, 384, kGemmSmemBytes, stream>>>(tmQ, tmX, gp);
+                else gemm_topk_kernel<false><<<grid, 384, kGemmSmemBytes, stream>>>(tmQ, tmX, gp);
             }
             LAUNCHED();
             if (!dense_out) {
@@ -945,7 +961,11 @@ static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, in
             t_scan += 40e-6 + f * bytes32 / 6.4e12;
             rem -= g;
         }
-        const double t_tc = 330e-6 + 1.07 * (bytes32 * 0.5) / 6.0e12 + 2.0 * double(nq) * double(n) * double(ix->d) / 900e12;
+        // one pass over the bf16 shadow at ~900 TFLOP/s effective -- or, in tf32 mode, over the
+        // fp32 matrix itself at half the tensor rate
+        const bool tf32 = ix->batch_mode == 3;
+        const double t_tc = 330e-6 + 1.07 * (bytes32 * (tf32 ? 1.0 : 0.5)) / 6.0e12 +
+                            2.0 * double(nq) * double(n) * double(ix->d) / (tf32 ? 450e12 : 900e12);
         use_tc = nq >= ix->batch_min_nq && (ix->batch_cost_model ? (nq >= 2 && t_tc < t_scan) : true);
     }
     if (!xch && !tl_force_scan && ix->batch_mode != 0 && use_tc && k <= 128 &&
@@ -1276,7 +1296,7 @@ int mvdb_index_set_option(mvdb_index* ix, const char* name, int64_t value) {
         if (value < 1 || value > 1024) return fail(MVDB_ERR_ARG, "coalesce_max must be 1..1024");
         ix->coalesce_max = int(value);
     } else if (s == "batch_mode") {
-        if (value < 0 || value > 2) return fail(MVDB_ERR_ARG, "batch_mode must be 0 (off), 1 (exact) or 2 (bf16)");
+        if (value < 0 || value > 3) return fail(MVDB_ERR_ARG, "batch_mode must be 0 (off), 1 (exact), 2 (bf16) or 3 (tf32)");
         ix->batch_mode = int(value);
     } else if (s == "gemm_debug") {
         ix->gemm_debug = int(value);

@@ -89,6 +89,38 @@ def test_batched_bf16_mode_recall(mv):
     eng.close()
 
 
+@pytest.mark.parametrize("n,d,nq,k", [(100_000, 384, 256, 10), (40_000, 1000, 130, 100), (9_000, 72, 64, 10)])
+def test_batched_tf32_mode(mv, n, d, nq, k):
+    """batch_mode 3: tcgen05 kind::tf32 over the fp32 matrix itself (no bf16 shadow).  Operands are
+    truncated to 10 mantissa bits, so |score - exact| <= 2 * 2^-10 * |q||x| (+ fp32 accumulation) --
+    a systematic shrink of the score rather than noise, which is why recall stays above bf16's;
+    recall against the fp32 oracle, with tombstones and a filter mask applied."""
+    x, q = _data(n, d, nq, seed=n % 97)
+    eng = mv.FlatIPEngine(d)
+    eng.set_option("batch_cost_model", 0)
+    eng.add(x)
+    eng.set_option("batch_mode", 3)
+    D, I = eng.search(q, k)
+    Dr, Ir = O.search_flat_ip(x, q, k)
+    recall = np.mean([len(set(I[i]) & set(Ir[i])) / k for i in range(nq)])
+    assert recall > 0.97, recall
+    assert np.all(np.diff(D, axis=1) <= 0)
+    exact = np.einsum("qkd,qd->qk", x[I].astype(np.float64), q.astype(np.float64))
+    assert np.abs(D - exact).max() < 2.2e-3          # of the rows it DID return
+    # masks and tombstones
+    eng.set_option("batch_mode", 3)
+    eng.remove_rows(np.arange(5, n, 9))
+    live = np.ones(n, dtype=bool)
+    live[np.arange(5, n, 9)] = False
+    adm = np.random.default_rng(4).random(n) < 0.4
+    D, I = eng.search(q, k, mask=adm)
+    assert np.all(I >= 0) and np.all((adm & live)[I])
+    Dr, Ir = O.search_masked(x, adm & live, q, k)
+    recall = np.mean([len(set(I[i]) & set(Ir[i])) / k for i in range(nq)])
+    assert recall > 0.97, recall
+    eng.close()
+
+
 def test_batched_overflow_falls_back_to_the_scan(mv):
     """Rows ordered by INCREASING similarity to a query make every row beat the
     running threshold: the candidate list overflows and that query is redone by
