@@ -77,6 +77,12 @@ int mvdb_index_reset(mvdb_index* ix);
  *   "scan_variant"  MVDB_SCAN_*          "fused_k_max"  largest k served by the fused select
  *   "grid_ctas"     CTAs of the scan kernel (0 = one per SM)
  *   "consumer_warps" consumer warps per CTA of the TMA scan (0 = auto)
+ *   "pdl"           (default 0) launch the scans of mvdb_index_search_device / _search_exchange
+ *                   with programmatic stream serialization: searches enqueued back to back on
+ *                   one stream overlap the serial tail of one (last-CTA merge, cross-GPU
+ *                   exchange) with the scan of the next.  Results are unchanged.  Contract while
+ *                   on: q_dev / mask_dev of a search must not be written by a KERNEL that
+ *                   immediately precedes it on the same stream (copies and events are fine)
  *   "dyn_tiles"     percentage (0..100, default 15) of the tiles the TMA scan claims from a
  *                   global counter instead of the static round-robin split, to level the
  *                   finishing times of the SMs; results are identical for every value

@@ -38,6 +38,7 @@ using namespace mvdb;
 // errors
 // ---------------------------------------------------------------------------
 static thread_local std::string g_err;
+static thread_local bool tl_allow_pdl = false;    // set by the device-buffer entry points (option "pdl")
 static thread_local bool tl_force_scan = false;   // overflow fallback of the batched path: stay on the fp32 scan
 static std::atomic<uint64_t> g_launches{0};
 
@@ -279,6 +280,8 @@ struct mvdb_workspace {
     uint64_t* partials = nullptr;
     size_t partials_cap = 0;
     unsigned int* ticket = nullptr;
+    unsigned int launch_seq = 0;   // parity selects the tile counter of a scan launch
+    bool prev_scan_big = false;    // the previous launch on this workspace was a one-CTA-per-SM scan (see "pdl")
     uint32_t* all_ord = nullptr;
     size_t all_ord_cap = 0;
     RadixState* radix = nullptr;
@@ -366,6 +369,7 @@ struct mvdb_index {
     int ld4 = 0;
     int sm_count = 0;
     size_t smem_optin = 0;
+    size_t smem_per_sm = 0;
     GrowBuf mat, live;
     std::vector<uint32_t> live_host;  // mirror of the device bitmask
     std::atomic<uint64_t> ntotal{0};
@@ -393,6 +397,7 @@ struct mvdb_index {
     unsigned long long* trace_dev = nullptr;   // debug timeline of the scan kernel (option "trace")
     int gemm_debug = 0;            // GemmParams::debug experiments (results are garbage when non-zero)
     unsigned long long* gemm_prof_dev = nullptr;   // debug wait-cycle counters of the GEMM kernels (option "gemm_prof"), [256][8]
+    int pdl = 0;                   // search_device: programmatic dependent launch of back-to-back scans (opt-in)
     int dyn_tiles = 15;            // % of the tiles the TMA scan claims from a global counter (rest: static round-robin)
     int l2_pin_mb = 0;             // head of the matrix kept L2-resident across scans (evict_last), MB
     int gemm_variant = 2;          // 0: one CTA per 128x256 tile; 1: CTA pairs (cta_group::2), 256x256 tiles;
@@ -610,9 +615,9 @@ __global__ void fill_empty_results_kernel(float* D, int64_t* I, int64_t total) {
 
 static int ws_scratch(mvdb_workspace* ws) {
     if (!ws->ticket) {
-        // ticket at +0, the dynamic scheduler's tile counter at +128 (its own L2 line)
-        CU_OK(cudaMalloc(&ws->ticket, 256));
-        CU_OK(cudaMemset(ws->ticket, 0, 256));
+        // ticket at +0, the dynamic scheduler's two tile counters at +128 and +256 (own L2 lines)
+        CU_OK(cudaMalloc(&ws->ticket, 512));
+        CU_OK(cudaMemset(ws->ticket, 0, 512));
     }
     return MVDB_OK;
 }
@@ -675,6 +680,7 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
     // mode 1 exact (bf16 candidates + fp32 re-score), 2 bf16 scores, 3 tf32 scores (fp32 operands
     // straight from the master matrix: no shadow copy, half the tensor rate, twice the bytes)
     const bool tf32 = mode == 3;
+    ws->prev_scan_big = false;
     if (!tf32) RC_OK(ensure_shadow(ix, n));
     RC_OK(grow_dev(&ws->b_qn, &ws->b_qn_cap, size_t(nq) * ix->ld));
     RC_OK(grow_dev(&ws->b_qnorm, &ws->b_qnorm_cap, size_t(nq)));
@@ -1038,9 +1044,33 @@ static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, in
                 if (plan.grid & 3) st &= ~3u;
                 p.static_iters = st;
                 p.dyn_tile0 = st * uint32_t(plan.grid);
-                p.tile_ctr = ws->ticket + 32;
+                // two counters, alternating per launch: with "pdl" the next scan claims tiles while this one is still finishing
+                p.tile_ctr = ws->ticket + 32 + 32 * (ws->launch_seq++ & 1u);
             }
-            plan.fn<<<plan.grid, plan.threads, plan.smem, stream>>>(p);
+            p.pdl_early = 0;
+            if (ix->pdl && tl_allow_pdl) {
+                // Entry trigger only when this launch AND the previous scan of this workspace fill every SM
+                // with one CTA each: then a CTA of this grid can only start where the previous grid has left,
+                // all of them have started only once the previous grid is complete, and the grid after this
+                // one (which waits for all of ours to start) cannot overlap the previous one.
+                const bool big = 2 * plan.smem + 2048 > size_t(ix->smem_per_sm) && plan.grid >= ix->sm_count;
+                p.pdl_early = (big && ws->prev_scan_big) ? 1u : 0u;
+                ws->prev_scan_big = big;
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(unsigned(plan.grid));
+                cfg.blockDim = dim3(unsigned(plan.threads));
+                cfg.dynamicSmemBytes = plan.smem;
+                cfg.stream = stream;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                attr[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = attr;
+                cfg.numAttrs = 1;
+                CU_OK(cudaLaunchKernelEx(&cfg, plan.fn, p));
+            } else {
+                ws->prev_scan_big = false;
+                plan.fn<<<plan.grid, plan.threads, plan.smem, stream>>>(p);
+            }
             LAUNCHED();
             CU_OK(cudaGetLastError());
             done += g;
@@ -1057,6 +1087,7 @@ static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, in
     RC_OK(grow_dev(&ws->keys, &ws->keys_cap, size_t(npad)));
     p.k = 1;
     const int hist_grid = int(std::min<uint64_t>(uint64_t(ix->sm_count) * 4, (uint64_t(n) + 511) / 512));
+    ws->prev_scan_big = false;
     for (int64_t qi = 0; qi < nq; qi++) {
         ScanPlan plan;
         RC_OK(plan_scan(ix, p, 1, &plan));
@@ -1218,6 +1249,7 @@ int mvdb_index_create(int d, int device, uint64_t capacity_hint, mvdb_index** ou
     ix->ld4 = int(ix->ld / 4);
     ix->sm_count = prop.multiProcessorCount;
     ix->smem_optin = prop.sharedMemPerBlockOptin;
+    ix->smem_per_sm = prop.sharedMemPerMultiprocessor;
     if (const char* sl = getenv("MVDB_SMEM_SLACK")) ix->smem_optin -= size_t(atoi(sl));
     size_t free_b = 0, total_b = 0;
     CU_OK(cudaMemGetInfo(&free_b, &total_b));
@@ -1317,6 +1349,8 @@ int mvdb_index_set_option(mvdb_index* ix, const char* name, int64_t value) {
             cudaFree(ix->trace_dev);
             ix->trace_dev = nullptr;
         }
+    } else if (s == "pdl") {
+        ix->pdl = value != 0;
     } else if (s == "dyn_tiles") {
         if (value < 0 || value > 100) return fail(MVDB_ERR_ARG, "dyn_tiles is a percentage, 0..100");
         ix->dyn_tiles = int(value);
@@ -1581,8 +1615,11 @@ int mvdb_index_search_device(mvdb_index* ix, mvdb_workspace* ws, const float* q_
     if (nq < 0 || k <= 0) return fail(MVDB_ERR_ARG, "need nq >= 0 and k > 0 (got nq=%lld k=%lld)", (long long)nq, (long long)k);
     if (nq && (!q_dev || !D_dev || !I_dev)) return fail(MVDB_ERR_ARG, "null buffer");
     std::shared_lock<std::shared_mutex> mv(ix->move_mu);
-    return run_search(ix, ws, q_dev, nq, k, mask_dev, mask_rows, normalize_queries, label_offset, D_dev, I_dev,
-                      static_cast<cudaStream_t>(stream), nullptr);
+    tl_allow_pdl = true;
+    const int rc = run_search(ix, ws, q_dev, nq, k, mask_dev, mask_rows, normalize_queries, label_offset, D_dev, I_dev,
+                              static_cast<cudaStream_t>(stream), nullptr);
+    tl_allow_pdl = false;
+    return rc;
 }
 
 // One host-buffer search on its own workspace: stage query (+mask), run, copy results back.
@@ -2102,8 +2139,11 @@ int mvdb_index_search_exchange(mvdb_index* ix, mvdb_workspace* ws, mvdb_exchange
     if (nq < 0 || k <= 0) return fail(MVDB_ERR_ARG, "need nq >= 0 and k > 0 (got nq=%lld k=%lld)", (long long)nq, (long long)k);
     if (nq && (!q_dev || !D_dev || !I_dev)) return fail(MVDB_ERR_ARG, "null buffer");
     std::shared_lock<std::shared_mutex> mv(ix->move_mu);
-    return run_search(ix, ws, q_dev, nq, k, mask_dev, mask_rows, normalize_queries, 0, D_dev, I_dev,
-                      static_cast<cudaStream_t>(stream), x);
+    tl_allow_pdl = true;
+    const int rc = run_search(ix, ws, q_dev, nq, k, mask_dev, mask_rows, normalize_queries, 0, D_dev, I_dev,
+                              static_cast<cudaStream_t>(stream), x);
+    tl_allow_pdl = false;
+    return rc;
 }
 
 int mvdb_debug_gemm_scores(mvdb_index* ix, const float* q, int64_t nq, float* out) {

@@ -37,6 +37,7 @@ struct ScanParams {
     uint64_t* partials;    // [nq][gridDim.x][k] keys
     unsigned int* ticket;  // zero before launch; reset by the last CTA
     unsigned int* tile_ctr;  // dynamic tile scheduler (NULL = static round-robin); zero before launch, reset by the last CTA
+    uint32_t pdl_early;      // trigger the dependent launch at kernel entry (only when one CTA fills an SM)
     uint32_t static_iters;   // ... iterations of every CTA served by the static round-robin first
     uint32_t dyn_tile0;      // ... first tile of the dynamically claimed remainder (= static_iters * grid, multiple of kDynChunk)
     float* outD;           // [nq][k]
@@ -224,6 +225,25 @@ __device__ __forceinline__ void trace_stamp(const ScanParams& p, int slot, int c
     }
 }
 
+// Programmatic dependent launch (opt-in, option "pdl"): when two searches are enqueued back to
+// back on one stream, the second starts scanning as soon as every CTA of the first has finished
+// ITS scan, so the first one's serial tail (CTA merges, last-CTA merge, cross-GPU exchange) runs
+// under the second one's scan.  Everything a scan shares with its predecessor -- partial lists,
+// ticket, result buffers, exchange slots -- is touched only AFTER pdl_wait(), which returns once
+// the previous grid has completed and its writes are visible.  The trigger comes after the wait,
+// so grid N+2 cannot start before grid N is complete: at most two grids are in flight, and the
+// only state used before the wait (the dynamic tile counter) alternates between two slots.
+// When a CTA needs more than half an SM's shared memory (pdl_early; d >= ~256) the trigger moves
+// to kernel entry: a CTA of N+1 can then only be placed on an SM that a CTA of N has LEFT, N+2
+// only where N+1 has left -- i.e. after N completed -- so the same two-grid bound holds and N+1's
+// scan also overlaps N's straggling scans and the launch latency (100 k x 512: 56 -> 47.5 us).
+// With smaller CTAs an entry trigger lets N+2 run next to N+1 while N still runs, and N+2 then
+// claims tiles from the counter N is about to reset (caught by
+// test_programmatic_dependent_launch_is_result_neutral); those launches trigger after the wait.
+// Both instructions are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void finish_scan(const ScanParams& p, uint8_t* smem_base, SmemHeader* hdr,
                                             uint64_t* selbuf, int cw, int ncw, int lane, int bar_id,
                                             int bar_threads) {
@@ -231,6 +251,8 @@ __device__ __forceinline__ void finish_scan(const ScanParams& p, uint8_t* smem_b
     const int G = gridDim.x;
     named_bar_sync(bar_id, bar_threads);
     if (blockIdx.x == 0) trace_stamp(p, 3, cw, lane);
+    pdl_wait();   // the previous search on this stream is complete: shared scratch and outputs are ours
+    if (!p.pdl_early) pdl_launch_dependents();   // ... and once EVERY CTA is here, the next search may start scanning
     // ---- CTA merge: warp (qi % ncw) owns query qi -------------------------
     for (int qi = cw; qi < nq; qi += ncw) {
         WarpSelect m = merge_cta_lists(hdr, selbuf, nq, qi, cw, ncw, cap, k, lane);
@@ -468,6 +490,7 @@ __global__ void __launch_bounds__(kTma ? 288 : 256, kTma ? 1 : 2) scan_q1_kernel
     const int ncw = (blockDim.x >> 5) - (kTma ? 1 : 0);
     const int cw = warp - (kTma ? 1 : 0);
     const uint32_t G = gridDim.x;
+    if (p.pdl_early) pdl_launch_dependents();   // one CTA per SM: the next search may take over every SM we leave
     const uint32_t T = (p.n + kRowsPerTile - 1) / kRowsPerTile;
     const uint32_t iters = (T > blockIdx.x) ? (T - blockIdx.x + G - 1) / G : 0;
     const int S = p.stages;
@@ -583,6 +606,7 @@ __global__ void __launch_bounds__(kTma ? 288 : 256, (kTma || NQ >= 8) ? 1 : 2) s
     const int ncw = (blockDim.x >> 5) - (kTma ? 1 : 0);
     const int cw = warp - (kTma ? 1 : 0);
     const uint32_t G = gridDim.x;
+    if (p.pdl_early) pdl_launch_dependents();   // one CTA per SM: the next search may take over every SM we leave
     const uint32_t T = (p.n + kRowsPerTile - 1) / kRowsPerTile;
     const uint32_t iters = (T > blockIdx.x) ? (T - blockIdx.x + G - 1) / G : 0;
     const int S = p.stages;

@@ -383,6 +383,65 @@ def test_dynamic_tile_schedule_is_result_neutral(mv, n, d, grid):
     eng.close()
 
 
+@pytest.mark.parametrize("n,d", [(3_000, 64), (40_000, 384), (150_000, 512), (20_000, 1024)])
+def test_programmatic_dependent_launch_is_result_neutral(mv, n, d):
+    """Option "pdl": searches enqueued back to back on one stream overlap (the next scan starts while
+    the previous one is still merging).  A shuffled mix of launches -- 1/2/4 queries, k = 10 and 100
+    (different kernels, shared-memory footprints and trigger points), with a filter mask, three
+    rounds without any synchronisation in between -- must return exactly what plain stream order
+    returns and match the oracle; and when every search writes the SAME output slot the last one
+    enqueued must be the one that stays."""
+    import torch
+    eng = mv.FlatIPEngine(d)
+    eng.add_synthetic(31, 0, n, dist=0, normalize=True)
+    eng.set_option("batch_mode", 0)
+    x = O.synth_rows(31, 0, n, d)
+    O.normalize_L2(x)
+    adm = np.random.default_rng(5).random(n) < 0.5
+    packed = np.zeros((n + 31) // 32 * 4, dtype=np.uint8)
+    pk = mv.pack_mask(adm)
+    packed[:pk.size] = pk
+    m_dev = torch.from_numpy(packed.view(np.int32)).cuda()
+    NQ = 48
+    qh = O.synth_rows(32, 0, NQ, d)
+    O.normalize_L2(qh)
+    q = torch.from_numpy(qh).cuda()
+    ws = eng.workspace()
+    st = torch.cuda.current_stream().cuda_stream
+    jobs = [(k, nq, i) for k in (10, 100) for nq in (1, 2, 4) for i in range(0, NQ, nq)]
+    np.random.default_rng(9).shuffle(jobs)
+    res = {}
+    for pdl in (0, 1):
+        eng.set_option("pdl", pdl)
+        out = {(k, nq): (torch.empty(NQ, k, device="cuda"), torch.empty(NQ, k, dtype=torch.int64, device="cuda"))
+               for k in (10, 100) for nq in (1, 2, 4)}
+        for rep in range(3):
+            for k, nq, i in jobs:
+                D, I = out[(k, nq)]
+                eng.search_device(ws, q[i:i + nq].data_ptr(), nq, k, D[i:i + nq].data_ptr(), I[i:i + nq].data_ptr(),
+                                  m_dev.data_ptr(), n, stream=st)
+        torch.cuda.synchronize()
+        res[pdl] = {key: (D.cpu().numpy(), I.cpu().numpy()) for key, (D, I) in out.items()}
+        # every search of one shape into ONE slot
+        for k, nq in ((10, 1), (100, 2)):
+            D1 = torch.empty(nq, k, device="cuda")
+            I1 = torch.empty(nq, k, dtype=torch.int64, device="cuda")
+            for i in range(0, NQ, nq):
+                eng.search_device(ws, q[i:i + nq].data_ptr(), nq, k, D1.data_ptr(), I1.data_ptr(), m_dev.data_ptr(), n, stream=st)
+            torch.cuda.synchronize()
+            assert np.array_equal(I1.cpu().numpy(), res[pdl][(k, nq)][1][NQ - nq:])
+            assert np.array_equal(D1.cpu().numpy(), res[pdl][(k, nq)][0][NQ - nq:])
+    for key in res[0]:
+        assert np.array_equal(res[0][key][1], res[1][key][1]) and np.array_equal(res[0][key][0], res[1][key][0]), key
+    for k in (10, 100):
+        Dr, Ir = O.search_masked(x, adm, qh, k)
+        rep_ = O.classify_parity(x, qh, res[1][(k, 1)][1], res[1][(k, 1)][0], Ir, Dr, rel_tol=REL_TOL, admissible=adm)
+        assert rep_["ok"], rep_
+    eng.set_option("pdl", 0)
+    del ws
+    eng.close()
+
+
 def test_coalesced_concurrent_searches_equal_direct_ones(mv):
     """Concurrent single-query calls are coalesced into shared passes (<= 8 per scan launch with
     per-query filters, tensor-core batch when unfiltered); every caller must get exactly what a
