@@ -249,22 +249,16 @@ def run_b200(args):
     # every step copies the query (d*4 B) and the packed filter (n/8 B) H2D and
     # the (D, I) result D2H inside the timed region.
     e2e_lat = []
-    if world > 1:
-        q_pin = torch.from_numpy(q_host).pin_memory()
-        m_pin = torch.from_numpy(words.view(np.int32)).pin_memory()
-        q_e2e = torch.empty((1, d), dtype=torch.float32, device="cuda")
-        m_e2e = torch.empty_like(mask_dev)
 
     def e2e_step(i):
         if world == 1:
             if args.no_filter:
                 return eng.search(q_host[i:i + 1], k)
             return eng.search(q_host[i:i + 1], k, mask=packed, mask_rows=n)
-        q_e2e.copy_(q_pin[i:i + 1], non_blocking=True)
-        if not args.no_filter:
-            m_e2e.copy_(m_pin, non_blocking=True)
-        D_t, I_t = step(i, q_e2e, m_e2e)
-        return D_t.cpu(), I_t.cpu()
+        # one pinned H2D ([filter words | query]), scan + fused exchange + merge, one D2H ([labels | distances])
+        if args.no_filter:
+            return index.search_packed(q_host[i:i + 1], k)
+        return index.search_packed(q_host[i:i + 1], k, words, n)
 
     for i in range(W):
         e2e_step(i)
@@ -306,7 +300,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": k * 12, "p50_latency_us": float(np.median(e2e_lat) * 1e6),
                     "qps_global": K / e2e_total,
                     "api": ("mvdb_index_search (C ABI, host buffers; H2D query+mask, D2H results inside)" if world == 1 else
-                            "pinned H2D query+mask -> RowShardedIndex.search_device (scan + exchange + merge) -> D2H")},
+                            "RowShardedIndex.search_packed: one pinned H2D (mask+query) -> scan + exchange + merge -> one D2H")},
             "gpu_launches": int(launches),
             "clocks": clk,
         }

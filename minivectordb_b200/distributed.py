@@ -64,6 +64,7 @@ class RowShardedIndex:
         self.offsets = [0] * self.world
         self.ntotal_global = 0
         self._bufs = {}
+        self._stage = {}
         self._xchg = None
         self.exchange = "none" if self.world == 1 else "nccl"
         if self.on_gpu and self.world > 1 and exchange in ("auto", "fused"):
@@ -138,9 +139,14 @@ class RowShardedIndex:
                 I_loc=torch.empty((nq, k), dtype=torch.int64, device=self._tdev),
                 D_parts=torch.empty((self.world, nq, k), dtype=torch.float32, device=self._tdev),
                 I_parts=torch.empty((self.world, nq, k), dtype=torch.int64, device=self._tdev),
-                D_out=torch.empty((nq, k), dtype=torch.float32, device=self._tdev),
-                I_out=torch.empty((nq, k), dtype=torch.int64, device=self._tdev),
             )
+            # results live in ONE buffer ([labels | distances]) so that a host caller needs one D2H transfer
+            on = nq * k
+            t["out"] = torch.empty(on + (on + 1) // 2, dtype=torch.int64, device=self._tdev)
+            t["I_out"] = t["out"][:on].view(nq, k)
+            t["D_out"] = t["out"][on:].view(torch.float32)[:on].view(nq, k)
+            if self.on_gpu:
+                t["out_pin"] = torch.empty_like(t["out"], device="cpu").pin_memory()
             self._bufs[key] = t
         return self._bufs[key]
 
@@ -198,6 +204,41 @@ class RowShardedIndex:
         dist.all_gather_into_tensor(b["D_parts"].view(-1), torch.from_numpy(D).contiguous().view(-1), group=self.group)
         dist.all_gather_into_tensor(b["I_parts"].view(-1), torch.from_numpy(I).contiguous().view(-1), group=self.group)
         return self._host_merge(b["D_parts"].numpy(), b["I_parts"].numpy(), k)
+
+    def search_packed(self, q, k: int, mask_words: Optional[np.ndarray] = None, mask_rows: int = 0,
+                      normalize: bool = False):
+        """Host-buffer search with the fewest transfers: the packed filter of THIS rank's shard
+        (uint8/int32 little-endian bit words, bit r = row r admissible, as `pack_mask` + zero padding to
+        whole 32-bit words) and the query travel H2D as one pinned transfer, (labels, distances) come
+        back as one.  Same query on every rank.  Returns numpy (D, I) with global row numbers."""
+        q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, self.d)
+        nq = q.shape[0]
+        if not self.on_gpu:
+            raise RuntimeError("search_packed needs the GPU engine")
+        nw = 0
+        if mask_words is not None:
+            mw = np.ascontiguousarray(mask_words).view(np.int32).reshape(-1)
+            nw = mw.shape[0]
+        q_at = (nw + 31) // 32 * 32                      # query starts on a 128-byte boundary
+        need = q_at + nq * self.d
+        st = self._stage.get(need)
+        if st is None:
+            st = (torch.empty(need, dtype=torch.int32).pin_memory(), torch.empty(need, dtype=torch.int32, device=self._tdev))
+            self._stage[need] = st
+        pin, dev = st
+        ph = pin.numpy()
+        if nw:
+            ph[:nw] = mw
+        ph[q_at:need] = q.view(np.int32).reshape(-1)
+        dev.copy_(pin, non_blocking=True)
+        qd = dev[q_at:need].view(torch.float32).view(nq, self.d)
+        D, I = self.search_device(qd, k, dev[:nw] if nw else None, mask_rows if nw else 0, normalize)
+        b = self._buffers(nq, k)
+        b["out_pin"].copy_(b["out"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        on = nq * k
+        host = b["out_pin"].numpy()
+        return host[on:].view(np.float32)[:on].reshape(nq, k).copy(), host[:on].reshape(nq, k).copy()
 
     def exchange_timed_out(self) -> bool:
         if self._xchg is None:

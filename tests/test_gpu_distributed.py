@@ -46,6 +46,22 @@ def _run_transport(rank, world, transport):
     Dr, Ir = O.search_masked(x, only0, q11, k)
     rep = O.classify_parity(x, q11, I, D, Ir, Dr, admissible=only0)
     assert rep["ok"], (transport, rep)
+    # host-buffer fast path (one H2D, one D2H) and pipelined launches (option "pdl") give the same answers
+    import minivectordb_b200 as mv
+    loc = adm[bounds[rank]:bounds[rank + 1]]
+    words = np.zeros((loc.size + 31) // 32 * 4, dtype=np.uint8)
+    pk = mv.pack_mask(loc)
+    words[:pk.size] = pk
+    Dm, Im = idx.search(q, k, mask_local=loc)
+    for pdl in (0, 1):
+        idx.engine.set_option("pdl", pdl)
+        for i in range(12):
+            Dp, Ip = idx.search_packed(q[i % 4:i % 4 + 1], k, words, loc.size)
+            assert np.array_equal(Ip[0], Im[i % 4]) and np.array_equal(Dp[0], Dm[i % 4]), (transport, pdl, i)
+        Du, Iu = idx.search_packed(q, kk)
+        Dr, Ir = O.search_flat_ip(x, q, kk)
+        assert O.classify_parity(x, q, Iu, Du, Ir, Dr)["ok"]
+    idx.engine.set_option("pdl", 0)
     assert not idx.exchange_timed_out()
     idx.close()
 
