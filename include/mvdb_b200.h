@@ -93,7 +93,18 @@ int mvdb_index_reset(mvdb_index* ix);
  *                   (scores of a tcgen05 kind::tf32 GEMM over the fp32 matrix itself: no shadow
  *                   copy, 10-bit mantissa operands, half the tensor rate)
  *   "batch_min_nq"  floor on the nq routed to the batched path (default 2; above it a cost model
- *                   picks the cheaper of the fp32 scan passes and one bf16 shadow pass; k <= 128) */
+ *                   picks the cheaper of the fp32 scan passes and one bf16 shadow pass; k <= 128)
+ *   "batch_cost_model" 1 (default) = let that cost model decide, 0 = every nq >= batch_min_nq
+ *                   goes to the tensor cores (tests)
+ *   "coalesce"      1 (default) = concurrent single-query host-buffer calls share one pass over
+ *                   the matrix (leader/follower, no added latency when idle); "coalesce_max"
+ *                   caps a shared pass (default 64 queries)
+ *   "gemm_variant"  tile scheme of the tensor-core batch: 0 one CTA per 128x256 tile, 1 CTA pairs
+ *                   (cta_group::2), 2 clusters of 2 sharing the row tile by TMA multicast
+ *                   (default), 3 clusters of 4; "gemm_l2_hint" 0/1/2 L2 eviction hints (A/B)
+ *   "l2_pin_mb"     experiment: keep the head of the matrix L2-resident across scans (default 0)
+ *   test / profiling hooks (see the mvdb_debug_* functions): "trace", "gemm_prof", and
+ *   "gemm_debug" (bit mask that switches parts of the GEMM kernel OFF -- results are garbage) */
 int mvdb_index_set_option(mvdb_index* ix, const char* name, int64_t value);
 
 /* ---- ingest -------------------------------------------------------------
