@@ -14,13 +14,17 @@
 //     bound of the running k-th best (|q~.x~ - q.x| <= 2^-8 (1+2^-10) |q||x| for
 //     round-to-nearest bf16 inputs, plus fp32 accumulation slack) and re-scores
 //     the survivors in fp32 with the GEMV path's exact summation order, so
-//     ids and distances are bit-identical to the single-query scan.
+//     ids and distances are bit-identical to the single-query scan;
+//   * "tf32" mode runs the same kernels with kind::tf32 over the fp32 matrix and the fp32
+//     queries themselves (32 fp32 per 128-byte k-block, K = 8 per instruction; no shadow copy).
 //
 // Tile: 128 queries (UMMA M, one TMEM lane per query) x 256 rows (UMMA N, one
 // TMEM column per row) x 64 bf16 of K per stage (= 128 B, SWIZZLE_128B).
 // Warp roles (384 threads, 1 CTA/SM, persistent):
 //   warp 0  TMA producer   cp.async.bulk.tensor.2d -> 4-stage smem ring
-//   warp 1  MMA issuer     one elected lane, tcgen05.mma.cta_group::1.kind::f16
+//   warp 1  MMA issuer     one elected lane, tcgen05.mma.cta_group::1.kind::f16; the next k-block's
+//                          barrier is PEEKED inside the same asm block (umma_*_x4_peek) because any
+//                          latency of this thread between two MMAs is a bubble in the tensor pipe
 //   warp 2  TMEM allocator 512 columns = 2 accumulator stages x 256
 //   warps 4-11 epilogue    tcgen05.ld 32x32b.x32: thread <-> query, columns <-> rows; two warps per
 //                          TMEM lane quadrant, each taking 128 of the 256 columns
@@ -113,16 +117,6 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T ; bf16 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
 }
 // arrive on an mbarrier once all previously issued tcgen05.mma have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -539,15 +533,6 @@ __device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) 
 }
 __device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_bf16_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                               uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
 }
 // one arrival on the barrier at this offset in EVERY CTA of `mask`, once the MMAs issued so far retire
 __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar, uint16_t mask) {
