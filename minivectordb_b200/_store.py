@@ -177,6 +177,74 @@ class GpuStore:
             raise ValueError(f"embedding has dimension {row.shape[0]}, database has {self.embedding_size}")
         return row
 
+    def _as_rows(self, embeddings) -> np.ndarray:
+        """A batch of embeddings as ONE float32 [m, d] block (same checks as `_as_row`, applied to
+        every row; ragged or wrong-sized input raises ValueError before anything is stored)."""
+        if isinstance(embeddings, np.ndarray) and embeddings.ndim == 2:
+            block = np.ascontiguousarray(embeddings, dtype=np.float32)
+        else:
+            rows = [np.asarray(e, dtype=np.float32).reshape(-1) for e in embeddings]
+            if not rows:
+                return np.zeros((0, self.embedding_size or 0), dtype=np.float32)
+            d0 = rows[0].shape[0] if self.embedding_size is None else self.embedding_size
+            for r in rows:
+                if r.shape[0] != d0:
+                    raise ValueError(f"embedding has dimension {r.shape[0]}, database has {d0}")
+            block = np.stack(rows)
+        if block.shape[0] == 0:
+            return block
+        if self.embedding_size is None:
+            self.embedding_size = int(block.shape[1])
+        elif block.shape[1] != self.embedding_size:
+            raise ValueError(f"embedding has dimension {block.shape[1]}, database has {self.embedding_size}")
+        return block
+
+    def _append_batch(self, uids, block: np.ndarray, metas) -> None:
+        """`_append` for m rows at once (caller holds the lock and has validated uids / dimension):
+        the bookkeeping lists grow by bulk extends and the only per-row Python left is the metadata
+        walk that feeds the filter columns and the inverted index."""
+        m = int(block.shape[0])
+        if m == 0:
+            return
+        if len(self._parts) > 1:
+            for uid, row, meta in zip(uids, block, metas):   # rows are balanced one by one across partitions
+                self._append(uid, row, meta)
+            return
+        gid0 = self._g_n
+        if gid0 + m > self._g_live.shape[0]:
+            grown = np.zeros(max(self._g_live.shape[0] * 2, gid0 + m), dtype=bool)
+            grown[:gid0] = self._g_live[:gid0]
+            self._g_live = grown
+        part = self._parts[0]
+        slot0 = len(part.gids)
+        gids = range(gid0, gid0 + m)
+        uids = list(uids)
+        metas = list(metas)
+        self._g_uid.extend(uids)
+        self._g_meta.extend(metas)
+        self._g_part.extend([0] * m)
+        self._g_slot.extend(range(slot0, slot0 + m))
+        part.gids.extend(gids)
+        part.pending.extend(block)          # one view per row: get_vector reads staged rows by slot
+        self._g_live[gid0:gid0 + m] = True
+        self._g_n = gid0 + m
+        self._n_live += m
+        self._uid_gid.update(zip(uids, gids))
+        columns, inv = self._filters.columns, self.inverted_index
+        new_column = type(self._filters).new_column
+        for gid, uid, meta in zip(gids, uids, metas):
+            for key, value in meta.items():
+                col = columns.get(key)
+                if col is None:
+                    col = columns[key] = new_column()
+                col.rows.append(gid)
+                col.vals.append(value)
+                inv[key].add(uid)
+        self._ever_stored = True
+        self._embeddings_changed = True
+        self._views = None
+        self._version += 1
+
     def _append(self, uid, row: np.ndarray, metadata: dict) -> None:
         """Caller holds the lock and has validated uid / dimension."""
         gid = self._g_n

@@ -138,6 +138,10 @@ class FilterIndex:
     def clear(self) -> None:
         self.columns = {}
 
+    @staticmethod
+    def new_column() -> "Column":
+        return Column()
+
     def add_row(self, row: int, metadata: dict) -> None:
         for key, value in metadata.items():
             col = self.columns.get(key)

@@ -86,9 +86,10 @@ class ShardedVectorDatabase(GpuStore):
                 if emb.ndim == 2 and emb.shape[0] > 0 and self.embedding_size is None:
                     self.embedding_size = int(emb.shape[1])
                 self.box_item_map[shard_id] = list(data['unique_ids'])
-                for row, uid in enumerate(data['unique_ids']):
+                for uid in data['unique_ids']:
                     self.inverse_box_item_map[uid] = shard_id
-                    self._append(uid, emb[row], data['metadata'][row])
+                if len(data['unique_ids']):
+                    self._append_batch(data['unique_ids'], emb, data['metadata'])
             if self._n_live:
                 self._flush()
 
@@ -174,12 +175,11 @@ class ShardedVectorDatabase(GpuStore):
             for uid in unique_ids:
                 if uid in self._uid_gid:
                     raise ValueError(f"Unique ID {uid} already exists.")
-            rows = [self._as_row(e) for e in embeddings]
+            rows = self._as_rows(embeddings)
             # pad missing metadata with {} (SVDB:259-261) -- on a copy: the reference
             # extends the caller's (default!) list in place, which leaks rows between calls
             metas = list(metadata_dicts) + [{} for _ in range(len(unique_ids) - len(metadata_dicts))]
-            for uid, row, meta in zip(unique_ids, rows, metas):
-                self._append(uid, row, meta)
+            self._append_batch(unique_ids, rows, metas[:len(unique_ids)])
             self._persist_rows(unique_ids, rows, metas)
 
     def delete_embeddings_batch(self, unique_ids):

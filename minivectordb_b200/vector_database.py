@@ -58,8 +58,7 @@ class VectorDatabase(GpuStore):
             self.embedding_size = int(emb.shape[1])
             self._ever_stored = True
             id_map = data['id_map']
-            for row in range(emb.shape[0]):
-                self._append(id_map[row], emb[row], data['metadata'][row])
+            self._append_batch([id_map[row] for row in range(emb.shape[0])], emb, data['metadata'])
             saved = data.get('inverted_index')
             if saved is not None:
                 self.inverted_index = defaultdict(set, {k: set(v) for k, v in saved.items()})
@@ -96,9 +95,12 @@ class VectorDatabase(GpuStore):
                 raise ValueError("Metadata dictionaries must be provided for all unique IDs.")
             if len(metadata_dicts) == 0:
                 metadata_dicts = [{} for _ in range(len(unique_ids))]
-            rows = [self._as_row(e) for e in embeddings]
-            for uid, row, meta in zip(unique_ids, rows, metadata_dicts):
-                self._append(uid, row, meta)
+            block = self._as_rows(embeddings)
+            if block.shape[0] != len(unique_ids) or len(metadata_dicts) != len(unique_ids):
+                # the reference zips the three lists (VDB:100-107): extra entries are ignored
+                m = min(block.shape[0], len(unique_ids), len(metadata_dicts))
+                unique_ids, block, metadata_dicts = list(unique_ids)[:m], block[:m], list(metadata_dicts)[:m]
+            self._append_batch(unique_ids, block, metadata_dicts)
 
     def delete_embedding(self, unique_id):
         with self.lock:
