@@ -288,7 +288,21 @@ __device__ __forceinline__ void finish_scan(const ScanParams& p, uint8_t* smem_b
         const uint64_t* src = p.partials + size_t(qi) * G * k;
         if (staged) {
             if (qi) named_bar_sync(bar_id, bar_threads);
-            for (int i = cw * kWarp + lane; i < G * k; i += bar_threads) mbuf[i] = __ldcg(src + i);
+            // loads first, stores after: issued one by one the compiler keeps every global load behind
+            // the previous shared-memory store (possible alias) and the sweep costs a round trip per key
+            for (int i0 = cw * kWarp + lane; i0 < G * k; i0 += 8 * bar_threads) {
+                uint64_t tmp[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int i = i0 + u * bar_threads;
+                    tmp[u] = (i < G * k) ? __ldcg(src + i) : kEmptyKey;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int i = i0 + u * bar_threads;
+                    if (i < G * k) mbuf[i] = tmp[u];
+                }
+            }
             named_bar_sync(bar_id, bar_threads);
             src = mbuf;
             if (qi == 0) trace_stamp(p, 9, cw, lane);

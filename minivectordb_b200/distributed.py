@@ -166,11 +166,13 @@ class RowShardedIndex:
                 int(bool(normalize)), ctypes.c_void_p(b["D_out"].data_ptr()), ctypes.c_void_p(b["I_out"].data_ptr()),
                 ctypes.c_void_p(st) if st else None))
             return b["D_out"], b["I_out"]
-        self.engine.search_device(self._ws, q_dev.data_ptr(), nq, k, b["D_loc"].data_ptr(), b["I_loc"].data_ptr(),
+        # a lone rank writes straight into the result buffer (one D2H for host callers, see search_packed)
+        D_loc, I_loc = (b["D_out"], b["I_out"]) if self.world == 1 else (b["D_loc"], b["I_loc"])
+        self.engine.search_device(self._ws, q_dev.data_ptr(), nq, k, D_loc.data_ptr(), I_loc.data_ptr(),
                                   mask_ptr=mask_dev.data_ptr() if mask_dev is not None else 0,
                                   mask_rows=mask_rows, normalize=normalize, label_offset=self.offset, stream=st)
         if self.world == 1:
-            return b["D_loc"], b["I_loc"]
+            return D_loc, I_loc
         dist.all_gather_into_tensor(b["D_parts"].view(-1), b["D_loc"].view(-1), group=self.group)
         dist.all_gather_into_tensor(b["I_parts"].view(-1), b["I_loc"].view(-1), group=self.group)
         merge_topk_device(self.device, b["D_parts"].data_ptr(), b["I_parts"].data_ptr(), self.world, nq, k,

@@ -6,7 +6,7 @@ from minivectordb_b200 import _native as N
 names = {0: "cta0 consumer start", 1: "cta0 query loaded", 2: "cta0 tiles done", 3: "cta0 warps compacted+barrier", 4: "cta0 CTA merge + partials written",
          5: "cta0 fence+barrier", 6: "cta0 ticket taken", 8: "last: start", 9: "last: partials staged", 10: "last: column merge done",
          11: "last: compact+barrier", 12: "last: final merge done", 13: "last: results written"}
-for n, d in ((1184, 512), (100_000, 512), (1_000_000, 384)):
+for n, d in ((8, 512), (1184, 512), (100_000, 512), (1_000_000, 384)):
     eng = mv.FlatIPEngine(d); eng.add_synthetic(1234, 0, n, 0, True); ws = eng.workspace()
     eng.set_option("trace", 1)
     q = torch.randn(1, d, device="cuda"); D = torch.empty(1, 10, device="cuda"); I = torch.empty(1, 10, dtype=torch.int64, device="cuda")
