@@ -414,6 +414,7 @@ struct mvdb_index {
     std::mutex co_mu;
     std::deque<struct CoalesceReq*> co_queue;
     int co_leaders = 0;
+    int co_max_leaders = 0;        // option "coalesce_leaders": 0 = auto (1 for large matrices, else 2)
     // workspace pool for host-buffer searches
     std::mutex pool_mu;
     std::condition_variable pool_cv;
@@ -1349,6 +1350,9 @@ int mvdb_index_set_option(mvdb_index* ix, const char* name, int64_t value) {
             cudaFree(ix->trace_dev);
             ix->trace_dev = nullptr;
         }
+    } else if (s == "coalesce_leaders") {
+        if (value < 0 || value > 2) return fail(MVDB_ERR_ARG, "coalesce_leaders must be 0 (auto), 1 or 2");
+        ix->co_max_leaders = int(value);
     } else if (s == "pdl") {
         ix->pdl = value != 0;
     } else if (s == "dyn_tiles") {
@@ -1752,14 +1756,21 @@ static int exec_coalesced(mvdb_index* ix, std::vector<CoalesceReq*>& batch) {
     return MVDB_OK;
 }
 
-// Leader/follower coalescing with zero added latency when idle: a thread that finds fewer than
-// two leaders active becomes one and serves whatever is queued (including its own request);
+// Leader/follower coalescing with zero added latency when idle: a thread that finds a free leader
+// seat (one or two, see below) takes it and serves whatever is queued (including its own request);
 // while a batch runs on the GPU new arrivals queue up and form the next batch.
 static int coalesced_search(mvdb_index* ix, CoalesceReq& req) {
     std::unique_lock<std::mutex> lk(ix->co_mu);
     ix->co_queue.push_back(&req);
-    bool seat;   // does this thread hold one of the (at most two) leader seats?
-    if (ix->co_leaders >= 2) {
+    bool seat;   // does this thread hold one of the leader seats?
+    // Two leaders overlap one batch's host staging with the other's GPU pass -- worth it only while a
+    // pass is as short as the staging.  Once the matrix pass dominates (>= 256 MB: tens of us), two
+    // concurrent passes just share the HBM bandwidth and halve the batch size; one leader then lets
+    // the queue grow into one bigger batch per pass.
+    int seats = ix->co_max_leaders;
+    if (seats <= 0)
+        seats = (ix->ntotal.load(std::memory_order_acquire) * uint64_t(ix->ld) * 4ull >= (256ull << 20)) ? 1 : 2;
+    if (ix->co_leaders >= seats) {
         req.cv.wait(lk, [&] { return req.done || req.promote; });
         seat = req.promote;   // a departing leader handed its seat over (possibly after our request was served)
     } else {
