@@ -43,6 +43,7 @@ constexpr int kGemmBM = 128;      // queries per tile
 constexpr int kGemmBN = 256;      // rows per tile
 constexpr int kGemmBK = 64;       // bf16 per k-block (128 bytes)
 constexpr int kGemmStages = 4;
+constexpr int kGemmMaxStages = 8;  // single-CTA kernel with a short A tile (a_rows < 128): up to 6 stages
 constexpr uint32_t kGemmABytes = kGemmBM * kGemmBK * 2;   // 16 KB
 constexpr uint32_t kGemmBBytes = kGemmBN * kGemmBK * 2;   // 32 KB
 constexpr uint32_t kGemmStageBytes = kGemmABytes + kGemmBBytes;
@@ -74,6 +75,12 @@ struct GemmParams {
     // for a free stage (empty), 5 epilogue warp 4 total, 6 its wait for an accumulator (tfull)
     // 7 wall time of the MMA thread in ns (globaltimer)
     unsigned long long* prof;
+    // single-CTA kernel only: query rows actually staged per k-block (32 / 64 / 128) and ring depth.
+    // A batch of <= 32 queries stages 4 KB of A instead of 16 KB per k-block, which buys a 6-deep
+    // instead of a 4-deep ring: the small-batch pass is HBM-bound and lives on bytes in flight.
+    // (The MMA still reads 128 rows; rows past a_rows alias the B tile and feed accumulator lanes
+    // that no epilogue thread reads.)
+    uint32_t a_rows, stages;
     int debug;   // experiments, results are garbage: 1 = no operand loads (barriers only), 2 = no epilogue work, 4 = epilogue reads TMEM but skips the reduction,
                  // 8 = MMA thread never waits for operands (use with 1)
 };
@@ -324,8 +331,8 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
 }
 
 struct GemmBarriers {
-    uint64_t full[kGemmStages];
-    uint64_t empty[kGemmStages];
+    uint64_t full[kGemmMaxStages];
+    uint64_t empty[kGemmMaxStages];
     uint64_t tfull[2];
     uint64_t tempty[2];
     uint32_t tmem_base;
@@ -337,11 +344,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     constexpr int kBK = gemm_bk<kTf32>();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(smem + kGemmStages * kGemmStageBytes);
+    const uint32_t n_stages = p.stages, a_bytes = p.a_rows * 128u, stage_bytes = a_bytes + kGemmBBytes;
+    GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(smem + n_stages * stage_bytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kGemmStages; s++) {
+        for (uint32_t s = 0; s < n_stages; s++) {
             mbar_init(&bars->full[s], 1);
             mbar_init(&bars->empty[s], 1);
         }
@@ -377,14 +385,14 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 const uint32_t xt = t / n_qb, qb = t % n_qb;
                     for (uint32_t kb = 0; kb < n_kb; kb++) {
                         mbar_wait(&bars->empty[stage], phase ^ 1u);
-                        uint8_t* sA = smem + stage * kGemmStageBytes;
-                        uint8_t* sB = sA + kGemmABytes;
-                        mbar_arrive_expect_tx(&bars->full[stage], kGemmStageBytes);
+                        uint8_t* sA = smem + stage * stage_bytes;
+                        uint8_t* sB = sA + a_bytes;
+                        mbar_arrive_expect_tx(&bars->full[stage], stage_bytes);
                         if (p.l2_hint >= 2) tma_load_2d_hint(sA, &tmQ, int(kb * kBK), int(qb * kGemmBM), &bars->full[stage], keep);
                         else tma_load_2d(sA, &tmQ, int(kb * kBK), int(qb * kGemmBM), &bars->full[stage]);
                         if (p.l2_hint >= 1) tma_load_2d_hint(sB, &tmX, int(kb * kBK), int(p.row0 + xt * kGemmBN), &bars->full[stage], keep);
                         else tma_load_2d(sB, &tmX, int(kb * kBK), int(p.row0 + xt * kGemmBN), &bars->full[stage]);
-                        if (++stage == kGemmStages) { stage = 0; phase ^= 1u; }
+                        if (++stage == n_stages) { stage = 0; phase ^= 1u; }
                     }
             }
         }
@@ -400,11 +408,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 const uint32_t d_tmem = tmem_base + acc * kGemmBN;
                 for (uint32_t kb = 0; kb < n_kb; kb++) {
                     if (!tok_full) mbar_wait(&bars->full[stage], phase);
-                    const uint32_t a_addr = smem_u32(smem + stage * kGemmStageBytes);
+                    const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
                     const uint64_t a_desc = umma_desc_sw128(a_addr);
-                    const uint64_t b_desc = umma_desc_sw128(a_addr + kGemmABytes);
+                    const uint64_t b_desc = umma_desc_sw128(a_addr + a_bytes);
                     const uint32_t cur = stage;
-                    if (++stage == kGemmStages) { stage = 0; phase ^= 1u; }
+                    if (++stage == n_stages) { stage = 0; phase ^= 1u; }
                     const bool last_kb = kb + 1 == n_kb;
                     const bool more = !(last_kb && t + 1 == t_hi);
                     const uint32_t tok = (kTf32 ? umma_tf32_x4_peek : umma_bf16_x4_peek)(d_tmem, a_desc, b_desc, idesc, kb != 0 ? 1u : 0u,

@@ -395,6 +395,7 @@ struct mvdb_index {
     int batch_cost_model = 1;      // 0: every batch of >= batch_min_nq queries takes the tensor path (tests, probes)
     int gemm_l2_hint = 0;
     unsigned long long* trace_dev = nullptr;   // debug timeline of the scan kernel (option "trace")
+    int gemm_short_a = 1;          // batches of <= 64 queries stage a short A tile and run a deeper ring (0 = always 128 rows)
     int gemm_debug = 0;            // GemmParams::debug experiments (results are garbage when non-zero)
     unsigned long long* gemm_prof_dev = nullptr;   // debug wait-cycle counters of the GEMM kernels (option "gemm_prof"), [256][8]
     int pdl = 0;                   // search_device: programmatic dependent launch of back-to-back scans (opt-in)
@@ -706,13 +707,18 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
     const void* const x_base = tf32 ? ix->mat.ptr() : ix->mat16.ptr();
     const int64_t x_ld = tf32 ? int64_t(ix->ld) : int64_t(ix->ld16);
     const int variant = tf32 ? (ix->gemm_variant >= 2 ? 2 : 0) : ix->gemm_variant;   // tf32: single CTA or cluster-2 multicast
-    if (tf32) RC_OK(encode_gemm_map(&tmQ, ws->b_qn, uint64_t(nq), ix->d, ix->ld, kGemmBM, true));
-    else RC_OK(encode_gemm_map(&tmQ, ws->b_q16, uint64_t(nq), ix->d, ix->ld16, kGemmBM));
+    // one query block (nq <= 128) always runs the single-CTA kernel: stage only as many query rows as
+    // there are (32 / 64 / 128) and spend the shared memory on a deeper ring (6 / 5 / 4 stages)
+    const uint32_t a_rows = (nq <= 32 && ix->gemm_short_a) ? 32u : (nq <= 64 && ix->gemm_short_a) ? 64u : uint32_t(kGemmBM);
+    const uint32_t v0_stages = a_rows == 32 ? 6u : a_rows == 64 ? 5u : uint32_t(kGemmStages);
+    const size_t v0_smem = size_t(v0_stages) * (a_rows * 128u + kGemmBBytes) + 256 + 1024;
+    if (tf32) RC_OK(encode_gemm_map(&tmQ, ws->b_qn, uint64_t(nq), ix->d, ix->ld, a_rows, true));
+    else RC_OK(encode_gemm_map(&tmQ, ws->b_q16, uint64_t(nq), ix->d, ix->ld16, a_rows));
     tmQ2 = tmQ;   // the pair kernel loads 128-query boxes too
     tmX2 = tmQ;
     tmX4 = tmQ;
-    CU_OK(cudaFuncSetAttribute(gemm_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes)));
-    CU_OK(cudaFuncSetAttribute(gemm_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes)));
+    CU_OK(cudaFuncSetAttribute(gemm_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ix->smem_optin)));
+    CU_OK(cudaFuncSetAttribute(gemm_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ix->smem_optin)));
     CU_OK(cudaFuncSetAttribute(gemm_topk_kernel_2cta, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemm2SmemBytes)));
     CU_OK(cudaFuncSetAttribute(gemm_topk_kernel_mc<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes)));
     CU_OK(cudaFuncSetAttribute(gemm_topk_kernel_mc<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes)));
@@ -754,6 +760,8 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
     gp.dense = dense_out;
     gp.prof = ix->gemm_prof_dev;
     gp.debug = ix->gemm_debug;
+    gp.a_rows = a_rows;
+    gp.stages = v0_stages;
     gp.dense_ld = n;
     const uint32_t n_qb = uint32_t((nq + kGemmBM - 1) / kGemmBM);
 
@@ -870,8 +878,8 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
             } else {
                 const uint64_t tiles = uint64_t((hi - lo) / kGemmBN) * n_qb;
                 const unsigned grid = unsigned(std::min<uint64_t>(uint64_t(ix->sm_count), tiles));
-                if (tf32) gemm_topk_kernel<true><<<grid, 384, kGemmSmemBytes, stream>>>(tmQ, tmX, gp);
-                else gemm_topk_kernel<false><<<grid, 384, kGemmSmemBytes, stream>>>(tmQ, tmX, gp);
+                if (tf32) gemm_topk_kernel<true><<<grid, 384, v0_smem, stream>>>(tmQ, tmX, gp);
+                else gemm_topk_kernel<false><<<grid, 384, v0_smem, stream>>>(tmQ, tmX, gp);
             }
             LAUNCHED();
             if (!dense_out) {
@@ -1331,6 +1339,8 @@ int mvdb_index_set_option(mvdb_index* ix, const char* name, int64_t value) {
     } else if (s == "batch_mode") {
         if (value < 0 || value > 3) return fail(MVDB_ERR_ARG, "batch_mode must be 0 (off), 1 (exact), 2 (bf16) or 3 (tf32)");
         ix->batch_mode = int(value);
+    } else if (s == "gemm_short_a") {
+        ix->gemm_short_a = value != 0;
     } else if (s == "gemm_debug") {
         ix->gemm_debug = int(value);
     } else if (s == "gemm_prof") {
