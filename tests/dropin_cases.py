@@ -89,6 +89,23 @@ def case_basics(VDB, tmp_path):
         db.store_embeddings_batch([7, 8], [[0.1, 0.2], [0.3, 0.4]], [{"a": 1}])
     with pytest.raises(ValueError):
         db.store_embedding(50, [0.1, 0.2, 0.3])  # wrong dimension
+    # a batch with one ragged / wrong-sized row stores NOTHING (block conversion happens first)
+    before = (dict(db.id_map), len(db.metadata))
+    with pytest.raises(ValueError):
+        db.store_embeddings_batch([60, 61], [[0.1, 0.2], [0.3, 0.4, 0.5]])
+    with pytest.raises(ValueError):
+        db.store_embeddings_batch([60, 61], np.zeros((2, 3), dtype=np.float32))
+    assert (dict(db.id_map), len(db.metadata)) == before
+    # batches as a list of rows and as one 2-D array land identically (bulk append path)
+    db.store_embeddings_batch([70, 71], [np.array([0.6, 0.1]), [0.2, 0.7]], [{"b": 1}, {"b": 2}])
+    db.store_embeddings_batch([72, 73], np.array([[0.3, 0.3], [0.9, 0.2]], dtype=np.float64))
+    assert (db.get_vector(71) == np.array([0.2, 0.7], dtype=np.float32)).all()
+    assert (db.get_vector(73) == np.array([0.9, 0.2], dtype=np.float32)).all()
+    assert db.metadata[db.inverse_id_map[70]] == {"b": 1} and db.metadata[db.inverse_id_map[72]] == {}
+    assert db.inverted_index["b"] == {70, 71}
+    assert db.find_most_similar([0.2, 0.7], metadata_filter={"b": {"$gt": 1}}, k=3)[0] == (71,)
+    for uid in (70, 71, 72, 73):
+        db.delete_embedding(uid)
     # delete renumbers densely (ref :349-363)
     db.delete_embedding(2)
     assert db.id_map == {0: 1, 1: 3} and db.inverse_id_map == {1: 0, 3: 1}
