@@ -45,7 +45,8 @@ class _Partition:
         self.engine: Optional[FlatIPEngine] = None
         self.gids: List[int] = []        # slot -> gid, for flushed AND pending slots
         self.flushed = 0                 # slots [0, flushed) live on the device
-        self.pending: List[np.ndarray] = []
+        self.pending: List[np.ndarray] = []          # staged rows, one entry per slot (get_vector reads them)
+        self.pending_blocks: List[np.ndarray] = []   # the same rows as 2-D blocks in arrival order (what a flush ships)
         self.dead_unflushed: List[int] = []  # slots deleted on the host, not yet tombstoned on the device
         self.n_dead = 0                  # tombstones currently held by the engine (+ unflushed ones)
         self._gids_np = None
@@ -226,6 +227,7 @@ class GpuStore:
         self._g_slot.extend(range(slot0, slot0 + m))
         part.gids.extend(gids)
         part.pending.extend(block)          # one view per row: get_vector reads staged rows by slot
+        part.pending_blocks.append(block)
         self._g_live[gid0:gid0 + m] = True
         self._g_n = gid0 + m
         self._n_live += m
@@ -260,6 +262,7 @@ class GpuStore:
         self._g_slot.append(len(part.gids))
         part.gids.append(gid)
         part.pending.append(row)
+        part.pending_blocks.append(row[None, :])
         self._g_live[gid] = True
         self._g_n = gid + 1
         self._n_live += 1
@@ -297,10 +300,14 @@ class GpuStore:
             if part.pending:
                 if part.engine is None:
                     part.engine = FlatIPEngine(self.embedding_size, device=part.device)
-                block = np.vstack(part.pending) if len(part.pending) > 1 else part.pending[0][None, :]
+                # a bulk store arrives as one block and is shipped as it is; np.vstack over a million
+                # row views cost seconds here
+                blocks = part.pending_blocks
+                block = blocks[0] if len(blocks) == 1 else np.concatenate(blocks)
                 part.engine.add(block, normalize=True)   # faiss.normalize_L2 + index.add (VDB:45-46)
                 part.flushed = len(part.gids)
                 part.pending = []
+                part.pending_blocks = []
             if part.dead_unflushed:
                 part.engine.remove_rows(np.asarray(part.dead_unflushed, dtype=np.int64))
                 part.dead_unflushed = []
