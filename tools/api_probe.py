@@ -13,15 +13,17 @@ from minivectordb_b200 import VectorDatabase, synth  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 d = int(sys.argv[2]) if len(sys.argv) > 2 else 384
 db = VectorDatabase(storage_file="/tmp/api_probe_none.pkl")
-t0 = time.perf_counter()
 step = 100_000
 rng = np.random.default_rng(0)
+t_store = 0.0      # time inside store_embeddings_batch only (generating the synthetic rows is not the database's work)
 for a in range(0, n, step):
     m = min(step, n - a)
     emb = synth.synth_rows(1234, a, m, d)
     vals = rng.integers(0, 100, m)
-    db.store_embeddings_batch(list(range(a, a + m)), list(emb), [{"value": int(v), "tag": f"t{int(v) % 16}"} for v in vals])
-t_store = time.perf_counter() - t0
+    ids, rows, metas = list(range(a, a + m)), list(emb), [{"value": int(v), "tag": f"t{int(v) % 16}"} for v in vals]
+    t0 = time.perf_counter()
+    db.store_embeddings_batch(ids, rows, metas)
+    t_store += time.perf_counter() - t0
 q = synth.synth_rows(4321, 0, 300, d)
 t0 = time.perf_counter()
 db.find_most_similar(q[0], k=10)
