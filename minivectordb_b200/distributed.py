@@ -216,7 +216,12 @@ class RowShardedIndex:
         q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, self.d)
         nq = q.shape[0]
         if not self.on_gpu:
-            raise RuntimeError("search_packed needs the GPU engine")
+            # CPU test path (gloo + injected engine): same contract, the packed words are unpacked again
+            loc = None
+            if mask_words is not None:
+                bits = np.unpackbits(np.ascontiguousarray(mask_words).view(np.uint8), bitorder="little")
+                loc = bits[:int(mask_rows)].astype(bool)
+            return self.search(q, k, mask_local=loc, normalize=normalize)
         nw = 0
         if mask_words is not None:
             mw = np.ascontiguousarray(mask_words).view(np.int32).reshape(-1)

@@ -53,6 +53,15 @@ def _worker(rank, world, port, ret):
         D, I = idx.search(q, k, mask_local=adm[bounds[rank]:bounds[rank + 1]])
         Dr, Ir = O.search_masked(x, adm, q, k)
         assert np.array_equal(I, Ir)
+        # packed-filter entry point (what bench.py's multi-GPU e2e leg calls): this rank's slice as 32-bit words
+        loc = adm[bounds[rank]:bounds[rank + 1]]
+        words = np.zeros((loc.size + 31) // 32 * 4, dtype=np.uint8)
+        pk = np.packbits(loc, bitorder="little")
+        words[:pk.size] = pk
+        Dp, Ip = idx.search_packed(q, k, words, loc.size)
+        assert np.array_equal(Ip, Ir) and np.array_equal(Dp, D)
+        Du, Iu = idx.search_packed(q[:1], k)
+        assert np.array_equal(Iu, O.search_flat_ip(x, q[:1], k)[1])
         # k larger than one shard's admissible rows: padding must not leak into the merge
         few = np.zeros(n, dtype=bool)
         few[[5, 1700, 1801, 4999]] = True
