@@ -4,7 +4,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import minivectordb_b200 as mv
 out = []
-for n, d, nq, k in ((1_000_000, 384, 4096, 10), (2_000_000, 1024, 4096, 100)):
+for n, d, nq, k in [((1_000_000, 384, 4096, 10), (2_000_000, 1024, 4096, 100), (10_000_000, 1024, 4096, 100))[int(c)] for c in os.environ.get("CASES", "0,1").split(",")]:
     eng = mv.FlatIPEngine(d); eng.add_synthetic(1234, 0, n, 0, True); ws = eng.workspace()
     q = torch.randn(nq, d, device="cuda"); q = q / q.norm(dim=1, keepdim=True)
     D = torch.empty(nq, k, device="cuda"); I = torch.empty(nq, k, dtype=torch.int64, device="cuda")
