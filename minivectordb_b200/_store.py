@@ -92,6 +92,7 @@ class EmbeddingsView:
 
 class GpuStore:
     MASK_CACHE_ENTRIES = 16      # device-resident filter masks kept per database
+    PARALLEL_PARTS_BYTES = 64 << 20   # partitions are scanned concurrently once the database is at least this big
     COMPACT_MIN_DEAD = 4096      # do not bother compacting below this many tombstones
     COMPACT_DEAD_FRACTION = 0.25
 
@@ -114,6 +115,7 @@ class GpuStore:
         self._active_searches = 0
         self._views = None               # cached (id_map, inverse_id_map, metadata, unique_ids)
         self._version = 0                # bumped by every mutation: invalidates cached filter masks
+        self._pool = None                 # worker threads that scan several partitions (GPUs) at once
         self._mask_cache = OrderedDict()  # filter repr -> (version, count, per-partition device-resident masks)
         self._mask_seen = OrderedDict()   # filter repr -> version at which it was last evaluated
         self._embeddings_changed = False  # kept for API parity (VDB:18); True while rows wait on the host
@@ -425,8 +427,16 @@ class GpuStore:
         try:
             search_k = min(int(k), count)  # VDB:489-492
             cands = []
-            for part, gids, handle in jobs:
-                D, I = part.engine.search(q, search_k, mask=handle, normalize=True)
+            if len(jobs) > 1 and self._n_live * (self.embedding_size or 1) * 4 >= self.PARALLEL_PARTS_BYTES:
+                # partitions live on different GPUs: scan them at the same time (the C ABI releases the GIL);
+                # below ~64 MB the thread hand-off costs more than the scans
+                if self._pool is None:
+                    from concurrent.futures import ThreadPoolExecutor
+                    self._pool = ThreadPoolExecutor(max_workers=len(self._parts), thread_name_prefix="mvdb-part")
+                results = list(self._pool.map(lambda j: j[0].engine.search(q, search_k, mask=j[2], normalize=True), jobs))
+            else:
+                results = [part.engine.search(q, search_k, mask=handle, normalize=True) for part, gids, handle in jobs]
+            for (part, gids, handle), (D, I) in zip(jobs, results):
                 for slot, dist in zip(I[0], D[0]):
                     if slot == -1:
                         continue  # VDB:500
@@ -448,6 +458,9 @@ class GpuStore:
         return ids, distances, metadatas
 
     def close(self) -> None:
+        if self._pool is not None:
+            self._pool.shutdown(wait=True)
+            self._pool = None
         for part in self._parts:
             if part.engine is not None:
                 part.engine.close()

@@ -27,6 +27,13 @@ def test_golden_scenario_svdb_two_partitions(classes, tmp_path):
     C.case_golden_scenario_svdb(classes[1], tmp_path, devices=[0, 1])
 
 
+def test_golden_scenario_svdb_partitions_scanned_in_parallel(classes, tmp_path, monkeypatch):
+    # large multi-GPU databases scan their partitions from worker threads; force that path here
+    import minivectordb_b200._store as store
+    monkeypatch.setattr(store.GpuStore, "PARALLEL_PARTS_BYTES", 0)
+    C.case_golden_scenario_svdb(classes[1], tmp_path, devices=[0, 1])
+
+
 def test_loads_reference_pickle(classes, tmp_path):
     C.case_loads_reference_pickle(classes[0], tmp_path)
 
