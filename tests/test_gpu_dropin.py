@@ -33,6 +33,13 @@ def test_golden_scenario_svdb_two_devices(classes, tmp_path):
     C.case_golden_scenario_svdb(classes[1], tmp_path, devices=[0, 1])
 
 
+def test_golden_scenario_svdb_partitions_in_parallel(classes, tmp_path, monkeypatch):
+    # two partitions (two GPUs when there are two, else both on GPU 0) scanned from worker threads
+    import minivectordb_b200._store as store
+    monkeypatch.setattr(store.GpuStore, "PARALLEL_PARTS_BYTES", 0)
+    C.case_golden_scenario_svdb(classes[1], tmp_path, devices=[0, 1] if _ndev() >= 2 else [0, 0])
+
+
 def test_loads_reference_pickle(classes, tmp_path):
     C.case_loads_reference_pickle(classes[0], tmp_path)
 
