@@ -67,22 +67,41 @@ class Column:
         self.rows.append(row)
         self.vals.append(value)
 
+    @staticmethod
+    def _classify(vals) -> str:
+        if all(_is_plain_number(v) for v in vals):   # bool is an int: True == 1, as in Python
+            return "num"
+        if all(isinstance(v, str) for v in vals):
+            return "str"
+        return "obj"
+
     def _typed(self):
+        """Typed numpy view of the column, extended INCREMENTALLY: only the entries appended since
+        the last call are converted (a database that keeps growing between filtered queries would
+        otherwise pay O(rows) Python-object conversion per query)."""
         n = len(self.rows)
-        if self._built != n:
-            self._rows_np = np.asarray(self.rows, dtype=np.int64)
-            vals = self.vals
-            if all(_is_plain_number(v) for v in vals):  # bool is an int: True == 1, as in Python
-                self._kind = "num"
-                self._vals_np = np.asarray(vals, dtype=np.float64)
-            elif all(isinstance(v, str) for v in vals):
-                self._kind = "str"
-                self._vals_np = np.asarray(vals, dtype=object)
-            else:
-                self._kind = "obj"
-                self._vals_np = None
-            self._built = n
-        return self._kind
+        lo = self._built
+        if lo == n:
+            return self._kind
+        tail_rows = np.asarray(self.rows[lo:], dtype=np.int64)
+        tail_vals = self.vals[lo:]
+        kind = self._classify(tail_vals)
+        if lo and kind != self._kind:
+            kind = "obj"   # the column stopped being homogeneous
+        if kind == "num":
+            tail = np.asarray(tail_vals, dtype=np.float64)
+        elif kind == "str":
+            tail = np.asarray(tail_vals, dtype=object)
+        else:
+            tail = None
+        self._rows_np = tail_rows if lo == 0 else np.concatenate((self._rows_np, tail_rows))
+        if tail is None:
+            self._vals_np = None
+        else:
+            self._vals_np = tail if lo == 0 else np.concatenate((self._vals_np, tail))
+        self._kind = kind
+        self._built = n
+        return kind
 
     def device_match(self, engine, nrows: int, op: Optional[str], operand):
         """The clause as a device-resident mask (MaskHandle).  Numeric column + numeric operand:
