@@ -68,12 +68,26 @@ class Column:
         self.vals.append(value)
 
     @staticmethod
-    def _classify(vals) -> str:
+    def _convert(vals):
+        """(kind, typed array or None) of a run of values: "num" (float64), "str" (object array) or
+        "obj" (no typed view).  Numbers take numpy's own conversion as the fast path: a numeric result
+        dtype proves that every element was a plain number (a str / None / list anywhere yields a
+        string or object dtype instead); integers beyond 2^53 are left to the exact Python path."""
+        first = vals[0]
+        if isinstance(first, _NUM_TYPES):
+            try:
+                arr = np.asarray(vals)
+            except (ValueError, TypeError, OverflowError):
+                arr = None
+            if arr is not None and arr.ndim == 1 and arr.dtype.kind in "iufb":
+                if arr.dtype.kind not in "iu" or (arr.size and np.abs(arr).max() <= _EXACT_INT):
+                    return "num", arr.astype(np.float64)
+                return "obj", None
         if all(_is_plain_number(v) for v in vals):   # bool is an int: True == 1, as in Python
-            return "num"
+            return "num", np.asarray(vals, dtype=np.float64)
         if all(isinstance(v, str) for v in vals):
-            return "str"
-        return "obj"
+            return "str", np.asarray(vals, dtype=object)
+        return "obj", None
 
     def _typed(self):
         """Typed numpy view of the column, extended INCREMENTALLY: only the entries appended since
@@ -84,16 +98,9 @@ class Column:
         if lo == n:
             return self._kind
         tail_rows = np.asarray(self.rows[lo:], dtype=np.int64)
-        tail_vals = self.vals[lo:]
-        kind = self._classify(tail_vals)
+        kind, tail = self._convert(self.vals[lo:])
         if lo and kind != self._kind:
-            kind = "obj"   # the column stopped being homogeneous
-        if kind == "num":
-            tail = np.asarray(tail_vals, dtype=np.float64)
-        elif kind == "str":
-            tail = np.asarray(tail_vals, dtype=object)
-        else:
-            tail = None
+            kind, tail = "obj", None   # the column stopped being homogeneous
         self._rows_np = tail_rows if lo == 0 else np.concatenate((self._rows_np, tail_rows))
         if tail is None:
             self._vals_np = None
