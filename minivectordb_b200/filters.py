@@ -51,7 +51,8 @@ def _is_plain_number(v) -> bool:
 class Column:
     """All rows that carry one metadata key: parallel lists (row id, value)."""
 
-    __slots__ = ("rows", "vals", "_rows_np", "_vals_np", "_kind", "_built", "_dev", "_dev_rows")
+    __slots__ = ("rows", "vals", "_rows_np", "_vals_np", "_kind", "_built", "_dev", "_dev_rows",
+                 "_post", "_post_plain", "_post_built")
 
     def __init__(self):
         self.rows: List[int] = []
@@ -62,6 +63,9 @@ class Column:
         self._built = 0
         self._dev = None        # DeviceColumn mirror (numeric columns only)
         self._dev_rows = 0      # rows [0, _dev_rows) of the database are mirrored
+        self._post = None       # `$in` postings: element -> entry indices, for list / tuple / set values
+        self._post_plain = None  # entry indices whose value is anything else (str: substring test, ...)
+        self._post_built = 0
 
     def append(self, row: int, value) -> None:
         self.rows.append(row)
@@ -147,12 +151,58 @@ class Column:
                    "$lte": lambda: v <= x, "$ne": lambda: v != x}[op]()
         elif kind == "str" and isinstance(operand, str) and op in (None, "$ne"):
             hit = (self._vals_np == operand) if op is None else (self._vals_np != operand)
+        if hit is None and op == "$in":
+            hit = self._match_in(operand)
         if hit is None:
             # generic path: the reference's own operator call per stored value
             fn = (lambda stored, x: stored == x) if op is None else _OPS[op]
             hit = np.fromiter((bool(fn(s, operand)) for s in self.vals), dtype=bool, count=len(self.vals))
         out[self._rows_np[hit]] = True
         return out
+
+    def _match_in(self, operand):
+        """`operand in stored` (VDB:172) through postings.  Stored lists / tuples / sets of hashable
+        elements are indexed element -> entries once (extended incrementally), so a tag filter costs
+        O(hits) instead of a Python call per row; `x in [a, b]` compares with ==, which is what a
+        dict lookup does for hashable values.  Every other stored value (a str means a SUBSTRING
+        test, an int raises TypeError, ...) still goes through the reference's own operator call.
+        Returns bool[len(vals)], or None when the operand cannot be looked up (unhashable)."""
+        try:
+            hash(operand)
+        except TypeError:
+            return None
+        if operand != operand:     # NaN: `in` falls back on identity, a lookup would not
+            return None
+        if self._post is None:
+            self._post, self._post_plain, self._post_built = {}, [], 0
+        post, plain = self._post, self._post_plain
+        vals = self.vals
+        for i in range(self._post_built, len(vals)):
+            s = vals[i]
+            if type(s) in (list, tuple, set, frozenset):
+                try:
+                    ok = all(hash(e) is not None and e == e for e in s)   # hashable, and no NaN (identity semantics)
+                except TypeError:
+                    ok = False
+                if ok:
+                    for e in s:
+                        lst = post.get(e)
+                        if lst is None:
+                            post[e] = [i]
+                        elif lst[-1] != i:
+                            lst.append(i)
+                    continue
+            plain.append(i)
+        self._post_built = len(vals)
+        hit = np.zeros(len(vals), dtype=bool)
+        idx = post.get(operand)
+        if idx:
+            hit[np.asarray(idx, dtype=np.int64)] = True
+        fn = _OPS["$in"]
+        for i in plain:
+            if fn(vals[i], operand):
+                hit[i] = True
+        return hit
 
 
 class FilterIndex:

@@ -46,3 +46,59 @@ def test_incrementally_typed_column_equals_a_fresh_one():
                     assert got == want, (name, upto, op)
                 else:
                     assert np.array_equal(got, want), (name, upto, op)
+
+
+def test_in_operator_postings_equal_the_per_row_operator_call():
+    """`{"tags": {"$in": "t3"}}` is `operand in stored` per row in the reference (VDB:172).  Lists /
+    tuples / sets of hashable elements are served from element -> rows postings; strings (substring
+    test), dicts (key test), nested or NaN-carrying lists and unhashable operands keep the exact
+    operator call.  Values AND TypeErrors must match the per-row evaluation, also when the column
+    keeps growing between queries."""
+    from minivectordb_b200.filters import _OPS
+    rng = np.random.default_rng(1)
+
+    def generic(c, n, operand):
+        out = np.zeros(n, dtype=bool)
+        hit = np.fromiter((bool(_OPS["$in"](s, operand)) for s in c.vals), dtype=bool, count=len(c.vals))
+        out[np.asarray(c.rows)[hit]] = True
+        return out
+
+    def same(c, n, operand):
+        try:
+            a = c.match(n, "$in", operand)
+        except TypeError:
+            a = "TypeError"
+        try:
+            b = generic(c, n, operand)
+        except TypeError:
+            b = "TypeError"
+        if isinstance(a, str) or isinstance(b, str):
+            return isinstance(a, str) and isinstance(b, str)
+        return np.array_equal(a, b)
+
+    for with_str in (False, True):
+        vals = []
+        for _ in range(3000):
+            r = rng.random()
+            if r < 0.6:
+                vals.append(["t%d" % rng.integers(0, 16), "t%d" % rng.integers(0, 16)])
+            elif r < 0.7:
+                vals.append(("x", 1, 2.0, True))
+            elif r < 0.8:
+                vals.append({"t3", "zz"})
+            elif r < 0.88:
+                vals.append("t3 and t5 substring" if with_str else ["t3", "t3"])
+            elif r < 0.93:
+                vals.append([["nested"], "t3"])
+            elif r < 0.96:
+                vals.append([float("nan"), "t3"])
+            else:
+                vals.append({"t3": 1})
+        c = Column()
+        k = 0
+        for upto in (10, 700, len(vals)):
+            while k < upto:
+                c.append(3 * k, vals[k])
+                k += 1
+            for operand in ("t3", "t15", 1, 1.0, True, "zz", "nested", ("a",), "sub", 2, ["nested"], float("nan")):
+                assert same(c, 3 * k + 1, operand), (with_str, upto, operand)
