@@ -52,7 +52,7 @@ class Column:
     """All rows that carry one metadata key: parallel lists (row id, value)."""
 
     __slots__ = ("rows", "vals", "_rows_np", "_vals_np", "_kind", "_built", "_dev", "_dev_rows",
-                 "_post", "_post_plain", "_post_built")
+                 "_post", "_post_plain", "_post_built", "_vocab", "_codes_np")
 
     def __init__(self):
         self.rows: List[int] = []
@@ -63,6 +63,8 @@ class Column:
         self._built = 0
         self._dev = None        # DeviceColumn mirror (numeric columns only)
         self._dev_rows = 0      # rows [0, _dev_rows) of the database are mirrored
+        self._vocab = None      # string columns: value -> code (dictionary encoding) ...
+        self._codes_np = None   # ... and the float64 code of every entry (what the device mirror holds)
         self._post = None       # `$in` postings: element -> entry indices, for list / tuple / set values
         self._post_plain = None  # entry indices whose value is anything else (str: substring test, ...)
         self._post_built = 0
@@ -110,6 +112,16 @@ class Column:
             self._vals_np = None
         else:
             self._vals_np = tail if lo == 0 else np.concatenate((self._vals_np, tail))
+        if kind == "str":
+            # dictionary encoding: equality on strings becomes equality on small integers, which numpy
+            # does at memory speed and the device predicate kernel can do on its mirror of the codes
+            if lo == 0 or self._vocab is None:
+                self._vocab, self._codes_np = {}, np.zeros(0, dtype=np.float64)
+            vocab = self._vocab
+            codes = np.fromiter((vocab.setdefault(v, len(vocab)) for v in tail), dtype=np.float64, count=len(tail))
+            self._codes_np = np.concatenate((self._codes_np, codes))
+        else:
+            self._vocab = self._codes_np = None
         self._kind = kind
         self._built = n
         return kind
@@ -119,7 +131,10 @@ class Column:
         evaluated by a CUDA kernel on the HBM-resident column (which is extended lazily with the
         rows appended since the last filter); anything else: evaluated here and uploaded."""
         kind = self._typed() if self.rows else None
-        if kind == "num" and _is_plain_number(operand) and op != "$in":
+        numeric = kind == "num" and _is_plain_number(operand) and op != "$in"
+        coded = kind == "str" and isinstance(operand, str) and op in (None, "$ne")
+        if numeric or coded:
+            src = self._vals_np if numeric else self._codes_np   # a column is one or the other for its whole life
             if self._dev is None:
                 self._dev, self._dev_rows = engine.column(), 0
             if self._dev_rows < nrows:
@@ -129,11 +144,12 @@ class Column:
                 present = np.zeros(m, dtype=np.uint8)
                 idx = self._rows_np[lo:] - self._dev_rows
                 keep = idx < m
-                vals[idx[keep]] = self._vals_np[lo:][keep]
+                vals[idx[keep]] = src[lo:][keep]
                 present[idx[keep]] = 1
                 self._dev.append(vals, present)
                 self._dev_rows = nrows
-            return self._dev.predicate(op, float(operand))
+            # a string nobody stored has no code: -1 equals nothing and differs from everything present
+            return self._dev.predicate(op, float(operand) if numeric else float(self._vocab.get(operand, -1)))
         self._dev = None   # the column stopped being purely numeric (or never was)
         return engine.mask_handle(self.match(nrows, op, operand))
 
@@ -150,7 +166,8 @@ class Column:
             hit = {None: lambda: v == x, "$gt": lambda: v > x, "$gte": lambda: v >= x, "$lt": lambda: v < x,
                    "$lte": lambda: v <= x, "$ne": lambda: v != x}[op]()
         elif kind == "str" and isinstance(operand, str) and op in (None, "$ne"):
-            hit = (self._vals_np == operand) if op is None else (self._vals_np != operand)
+            code = float(self._vocab.get(operand, -1))
+            hit = (self._codes_np == code) if op is None else (self._codes_np != code)
         if hit is None and op == "$in":
             hit = self._match_in(operand)
         if hit is None:

@@ -102,3 +102,24 @@ def test_in_operator_postings_equal_the_per_row_operator_call():
                 k += 1
             for operand in ("t3", "t15", 1, 1.0, True, "zz", "nested", ("a",), "sub", 2, ["nested"], float("nan")):
                 assert same(c, 3 * k + 1, operand), (with_str, upto, operand)
+
+
+def test_dictionary_coded_string_columns():
+    """String equality / $ne run on integer codes (host) and on the device mirror of the codes; the
+    answers must be those of comparing the strings, for values seen, never seen, and after growth."""
+    rng = np.random.default_rng(2)
+    vals = ["t%d" % v for v in rng.integers(0, 9, 4000)]
+    c = Column()
+    k = 0
+    for upto in (5, 900, len(vals)):
+        while k < upto:
+            c.append(2 * k + 1, vals[k])
+            k += 1
+        arr = np.asarray(vals[:k], dtype=object)
+        for operand in ("t3", "t8", "never", ""):
+            for op, want in ((None, arr == operand), ("$ne", arr != operand)):
+                out = np.zeros(2 * k + 2, dtype=bool)
+                out[2 * np.flatnonzero(want) + 1] = True
+                assert np.array_equal(c.match(2 * k + 2, op, operand), out), (upto, op, operand)
+    # a non-string operand on a string column keeps the generic comparison (never equal)
+    assert not c.match(2 * k + 2, None, 3).any() and c.match(2 * k + 2, "$ne", 3).sum() == k

@@ -159,6 +159,10 @@ def test_device_filter_evaluation_matches_host_evaluation(classes, tmp_path):
         dict(metadata_filter={"value": {"$gt": 10}}, or_filters={"tag": "t1", "score": {"$gt": 0.5}}),
         dict(exclude_filter={"value": 42}),
         dict(metadata_filter={"value": {"$gt": 30}}, exclude_filter=[{"tag": "t2"}, {"value": 77}]),
+        dict(metadata_filter={"tag": {"$ne": "t3"}}),                      # string columns are dictionary-coded on the device
+        dict(metadata_filter={"tag": "never-stored"}),
+        dict(metadata_filter={"value": {"$lt": 90}}, exclude_filter={"tag": "never-stored"}),
+        dict(metadata_filter={"tag": {"$ne": "never-stored"}, "value": {"$gt": 95}}),
         dict(metadata_filter={"mixed": {"$ne": 11}}),
         dict(metadata_filter={"nokey": {"$gt": 1}}),
     ]
