@@ -191,7 +191,12 @@ int mvdb_index_search_with_mask(mvdb_index* ix, const float* q, int64_t nq, int6
  * per row); predicates ($gt $gte $lt $lte $ne, equality: op 2 3 4 5 1 0) and the AND / OR /
  * exclude combinators (how 0 / 1 / 2 = and-not) run as small kernels and yield a mask handle
  * directly -- no per-row Python, no mask upload.  Rows lacking the key never match, as in
- * the reference's inverted-index walk (vector_database.py:260). */
+ * the reference's inverted-index walk (vector_database.py:260).
+ * Ordering guarantee: the filter kernels run on one internal stream per index, in call order; a
+ * mask handle carries an event recorded behind its latest writer and every search that is given
+ * the handle waits for that event on its own stream.  So "predicate -> combine -> search" needs no
+ * synchronisation by the caller, from any thread.  A handle must not be combined into / destroyed
+ * while another thread is searching with it. */
 typedef struct mvdb_column mvdb_column;
 int mvdb_column_create(mvdb_index* ix, mvdb_column** out);
 int mvdb_column_destroy(mvdb_column* c);

@@ -147,26 +147,31 @@ class GpuStore:
         """All live rows, logical order, float32 [n_live, d] (what the reference's
         `self.embeddings` holds: normalised rows once flushed, raw while pending)."""
         with self.lock:
-            d = self.embedding_size or 0
-            gids = self._live_gids()
-            out = np.empty((gids.shape[0], d), dtype=np.float32)
-            if gids.shape[0] == 0:
-                return out
-            gpart = np.asarray(self._g_part, dtype=np.int64)[gids]
-            gslot = np.asarray(self._g_slot, dtype=np.int64)[gids]
-            for pi, part in enumerate(self._parts):
-                sel = np.flatnonzero(gpart == pi)
-                if sel.size == 0:
-                    continue
-                slots = gslot[sel]
-                on_dev = slots < part.flushed
-                if on_dev.any():
-                    lo, hi = int(slots[on_dev].min()), int(slots[on_dev].max()) + 1
-                    block = part.engine.reconstruct_n(lo, hi - lo)
-                    out[sel[on_dev]] = block[slots[on_dev] - lo]
-                for j in np.flatnonzero(~on_dev):
-                    out[sel[j]] = part.pending[int(slots[j]) - part.flushed]
+            return self._materialize_locked()
+
+    def _materialize_locked(self) -> np.ndarray:
+        """`_materialize` for callers that already hold the lock (persist_to_disk builds the
+        matrix and the id views under ONE lock, as the reference does, VDB:538-548)."""
+        d = self.embedding_size or 0
+        gids = self._live_gids()
+        out = np.empty((gids.shape[0], d), dtype=np.float32)
+        if gids.shape[0] == 0:
             return out
+        gpart = np.asarray(self._g_part, dtype=np.int64)[gids]
+        gslot = np.asarray(self._g_slot, dtype=np.int64)[gids]
+        for pi, part in enumerate(self._parts):
+            sel = np.flatnonzero(gpart == pi)
+            if sel.size == 0:
+                continue
+            slots = gslot[sel]
+            on_dev = slots < part.flushed
+            if on_dev.any():
+                lo, hi = int(slots[on_dev].min()), int(slots[on_dev].max()) + 1
+                block = part.engine.reconstruct_n(lo, hi - lo)
+                out[sel[on_dev]] = block[slots[on_dev] - lo]
+            for j in np.flatnonzero(~on_dev):
+                out[sel[j]] = part.pending[int(slots[j]) - part.flushed]
+        return out
 
     # --------------------------------------------------------------- mutation
     def _as_row(self, embedding) -> np.ndarray:
@@ -184,7 +189,9 @@ class GpuStore:
         """A batch of embeddings as ONE float32 [m, d] block (same checks as `_as_row`, applied to
         every row; ragged or wrong-sized input raises ValueError before anything is stored)."""
         if isinstance(embeddings, np.ndarray) and embeddings.ndim == 2:
-            block = np.ascontiguousarray(embeddings, dtype=np.float32)
+            # always a private copy: the block is staged until the next flush, and the reference copies
+            # too (np.array + np.vstack, VDB:26, 107) -- a caller may reuse its batch buffer right away
+            block = np.array(embeddings, dtype=np.float32, order='C')
         else:
             rows = [np.asarray(e, dtype=np.float32).reshape(-1) for e in embeddings]
             if not rows:
@@ -461,6 +468,14 @@ class GpuStore:
         if self._pool is not None:
             self._pool.shutdown(wait=True)
             self._pool = None
+        # native mask / column handles point into their index: release them BEFORE the engines go
+        for _, _, jobs in self._mask_cache.values():
+            for job in jobs:
+                if hasattr(job[2], "close"):
+                    job[2].close()
+        self._mask_cache.clear()
+        self._mask_seen.clear()
+        self._filters.close_device()
         for part in self._parts:
             if part.engine is not None:
                 part.engine.close()

@@ -339,6 +339,10 @@ struct mvdb_mask {         // device-resident filter, uploaded once, reusable by
     uint32_t* dev;
     uint64_t rows;
     uint32_t words;
+    // The mask kernels (predicate / fill / combine) run on the index's filter stream; `ready` is
+    // recorded after the last one that wrote this mask and every search that reads the mask makes its
+    // own (non-blocking) stream wait for it -- no host synchronisation between filter and search.
+    cudaEvent_t ready = nullptr;
 };
 
 struct mvdb_column {       // one numeric metadata column, row-aligned with the index
@@ -409,6 +413,7 @@ struct mvdb_index {
     int consumer_warps = 0;
     unsigned long long* count_dev = nullptr;   // scratch of mvdb_mask_count
     std::mutex count_mu;
+    cudaStream_t filter_stream = nullptr;      // every device-side filter kernel runs here, in call order
     // query coalescer: concurrent single-query host searches share one pass over the matrix
     int coalesce = 1;
     int coalesce_max = 64;
@@ -1269,6 +1274,7 @@ int mvdb_index_create(int d, int device, uint64_t capacity_hint, mvdb_index** ou
     ix->ld16 = int64_t(align_up(size_t(d), 8));
     if (rc == MVDB_OK) rc = ix->mat16.init(device, std::max<size_t>(reserve / (size_t(ix->ld) * 4) * ix->ld16 * 2, size_t(1) << 21));
     cudaError_t e = cudaStreamCreateWithFlags(&ix->mut_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ix->filter_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&ix->max_norm2_bits, sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(ix->max_norm2_bits, 0, sizeof(int));
     if (rc != MVDB_OK || e != cudaSuccess) {
@@ -1297,6 +1303,7 @@ int mvdb_index_destroy(mvdb_index* ix) {
     cudaFree(ix->stage_dev[1]);
     cudaFree(ix->rows_dev);
     if (ix->mut_stream) cudaStreamDestroy(ix->mut_stream);
+    if (ix->filter_stream) cudaStreamDestroy(ix->filter_stream);
     delete ix;
     return MVDB_OK;
 }
@@ -1636,6 +1643,18 @@ int mvdb_index_search_device(mvdb_index* ix, mvdb_workspace* ws, const float* q_
     return rc;
 }
 
+// record "this mask's latest writer has been enqueued" on the filter stream
+static int mask_mark_ready(mvdb_mask* m) {
+    if (!m->ready) CU_OK(cudaEventCreateWithFlags(&m->ready, cudaEventDisableTiming));
+    CU_OK(cudaEventRecord(m->ready, m->ix->filter_stream));
+    return MVDB_OK;
+}
+// make `st` wait for the kernels that produced the mask (no host synchronisation)
+static int mask_wait(const mvdb_mask* m, cudaStream_t st) {
+    if (m && m->ready) CU_OK(cudaStreamWaitEvent(st, m->ready, 0));
+    return MVDB_OK;
+}
+
 // One host-buffer search on its own workspace: stage query (+mask), run, copy results back.
 static int search_host_direct(mvdb_index* ix, const float* q, int64_t nq, int64_t k, const uint8_t* mask,
                               uint64_t mask_rows, int normalize_queries, float* D, int64_t* I,
@@ -1664,6 +1683,7 @@ static int search_host_direct(mvdb_index* ix, const float* q, int64_t nq, int64_
     if (handle) {
         mask_dev = handle->dev;      // already resident: no per-query upload
         mask_rows = handle->rows;
+        RC_OK(mask_wait(handle, st));
     } else if (mask) {
         const uint64_t rows = std::min<uint64_t>(mask_rows, ix->ntotal.load(std::memory_order_acquire));
         mask_rows = rows;
@@ -1740,6 +1760,7 @@ static int exec_coalesced(mvdb_index* ix, std::vector<CoalesceReq*>& batch) {
         memcpy(ws->q_pin + i * ix->d, r->q, size_t(ix->d) * 4);
         if (r->handle) {
             qmasks[size_t(i)] = QMaskRef{r->handle->dev, r->handle->words};
+            RC_OK(mask_wait(r->handle, st));
         } else if (r->mask) {
             // rows past the caller's mask_rows are not admissible: zero-filled tail
             uint32_t* dst = ws->mask_pin + size_t(slot) * words;
@@ -1855,7 +1876,8 @@ int mvdb_index_mask_create(mvdb_index* ix, const uint8_t* mask, uint64_t mask_ro
     if (mask_rows & 7) reinterpret_cast<uint8_t*>(host.data())[bytes - 1] &= uint8_t((1u << (mask_rows & 7)) - 1u);
     mvdb_mask* m = new mvdb_mask{ix, nullptr, mask_rows, uint32_t(words)};
     cudaError_t e = cudaMalloc(&m->dev, host.size() * 4);
-    if (e == cudaSuccess) e = cudaMemcpy(m->dev, host.data(), host.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(m->dev, host.data(), host.size() * 4, cudaMemcpyHostToDevice, ix->filter_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ix->filter_stream);   // `host` goes out of scope; the upload is complete
     if (e != cudaSuccess) {
         cudaFree(m->dev);
         delete m;
@@ -1868,7 +1890,8 @@ int mvdb_index_mask_create(mvdb_index* ix, const uint8_t* mask, uint64_t mask_ro
 int mvdb_mask_destroy(mvdb_mask* m) {
     if (!m) return MVDB_OK;
     DeviceGuard guard(m->ix->device);
-    cudaFree(m->dev);
+    cudaFree(m->dev);   // synchronises the device: no filter kernel or search still reads it
+    if (m->ready) cudaEventDestroy(m->ready);
     delete m;
     return MVDB_OK;
 }
@@ -1898,6 +1921,9 @@ int mvdb_column_append(mvdb_column* c, const double* values, const uint8_t* pres
     if (n == 0) return MVDB_OK;
     if (!values || !present) return fail(MVDB_ERR_ARG, "null data");
     ENTER(c->ix);
+    // everything on the filter stream, so that it is ordered with the predicate kernels that read the
+    // column (searches run on non-blocking streams: the legacy default stream orders nothing for them)
+    cudaStream_t fs = c->ix->filter_stream;
     const uint64_t need = c->len + n;
     if (need > c->cap) {
         const uint64_t ncap = align_up(std::max<uint64_t>(need, c->cap * 2), 1024);
@@ -1905,9 +1931,10 @@ int mvdb_column_append(mvdb_column* c, const double* values, const uint8_t* pres
         uint32_t* nh = nullptr;
         CU_OK(cudaMalloc(&nv, ncap * 8));
         cudaError_t e = cudaMalloc(&nh, ncap / 8 + 8);
-        if (e == cudaSuccess) e = cudaMemset(nh, 0, ncap / 8 + 8);
-        if (e == cudaSuccess && c->len) e = cudaMemcpy(nv, c->vals, c->len * 8, cudaMemcpyDeviceToDevice);
-        if (e == cudaSuccess && c->len) e = cudaMemcpy(nh, c->has, (c->len + 31) / 32 * 4, cudaMemcpyDeviceToDevice);
+        if (e == cudaSuccess) e = cudaMemsetAsync(nh, 0, ncap / 8 + 8, fs);
+        if (e == cudaSuccess && c->len) e = cudaMemcpyAsync(nv, c->vals, c->len * 8, cudaMemcpyDeviceToDevice, fs);
+        if (e == cudaSuccess && c->len) e = cudaMemcpyAsync(nh, c->has, (c->len + 31) / 32 * 4, cudaMemcpyDeviceToDevice, fs);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(fs);   // the old buffers are freed below
         if (e != cudaSuccess) {
             cudaFree(nv);
             cudaFree(nh);
@@ -1919,17 +1946,21 @@ int mvdb_column_append(mvdb_column* c, const double* values, const uint8_t* pres
         c->has = nh;
         c->cap = ncap;
     }
-    CU_OK(cudaMemcpy(c->vals + c->len, values, n * 8, cudaMemcpyHostToDevice));
+    CU_OK(cudaMemcpyAsync(c->vals + c->len, values, n * 8, cudaMemcpyHostToDevice, fs));
     // presence bits: merge the partially filled first word on the host
     const uint64_t w0 = c->len / 32, w1 = (need + 31) / 32;
     std::vector<uint32_t> words(size_t(w1 - w0), 0u);
-    if (c->len % 32) CU_OK(cudaMemcpy(words.data(), c->has + w0, 4, cudaMemcpyDeviceToHost));
+    if (c->len % 32) {
+        CU_OK(cudaMemcpyAsync(words.data(), c->has + w0, 4, cudaMemcpyDeviceToHost, fs));
+        CU_OK(cudaStreamSynchronize(fs));
+    }
     for (uint64_t i = 0; i < n; i++)
         if (present[i]) {
             const uint64_t r = c->len + i;
             words[size_t(r / 32 - w0)] |= 1u << (r % 32);
         }
-    CU_OK(cudaMemcpy(c->has + w0, words.data(), words.size() * 4, cudaMemcpyHostToDevice));
+    CU_OK(cudaMemcpyAsync(c->has + w0, words.data(), words.size() * 4, cudaMemcpyHostToDevice, fs));
+    CU_OK(cudaStreamSynchronize(fs));   // the caller's and our host buffers are free again
     c->len = need;
     return MVDB_OK;
 }
@@ -1954,11 +1985,12 @@ int mvdb_mask_from_predicate(mvdb_index* ix, const mvdb_column* c, int op, doubl
     mvdb_mask* m = nullptr;
     RC_OK(new_mask(ix, c->len, &m));
     if (m->words) {
-        predicate_mask_kernel<<<(m->words + 255) / 256, 256>>>(c->vals, c->has, c->len, op, operand, m->dev, m->words);
+        predicate_mask_kernel<<<(m->words + 255) / 256, 256, 0, ix->filter_stream>>>(c->vals, c->has, c->len, op, operand, m->dev,
+                                                                                      m->words);
         LAUNCHED();
     }
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) {
+    if (e != cudaSuccess || mask_mark_ready(m) != MVDB_OK) {
         mvdb_mask_destroy(m);
         return fail(MVDB_ERR_CUDA, "predicate kernel failed: %s", cudaGetErrorString(e));
     }
@@ -1973,8 +2005,12 @@ int mvdb_mask_create_filled(mvdb_index* ix, uint64_t rows, mvdb_mask** out) {
     mvdb_mask* m = nullptr;
     RC_OK(new_mask(ix, rows, &m));
     if (m->words) {
-        fill_mask_kernel<<<(m->words + 255) / 256, 256>>>(m->dev, rows, m->words);
+        fill_mask_kernel<<<(m->words + 255) / 256, 256, 0, ix->filter_stream>>>(m->dev, rows, m->words);
         LAUNCHED();
+    }
+    if (cudaGetLastError() != cudaSuccess || mask_mark_ready(m) != MVDB_OK) {
+        mvdb_mask_destroy(m);
+        return fail(MVDB_ERR_CUDA, "fill kernel failed");
     }
     *out = m;
     return MVDB_OK;
@@ -1985,11 +2021,13 @@ int mvdb_mask_combine(mvdb_mask* dst, const mvdb_mask* src, int how) {
     if (how < 0 || how > 2) return fail(MVDB_ERR_ARG, "bad combine mode");
     ENTER(dst->ix);
     if (dst->words) {
-        combine_mask_kernel<<<(dst->words + 255) / 256, 256>>>(dst->dev, dst->words, src->dev, src->words, how);
+        // src was produced on the same stream (or uploaded synchronously): stream order is enough
+        combine_mask_kernel<<<(dst->words + 255) / 256, 256, 0, dst->ix->filter_stream>>>(dst->dev, dst->words, src->dev, src->words,
+                                                                                           how);
         LAUNCHED();
     }
     CU_OK(cudaGetLastError());
-    return MVDB_OK;
+    return mask_mark_ready(dst);
 }
 
 int mvdb_mask_count(const mvdb_mask* m, uint64_t* count) {
@@ -2000,18 +2038,20 @@ int mvdb_mask_count(const mvdb_mask* m, uint64_t* count) {
     std::lock_guard<std::mutex> cg(ix->count_mu);
     if (!ix->count_dev) CU_OK(cudaMalloc(&ix->count_dev, 8));
     unsigned long long* dev = ix->count_dev;
-    cudaError_t e = cudaMemset(dev, 0, 8);
+    cudaStream_t fs = ix->filter_stream;   // behind the kernels that built the mask
+    cudaError_t e = cudaMemsetAsync(dev, 0, 8, fs);
     // rows of the mask that are still live; the live bitmask covers at least as many words
     const uint64_t nt = ix->ntotal.load(std::memory_order_acquire);
     const uint32_t words = uint32_t(std::min<uint64_t>(m->words, (nt + 31) / 32));
     if (e == cudaSuccess && words) {
         const uint32_t* live = ix->ndead.load(std::memory_order_acquire) ? static_cast<const uint32_t*>(ix->live.ptr()) : nullptr;
-        count_mask_kernel<<<(words + 255) / 256, 256>>>(m->dev, live, words, dev);
+        count_mask_kernel<<<(words + 255) / 256, 256, 0, fs>>>(m->dev, live, words, dev);
         LAUNCHED();
         e = cudaGetLastError();
     }
     unsigned long long v = 0;
-    if (e == cudaSuccess) e = cudaMemcpy(&v, dev, 8, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&v, dev, 8, cudaMemcpyDeviceToHost, fs);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(fs);
     if (e != cudaSuccess) return fail(MVDB_ERR_CUDA, "mask count failed: %s", cudaGetErrorString(e));
     *count = v;
     return MVDB_OK;

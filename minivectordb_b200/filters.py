@@ -229,7 +229,16 @@ class FilterIndex:
         self.columns: Dict[str, Column] = {}
 
     def clear(self) -> None:
+        self.close_device()
         self.columns = {}
+
+    def close_device(self) -> None:
+        """Release the HBM mirrors of the columns now (they point into their index, which the
+        caller is about to destroy or compact)."""
+        for col in self.columns.values():
+            dev, col._dev, col._dev_rows = col._dev, None, 0
+            if dev is not None:
+                dev.close()
 
     @staticmethod
     def new_column() -> "Column":

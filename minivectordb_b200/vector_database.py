@@ -65,8 +65,8 @@ class VectorDatabase(GpuStore):
             self._flush()  # the reference builds its index at load time (VDB:39-40)
 
     def persist_to_disk(self):
-        emb = self._materialize() if self._ever_stored else None
-        with self.lock:
+        with self.lock:   # one lock for the matrix AND the id views: a concurrent store cannot fall between them
+            emb = self._materialize_locked() if self._ever_stored else None
             id_map, inverse_id_map, metadata, _ = self._build_views()
             data = {'embeddings': emb, 'metadata': metadata, 'id_map': id_map,
                     'inverse_id_map': inverse_id_map, 'inverted_index': self.inverted_index}

@@ -89,3 +89,56 @@ def test_compaction_keeps_everything_consistent(classes, tmp_path, monkeypatch):
     db.store_embedding("new", embs[0], {"g": 9})
     assert db.find_most_similar(embs[0], k=1)[0] == ("new",)
     assert len(db.find_most_similar(embs[0], k=999, metadata_filter={"g": {"$lt": 4}})[0]) == 100
+
+
+def test_batch_buffer_can_be_reused_after_store(classes, tmp_path):
+    """The reference copies on ingest (np.array + np.vstack, ref vector_database.py:26, 107): a caller
+    that refills its batch buffer between two stores must not change rows already stored."""
+    import numpy as np
+    for cls, kw in ((classes[0], dict(storage_file=str(tmp_path / "reuse.pkl"))),
+                    (classes[1], dict(storage_dir=str(tmp_path / "reuse_shards")))):
+        db = cls(**kw)
+        buf = np.zeros((2, 4), dtype=np.float32)
+        buf[0, 0] = buf[1, 1] = 1.0
+        db.store_embeddings_batch(["a", "b"], buf)
+        buf[:] = 0.0
+        buf[0, 2] = buf[1, 3] = 1.0
+        db.store_embeddings_batch(["c", "d"], buf)
+        buf[:] = 7.0   # ... and scribbled over before the first search flushes anything
+        assert np.array_equal(db.get_vector("a"), np.array([1, 0, 0, 0], dtype=np.float32))
+        ids, dist, _ = db.find_most_similar(np.array([1, 0, 0, 0], dtype=np.float32), k=1)
+        assert ids == ("a",) and abs(dist[0] - 1.0) < 1e-6
+        ids, dist, _ = db.find_most_similar(np.array([0, 0, 0, 1], dtype=np.float32), k=1)
+        assert ids == ("d",) and abs(dist[0] - 1.0) < 1e-6
+
+
+def test_persist_is_consistent_under_concurrent_stores(classes, tmp_path):
+    """persist_to_disk builds the matrix and the id views under ONE lock (ref vector_database.py:
+    538-548): a pickle written while another thread stores rows always reloads."""
+    import pickle
+    import threading
+    import numpy as np
+    path = str(tmp_path / "race.pkl")
+    db = classes[0](storage_file=path)
+    rng = np.random.default_rng(1)
+    db.store_embeddings_batch(list(range(50)), rng.standard_normal((50, 8)).astype(np.float32))
+    stop = threading.Event()
+
+    def writer():
+        i = 1000
+        while not stop.is_set():
+            db.store_embedding(i, rng.standard_normal(8).astype(np.float32), {"w": i})
+            i += 1
+
+    t = threading.Thread(target=writer)
+    t.start()
+    try:
+        for _ in range(30):
+            db.persist_to_disk()
+            data = pickle.load(open(path, "rb"))
+            n = data["embeddings"].shape[0]
+            assert n == len(data["id_map"]) == len(data["inverse_id_map"]) == len(data["metadata"])
+    finally:
+        stop.set()
+        t.join()
+    assert len(classes[0](storage_file=path).id_map) == n
