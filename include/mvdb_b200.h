@@ -252,12 +252,39 @@ int mvdb_exchange_ipc_handle(mvdb_exchange* x, void* handle64);
  * int64 global row numbers of each rank's row 0. */
 int mvdb_exchange_connect(mvdb_exchange* x, const void* handles, const int64_t* offsets);
 int mvdb_exchange_set_offsets(mvdb_exchange* x, const int64_t* offsets);
-/* *timed_out = 1 if a kernel gave up waiting for a peer (peer died). */
+/* Same-process flavour of connect: xs[0..n-1] are the exchange objects of ranks 0..n-1, all created in
+ * THIS process (one per device); peers are reached through cudaDeviceEnablePeerAccess, no IPC handles. */
+int mvdb_exchange_connect_local(mvdb_exchange* const* xs, int n, const int64_t* offsets);
+/* Options: "timeout_ms" (default 2000) -- how long a search's last CTA waits for a peer's top-k
+ * before it gives up and raises the status flag. */
+int mvdb_exchange_set_option(mvdb_exchange* x, const char* name, int64_t value);
+/* *timed_out = 1 if a kernel gave up waiting for a peer (peer died or never launched); the results of
+ * that search are undefined.  The flag lives in pinned host memory: valid after any synchronise that
+ * covers the search, reading it costs no CUDA call. */
 int mvdb_exchange_status(mvdb_exchange* x, int* timed_out);
 int mvdb_exchange_destroy(mvdb_exchange* x);
 int mvdb_index_search_exchange(mvdb_index* ix, mvdb_workspace* ws, mvdb_exchange* x, const float* q_dev,
                                int64_t nq, int64_t k, const uint32_t* mask_dev, uint64_t mask_rows,
                                int normalize_queries, float* D_dev, int64_t* I_dev, void* stream);
+
+/* ---- shard group: one process, several GPUs ---------------------------------
+ * The reference's ShardedVectorDatabase searches ONE in-memory index over all rows
+ * (sharded_vector_database.py:79-84, 598-662).  A group is that index spread over the GPUs of one
+ * box: shards[i] holds a part of the rows on its own device, and mvdb_group_search answers a query
+ * over all of them -- one host thread stages the query (and each shard's filter) to every device,
+ * launches every device's scan, the scans' last CTAs exchange the per-shard top-k over NVLink and
+ * merge (the same fused kernels as mvdb_index_search_exchange), and the merged list is read back
+ * from shard 0 in one transfer.  Returned labels are (shard << 40) | row-of-that-shard; exact score
+ * ties are ordered by (shard, row).  masks[i] / host_masks[i] (either may be NULL, per shard or as
+ * a whole) filter shard i as in mvdb_index_search_with_mask / mvdb_index_search.  k <= 128.
+ * Searches on one group are serialised.  The shards stay usable on their own (add / remove). */
+typedef struct mvdb_group mvdb_group;
+int mvdb_group_create(mvdb_index* const* shards, int n, mvdb_group** out);
+int mvdb_group_destroy(mvdb_group* g);
+int mvdb_group_set_option(mvdb_group* g, const char* name, int64_t value);   /* forwarded to every exchange */
+int mvdb_group_search(mvdb_group* g, const float* q, int64_t nq, int64_t k, const mvdb_mask* const* masks,
+                      const uint8_t* const* host_masks, const uint64_t* host_mask_rows,
+                      int normalize_queries, float* D, int64_t* I);
 
 /* Test hook: the raw bf16 tensor-core scores of q[nq,d] against every stored row
  * (out[nq][ntotal], host).  Exists so that the tcgen05 GEMM can be validated

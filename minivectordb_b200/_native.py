@@ -39,6 +39,8 @@ EXPORTS = [
     "mvdb_index_mask_create", "mvdb_mask_destroy", "mvdb_index_search_with_mask",
     "mvdb_column_create", "mvdb_column_destroy", "mvdb_column_append", "mvdb_mask_from_predicate",
     "mvdb_mask_create_filled", "mvdb_mask_combine", "mvdb_mask_count", "mvdb_debug_read_trace", "mvdb_debug_read_gemm_prof",
+    "mvdb_exchange_connect_local", "mvdb_exchange_set_option",
+    "mvdb_group_create", "mvdb_group_destroy", "mvdb_group_set_option", "mvdb_group_search",
 ]
 
 
@@ -148,6 +150,12 @@ def lib():
             "mvdb_debug_read_trace": (i, [c_vp, c_vp]),
             "mvdb_debug_read_gemm_prof": (i, [c_vp, c_vp, ctypes.c_int]),
             "mvdb_index_search_exchange": (i, [c_vp, c_vp, c_vp, c_vp, i64, i64, c_vp, u64, i, c_vp, c_vp, c_vp]),
+            "mvdb_exchange_connect_local": (i, [c_vp, i, c_vp]),
+            "mvdb_exchange_set_option": (i, [c_vp, ctypes.c_char_p, i64]),
+            "mvdb_group_create": (i, [c_vp, i, ctypes.POINTER(c_vp)]),
+            "mvdb_group_destroy": (i, [c_vp]),
+            "mvdb_group_set_option": (i, [c_vp, ctypes.c_char_p, i64]),
+            "mvdb_group_search": (i, [c_vp, c_vp, i64, i64, c_vp, c_vp, c_vp, i, c_vp, c_vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)

@@ -119,6 +119,7 @@ class GpuStore:
         self._mask_cache = OrderedDict()  # filter repr -> (version, count, per-partition device-resident masks)
         self._mask_seen = OrderedDict()   # filter repr -> version at which it was last evaluated
         self._embeddings_changed = False  # kept for API parity (VDB:18); True while rows wait on the host
+        self._group = None                # several partitions: the engines searched as ONE index (fused NVLink exchange)
 
     # ------------------------------------------------------------------ views
     def _live_gids(self) -> np.ndarray:
@@ -305,6 +306,16 @@ class GpuStore:
     # ------------------------------------------------------------------ flush
     def _flush(self) -> None:
         """Move staged rows / tombstones to the GPU.  Caller holds the lock."""
+        if len(self._parts) > 1 and self._group is None and any(p.pending for p in self._parts):
+            # several GPUs: every partition gets its engine now and the engines are tied into one shard
+            # group -- one host thread launches every device's scan and the scans exchange and merge
+            # their top-k over NVLink inside the kernel (no thread pool, no Python merge)
+            for part in self._parts:
+                if part.engine is None:
+                    part.engine = FlatIPEngine(self.embedding_size, device=part.device)
+            group_cls = getattr(type(self._parts[0].engine), "group_class", None)
+            if group_cls is not None:
+                self._group = group_cls([p.engine for p in self._parts])
         for part in self._parts:
             if part.pending:
                 if part.engine is None:
@@ -434,7 +445,22 @@ class GpuStore:
         try:
             search_k = min(int(k), count)  # VDB:489-492
             cands = []
-            if len(jobs) > 1 and self._n_live * (self.embedding_size or 1) * 4 >= self.PARALLEL_PARTS_BYTES:
+            results = None
+            if self._group is not None and search_k <= self._group.K_MAX:
+                # ONE call: every device scans its partition at the same time, the per-device top-k are exchanged
+                # over NVLink and merged by the scan kernels themselves; (shard, row) pairs come back merged
+                masks = None
+                if any(j[2] is not None for j in jobs):
+                    masks = [np.zeros(0, dtype=bool)] * len(self._parts)   # partitions without a job hold nothing admissible
+                    for part, gids, handle in jobs:
+                        masks[self._parts.index(part)] = handle
+                D, S, R = self._group.search(q, search_k, masks=masks, normalize=True)
+                for dist, s_, r_ in zip(D[0], S[0], R[0]):
+                    if s_ >= 0:
+                        cands.append((dist, self._parts[int(s_)].gids[int(r_)]))
+                cands.sort(key=lambda c: (-c[0], c[1]))  # exact ties: insertion order, as one index would return them
+                results, jobs = [], []
+            elif len(jobs) > 1 and self._n_live * (self.embedding_size or 1) * 4 >= self.PARALLEL_PARTS_BYTES:
                 # partitions live on different GPUs: scan them at the same time (the C ABI releases the GIL);
                 # below ~64 MB the thread hand-off costs more than the scans
                 if self._pool is None:
@@ -443,12 +469,13 @@ class GpuStore:
                 results = list(self._pool.map(lambda j: j[0].engine.search(q, search_k, mask=j[2], normalize=True), jobs))
             else:
                 results = [part.engine.search(q, search_k, mask=handle, normalize=True) for part, gids, handle in jobs]
+            n_jobs = len(jobs)
             for (part, gids, handle), (D, I) in zip(jobs, results):
                 for slot, dist in zip(I[0], D[0]):
                     if slot == -1:
                         continue  # VDB:500
                     cands.append((dist, gids[slot]))
-            if len(jobs) > 1:
+            if n_jobs > 1:
                 cands.sort(key=lambda c: (-c[0], c[1]))  # score desc, insertion order on exact ties
                 cands = cands[:search_k]
             found = [(g_uid[g], dist, g_meta[g]) for dist, g in cands if g_live[g]]
@@ -476,6 +503,9 @@ class GpuStore:
         self._mask_cache.clear()
         self._mask_seen.clear()
         self._filters.close_device()
+        if self._group is not None:
+            self._group.close()
+            self._group = None
         for part in self._parts:
             if part.engine is not None:
                 part.engine.close()

@@ -436,9 +436,12 @@ struct mvdb_exchange {
     void* peer_base[kMaxWorld] = {};
     XchgDev host = {};
     XchgDev* dev = nullptr;
-    unsigned int* status = nullptr;
+    unsigned int* status = nullptr;        // pinned, mapped host word written by the kernel on a peer timeout
+    unsigned int* status_dev = nullptr;    // its device alias
+    uint64_t timeout_ns = 2000000000ull;   // option "timeout_ms" (default 2 s)
     uint64_t seq = 0;
     bool connected = false;
+    bool local_peers = false;              // connected through same-process peer access (nothing to unmap)
 };
 
 struct DeviceGuard {
@@ -2107,12 +2110,15 @@ int mvdb_exchange_create(int device, int rank, int world, int k_max, int nq_max,
     cudaError_t e = cudaMalloc(&x->local, words * 8);
     if (e == cudaSuccess) e = cudaMemset(x->local, 0, words * 8);
     if (e == cudaSuccess) e = cudaMalloc(&x->dev, sizeof(XchgDev));
-    if (e == cudaSuccess) e = cudaMalloc(&x->status, sizeof(unsigned int));
-    if (e == cudaSuccess) e = cudaMemset(x->status, 0, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&x->status), sizeof(unsigned int), cudaHostAllocMapped);
+    if (e == cudaSuccess) {
+        *x->status = 0u;
+        e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&x->status_dev), x->status, 0);
+    }
     if (e != cudaSuccess) {
         cudaFree(x->local);
         cudaFree(x->dev);
-        cudaFree(x->status);
+        if (x->status) cudaFreeHost(x->status);
         delete x;
         return fail(MVDB_ERR_CUDA, "exchange allocation failed: %s", cudaGetErrorString(e));
     }
@@ -2155,10 +2161,63 @@ int mvdb_exchange_connect(mvdb_exchange* x, const void* handles, const int64_t* 
     x->host.rank = x->rank;
     x->host.k_max = x->k_max;
     x->host.nq_max = x->nq_max;
-    x->host.status = x->status;
+    x->host.status = x->status_dev;
+    x->host.timeout_ns = x->timeout_ns;
     RC_OK(exchange_upload(x));
     x->connected = true;
     return MVDB_OK;
+}
+
+/* Same-process flavour: the `n` exchange objects (ranks 0..n-1, one per device) live in THIS process, so
+ * the peers' buffers are reached through cudaDeviceEnablePeerAccess instead of CUDA IPC handles. */
+int mvdb_exchange_connect_local(mvdb_exchange* const* xs, int n, const int64_t* offsets) {
+    if (!xs || !offsets || n < 1 || n > kMaxWorld) return fail(MVDB_ERR_ARG, "bad arguments");
+    for (int i = 0; i < n; i++)
+        if (!xs[i] || xs[i]->world != n || xs[i]->rank != i) return fail(MVDB_ERR_ARG, "exchange %d is not rank %d of %d", i, i, n);
+    for (int i = 0; i < n; i++) {
+        mvdb_exchange* x = xs[i];
+        DeviceGuard guard(x->device);
+        if (!guard.ok) return fail(MVDB_ERR_CUDA, "cudaSetDevice(%d) failed", x->device);
+        for (int p = 0; p < n; p++) {
+            if (p != i && xs[p]->device != x->device) {
+                int can = 0;
+                CU_OK(cudaDeviceCanAccessPeer(&can, x->device, xs[p]->device));
+                if (!can) return fail(MVDB_ERR_STATE, "device %d cannot access device %d", x->device, xs[p]->device);
+                cudaError_t e = cudaDeviceEnablePeerAccess(xs[p]->device, 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) (void)cudaGetLastError();
+                else if (e != cudaSuccess) return fail(MVDB_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d) failed: %s", xs[p]->device, cudaGetErrorString(e));
+            }
+            x->host.recv[p] = xs[p]->local;
+            x->host.flags[p] = xs[p]->local + xs[p]->recv_words;
+            x->host.offsets[p] = offsets[p];
+        }
+        x->host.world = n;
+        x->host.rank = i;
+        x->host.k_max = x->k_max;
+        x->host.nq_max = x->nq_max;
+        x->host.status = x->status_dev;
+        x->host.timeout_ns = x->timeout_ns;
+        RC_OK(exchange_upload(x));
+        x->connected = true;
+        x->local_peers = true;
+    }
+    return MVDB_OK;
+}
+
+int mvdb_exchange_set_option(mvdb_exchange* x, const char* name, int64_t value) {
+    if (!x || !name) return fail(MVDB_ERR_ARG, "null argument");
+    if (std::string(name) == "timeout_ms") {
+        if (value < 1 || value > 600000) return fail(MVDB_ERR_ARG, "timeout_ms must be 1..600000");
+        x->timeout_ns = uint64_t(value) * 1000000ull;
+        x->host.timeout_ns = x->timeout_ns;
+        if (x->connected) {
+            DeviceGuard guard(x->device);
+            CU_OK(cudaDeviceSynchronize());
+            return exchange_upload(x);
+        }
+        return MVDB_OK;
+    }
+    return fail(MVDB_ERR_ARG, "unknown exchange option '%s'", name);
 }
 
 int mvdb_exchange_set_offsets(mvdb_exchange* x, const int64_t* offsets) {
@@ -2171,10 +2230,8 @@ int mvdb_exchange_set_offsets(mvdb_exchange* x, const int64_t* offsets) {
 
 int mvdb_exchange_status(mvdb_exchange* x, int* timed_out) {
     if (!x || !timed_out) return fail(MVDB_ERR_ARG, "null argument");
-    DeviceGuard guard(x->device);
-    unsigned int v = 0;
-    CU_OK(cudaMemcpy(&v, x->status, sizeof v, cudaMemcpyDeviceToHost));
-    *timed_out = int(v);
+    // the word lives in pinned host memory: valid after any synchronise that covered the search, no CUDA call
+    *timed_out = int(*reinterpret_cast<volatile unsigned int*>(x->status));
     return MVDB_OK;
 }
 
@@ -2186,7 +2243,7 @@ int mvdb_exchange_destroy(mvdb_exchange* x) {
         if (x->peer_base[p]) cudaIpcCloseMemHandle(x->peer_base[p]);
     cudaFree(x->local);
     cudaFree(x->dev);
-    cudaFree(x->status);
+    if (x->status) cudaFreeHost(x->status);
     delete x;
     return MVDB_OK;
 }
@@ -2205,6 +2262,198 @@ int mvdb_index_search_exchange(mvdb_index* ix, mvdb_workspace* ws, mvdb_exchange
                               static_cast<cudaStream_t>(stream), x);
     tl_allow_pdl = false;
     return rc;
+}
+
+// ---------------------------------------------------------------------------
+// Shard group: the row shards of ONE database on several GPUs of one box, driven by ONE process.
+// Stands in for the single in-memory index of the reference's ShardedVectorDatabase
+// (ref sharded_vector_database.py:79-84, 598-662) when `devices=[...]` spreads it over GPUs.
+// One host thread stages the query (+ each shard's filter) to every device, launches every
+// device's scan and only then waits: the scans run concurrently, their last CTAs exchange the
+// per-shard top-k over NVLink (peer stores, same kernels as the one-process-per-GPU path) and
+// every device ends with the merged global list; the host fetches it from shard 0 in one transfer.
+// ---------------------------------------------------------------------------
+struct mvdb_group {
+    int n = 0;
+    std::vector<mvdb_index*> shards;
+    std::vector<mvdb_workspace*> ws;
+    std::vector<mvdb_exchange*> xch;
+    std::vector<float*> D_dev;        // per shard: [nq_cap * k_cap] merged distances (every shard gets the same)
+    std::vector<int64_t*> I_dev;
+    size_t out_cap = 0;
+    std::mutex mu;                    // all shards must see the same sequence of searches
+};
+
+int mvdb_group_create(mvdb_index* const* shards, int n, mvdb_group** out) {
+    if (!out) return fail(MVDB_ERR_ARG, "null out");
+    *out = nullptr;
+    if (!shards || n < 1 || n > kMaxWorld) return fail(MVDB_ERR_ARG, "need 1..%d shards", kMaxWorld);
+    for (int i = 0; i < n; i++) {
+        if (!shards[i]) return fail(MVDB_ERR_ARG, "null shard");
+        if (shards[i]->d != shards[0]->d) return fail(MVDB_ERR_ARG, "shards differ in dimension");
+        for (int j = 0; j < i; j++)
+            if (shards[j] == shards[i]) return fail(MVDB_ERR_ARG, "shard %d listed twice", i);
+        // several shards MAY share a device (tests on a one-GPU box): a scan whose last CTA waits for a peer
+        // holds one SM only, so the peer's scan on the same device still runs
+    }
+    mvdb_group* g = new mvdb_group();
+    g->n = n;
+    g->shards.assign(shards, shards + n);
+    g->ws.assign(size_t(n), nullptr);
+    g->xch.assign(size_t(n), nullptr);
+    g->D_dev.assign(size_t(n), nullptr);
+    g->I_dev.assign(size_t(n), nullptr);
+    int rc = MVDB_OK;
+    std::vector<int64_t> offs(size_t(n), 0);
+    for (int i = 0; i < n && rc == MVDB_OK; i++) {
+        offs[size_t(i)] = int64_t(i) << 40;   // label = shard << 40 | row of the shard (stable under inserts)
+        DeviceGuard guard(shards[i]->device);
+        rc = ws_new(shards[i], &g->ws[size_t(i)]);
+        if (rc == MVDB_OK) rc = mvdb_exchange_create(shards[i]->device, i, n, 128, 8, &g->xch[size_t(i)]);
+    }
+    if (rc == MVDB_OK) rc = mvdb_exchange_connect_local(g->xch.data(), n, offs.data());
+    if (rc != MVDB_OK) {
+        std::string keep = g_err;
+        mvdb_group_destroy(g);
+        g_err = keep;
+        return rc;
+    }
+    *out = g;
+    return MVDB_OK;
+}
+
+int mvdb_group_destroy(mvdb_group* g) {
+    if (!g) return MVDB_OK;
+    // nobody unmaps while a peer may still write: drain every device first
+    for (int i = 0; i < g->n; i++) {
+        DeviceGuard guard(g->shards[size_t(i)]->device);
+        cudaDeviceSynchronize();
+    }
+    for (int i = 0; i < g->n; i++) {
+        DeviceGuard guard(g->shards[size_t(i)]->device);
+        if (g->xch[size_t(i)]) mvdb_exchange_destroy(g->xch[size_t(i)]);
+        if (g->ws[size_t(i)]) ws_free(g->ws[size_t(i)]);
+        cudaFree(g->D_dev[size_t(i)]);
+        cudaFree(g->I_dev[size_t(i)]);
+    }
+    delete g;
+    return MVDB_OK;
+}
+
+int mvdb_group_set_option(mvdb_group* g, const char* name, int64_t value) {
+    if (!g || !name) return fail(MVDB_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(g->mu);
+    for (int i = 0; i < g->n; i++) RC_OK(mvdb_exchange_set_option(g->xch[size_t(i)], name, value));
+    return MVDB_OK;
+}
+
+int mvdb_group_search(mvdb_group* g, const float* q, int64_t nq, int64_t k, const mvdb_mask* const* masks,
+                      const uint8_t* const* host_masks, const uint64_t* host_mask_rows, int normalize_queries,
+                      float* D, int64_t* I) {
+    if (!g) return fail(MVDB_ERR_ARG, "null group");
+    if (nq < 0 || k <= 0) return fail(MVDB_ERR_ARG, "need nq >= 0 and k > 0 (got nq=%lld k=%lld)", (long long)nq, (long long)k);
+    if (nq == 0) return MVDB_OK;
+    if (!q || !D || !I) return fail(MVDB_ERR_ARG, "null buffer");
+    if (k > 128) return fail(MVDB_ERR_ARG, "the fused exchange supports k <= 128 (got %lld)", (long long)k);
+    const int d = g->shards[0]->d;
+    const size_t qn = size_t(nq) * d, on = size_t(nq) * k;
+    std::lock_guard<std::mutex> lk(g->mu);
+    int cur_dev = -1;
+    cudaGetDevice(&cur_dev);
+    struct Restore {
+        int dev;
+        ~Restore() { if (dev >= 0) cudaSetDevice(dev); }
+    } restore{cur_dev};
+    // shared locks of every shard for the whole search: rows do not move under any of the scans
+    std::vector<std::shared_lock<std::shared_mutex>> locks;
+    locks.reserve(size_t(g->n));
+    for (int s = 0; s < g->n; s++) locks.emplace_back(g->shards[size_t(s)]->move_mu);
+    // phase 1: everything that can fail or block (allocations, staging) BEFORE the first launch -- once one
+    // device's scan is in flight every other device must launch too, or the first one waits for its timeout
+    std::vector<const uint32_t*> mask_dev(size_t(g->n), nullptr);
+    std::vector<uint64_t> mask_rows(size_t(g->n), 0);
+    std::vector<const float*> q_dev(size_t(g->n), nullptr);
+    for (int s = 0; s < g->n; s++) {
+        mvdb_index* ix = g->shards[size_t(s)];
+        mvdb_workspace* ws = g->ws[size_t(s)];
+        CU_OK(cudaSetDevice(ix->device));
+        if (on > g->out_cap || !g->D_dev[size_t(s)]) {
+            cudaFree(g->D_dev[size_t(s)]);
+            cudaFree(g->I_dev[size_t(s)]);
+            g->D_dev[size_t(s)] = nullptr;
+            g->I_dev[size_t(s)] = nullptr;
+            CU_OK(cudaMalloc(&g->D_dev[size_t(s)], std::max(on, g->out_cap) * 4));
+            CU_OK(cudaMalloc(&g->I_dev[size_t(s)], std::max(on, g->out_cap) * 8));
+        }
+        RC_OK(ws_scratch(ws));
+        const mvdb_mask* h = masks ? masks[s] : nullptr;
+        const uint8_t* hm = (!h && host_masks) ? host_masks[s] : nullptr;
+        if (h && h->ix != ix) return fail(MVDB_ERR_ARG, "mask handle %d belongs to another index", s);
+        size_t words = 0, q_at = 0;
+        if (hm) {
+            mask_rows[size_t(s)] = std::min<uint64_t>(host_mask_rows ? host_mask_rows[s] : 0, ix->ntotal.load(std::memory_order_acquire));
+            words = (mask_rows[size_t(s)] + 31) / 32;
+            q_at = align_up(words * 4, 128) / 4;
+        }
+        // one transfer per shard: [filter words | pad | queries]
+        RC_OK(grow_dev(&ws->mask_dev, &ws->mask_cap, q_at + qn));
+        RC_OK(grow_pin(&ws->mask_pin, &ws->mask_pin_cap, q_at + qn));
+        if (hm && words) {
+            const size_t bytes = (mask_rows[size_t(s)] + 7) / 8;
+            ws->mask_pin[words - 1] = 0;
+            memcpy(ws->mask_pin, hm, bytes);
+            if (mask_rows[size_t(s)] & 7) reinterpret_cast<uint8_t*>(ws->mask_pin)[bytes - 1] &= uint8_t((1u << (mask_rows[size_t(s)] & 7)) - 1u);
+        }
+        memcpy(ws->mask_pin + q_at, q, qn * 4);
+        q_dev[size_t(s)] = reinterpret_cast<const float*>(ws->mask_dev + q_at);
+        if (hm) mask_dev[size_t(s)] = ws->mask_dev;
+        if (h) {
+            mask_dev[size_t(s)] = h->dev;
+            mask_rows[size_t(s)] = h->rows;
+        }
+    }
+    if (on > g->out_cap) g->out_cap = on;
+    // phase 2: copies and launches, device after device; nothing here waits for the GPU
+    int rc = MVDB_OK;
+    for (int s = 0; s < g->n && rc == MVDB_OK; s++) {
+        mvdb_index* ix = g->shards[size_t(s)];
+        mvdb_workspace* ws = g->ws[size_t(s)];
+        cudaError_t e = cudaSetDevice(ix->device);
+        const size_t q_at = size_t(reinterpret_cast<const uint32_t*>(q_dev[size_t(s)]) - ws->mask_dev);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ws->mask_dev, ws->mask_pin, (q_at + qn) * 4, cudaMemcpyHostToDevice, ws->stream);
+        if (e != cudaSuccess) {
+            rc = fail(MVDB_ERR_CUDA, "staging for shard %d failed: %s", s, cudaGetErrorString(e));
+            break;
+        }
+        if (masks && masks[s]) rc = mask_wait(masks[s], ws->stream);
+        if (rc == MVDB_OK)
+            rc = run_search(ix, ws, q_dev[size_t(s)], nq, k, mask_dev[size_t(s)], mask_rows[size_t(s)], normalize_queries, 0,
+                            g->D_dev[size_t(s)], g->I_dev[size_t(s)], ws->stream, g->xch[size_t(s)]);
+    }
+    // phase 3: the merged list is on every device; read it from shard 0 ([labels | distances], one sync)
+    mvdb_workspace* ws0 = g->ws[0];
+    cudaSetDevice(g->shards[0]->device);
+    if (rc == MVDB_OK) {
+        rc = grow_pin(&ws0->I_pin, &ws0->I_pin_cap, on + (on + 1) / 2);
+        if (rc == MVDB_OK) {
+            cudaError_t e = cudaMemcpyAsync(ws0->I_pin, g->I_dev[0], on * 8, cudaMemcpyDeviceToHost, ws0->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(ws0->I_pin + on, g->D_dev[0], on * 4, cudaMemcpyDeviceToHost, ws0->stream);
+            if (e != cudaSuccess) rc = fail(MVDB_ERR_CUDA, "result copy failed: %s", cudaGetErrorString(e));
+        }
+    }
+    // always drain every shard's stream: a failed launch on one device leaves the others waiting for their timeout
+    for (int s = 0; s < g->n; s++) {
+        cudaSetDevice(g->shards[size_t(s)]->device);
+        cudaError_t e = cudaStreamSynchronize(g->ws[size_t(s)]->stream);
+        if (e != cudaSuccess && rc == MVDB_OK) rc = fail(MVDB_ERR_CUDA, "shard %d failed: %s", s, cudaGetErrorString(e));
+    }
+    if (rc != MVDB_OK) return rc;
+    for (int s = 0; s < g->n; s++)
+        if (*reinterpret_cast<volatile unsigned int*>(g->xch[size_t(s)]->status))
+            return fail(MVDB_ERR_STATE, "shard %d gave up waiting for a peer's top-k (exchange timeout)", s);
+    memcpy(I, ws0->I_pin, on * 8);
+    memcpy(D, ws0->I_pin + on, on * 4);
+    return MVDB_OK;
 }
 
 int mvdb_debug_gemm_scores(mvdb_index* ix, const float* q, int64_t nq, float* out) {

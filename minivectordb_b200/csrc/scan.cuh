@@ -83,7 +83,9 @@ struct XchgDev {
     uint64_t* flags[kMaxWorld];   // flags[p] = rank p's flag array (peer-mapped)
     int64_t offsets[kMaxWorld];   // global row number of rank p's row 0
     int world, rank, k_max, nq_max;
-    unsigned int* status;         // local: set to 1 if a wait timed out
+    unsigned int* status;         // pinned host memory (mapped): set to 1 if a wait timed out -- the host reads it
+                                  // after every synchronise without a CUDA call
+    uint64_t timeout_ns;          // how long the last CTA waits for a peer's flag before giving up
 };
 
 __device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
@@ -150,7 +152,8 @@ __device__ __forceinline__ void xchg_merge(const XchgDev* x, uint64_t seq, int q
 }
 
 // flags: publish `seq` to every rank, then wait for every rank's `seq` in my own flags.
-// Called by one warp.  Gives up after ~10 s (a peer died) and raises x->status.
+// Called by one warp.  Gives up after x->timeout_ns (a peer died or never launched) and raises
+// x->status; the results of that search are then garbage and the host raises an error.
 __device__ __forceinline__ void xchg_publish_and_wait(const XchgDev* x, uint64_t seq, int lane) {
     const int par = int(seq & 1);
     if (lane < x->world) st_release_sys(x->flags[lane] + par * x->world + x->rank, seq);
@@ -159,8 +162,9 @@ __device__ __forceinline__ void xchg_publish_and_wait(const XchgDev* x, uint64_t
         const uint64_t t0 = global_timer_ns();
         while (ld_acquire_sys(f) < seq) {
             __nanosleep(200);
-            if (global_timer_ns() - t0 > 10000000000ull) {
-                *x->status = 1u;
+            if (global_timer_ns() - t0 > x->timeout_ns) {
+                *reinterpret_cast<volatile unsigned int*>(x->status) = 1u;
+                __threadfence_system();
                 break;
             }
         }

@@ -37,14 +37,28 @@ from . import _native as N
 from .engine import FlatIPEngine, merge_topk_device
 
 
+class ExchangeTimeout(RuntimeError):
+    """A rank's scan gave up waiting for a peer's top-k (the peer died or never issued the search)."""
+
+
 class RowShardedIndex:
     FUSED_K_MAX = 128
     FUSED_NQ_MAX = 8
+    STABLE_SHIFT = 40      # numbering="stable": label = rank << 40 | row of that rank's shard
 
     def __init__(self, d: int, device: Optional[int] = None, group=None,
-                 engine_factory: Callable[..., FlatIPEngine] = None, host_merge=None, exchange: str = "auto"):
+                 engine_factory: Callable[..., FlatIPEngine] = None, host_merge=None, exchange: str = "auto",
+                 numbering: str = "contiguous"):
         """`engine_factory` / `host_merge` exist for the CPU (gloo) tests of the
-        exchange logic; the product path uses the CUDA engine and merge kernel."""
+        exchange logic; the product path uses the CUDA engine and merge kernel.
+
+        numbering="contiguous": labels are global row numbers, rank r holding rows [offset_r, offset_r + n_r)
+        (a read-mostly index loaded in rank order).  numbering="stable": label = rank << 40 | local row, which
+        never changes when other ranks grow -- the numbering `add_balanced` / `remove` need (ref
+        sharded_vector_database.py:104-132 inserts into the first non-full shard, :206-241 deletes by id)."""
+        if numbering not in ("contiguous", "stable"):
+            raise ValueError("numbering must be 'contiguous' or 'stable'")
+        self.numbering = numbering
         self.d = int(d)
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -123,12 +137,66 @@ class RowShardedIndex:
         else:
             counts.copy_(mine)
         counts = counts.cpu().tolist()
-        self.offsets = [int(sum(counts[:r])) for r in range(self.world)]
+        self.counts = [int(c) for c in counts]
+        if self.numbering == "stable":
+            self.offsets = [r << self.STABLE_SHIFT for r in range(self.world)]
+        else:
+            self.offsets = [int(sum(counts[:r])) for r in range(self.world)]
         self.offset = self.offsets[self.rank]
         self.ntotal_global = int(sum(counts))
         if self._xchg is not None:
             offs = (ctypes.c_int64 * self.world)(*self.offsets)
             N.check(N.lib().mvdb_exchange_set_offsets(self._xchg, offs))
+
+    def add_balanced(self, x, normalize: bool = True) -> np.ndarray:
+        """Collective insert of the SAME block `x` on every rank: the rows go, one by one, to the rank
+        that holds the fewest rows (lowest rank on a draw) -- the multi-GPU reading of the reference's
+        "first shard with room" (ref sharded_vector_database.py:98-132).  Needs numbering="stable".
+        Returns the int64 label of every row of `x` (identical on every rank)."""
+        if self.numbering != "stable":
+            raise ValueError("add_balanced needs numbering='stable' (labels must survive other ranks' growth)")
+        x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, self.d)
+        if not hasattr(self, "counts"):
+            self._sync_offsets()
+        counts = list(self.counts)
+        owner = np.empty(x.shape[0], dtype=np.int64)
+        labels = np.empty(x.shape[0], dtype=np.int64)
+        for i in range(x.shape[0]):   # every rank replays the same deterministic assignment
+            r = min(range(self.world), key=lambda j: (counts[j], j))
+            owner[i] = r
+            labels[i] = (r << self.STABLE_SHIFT) | counts[r]
+            counts[r] += 1
+        mine = x[owner == self.rank]
+        if mine.shape[0]:
+            first = self.engine.add(mine, normalize=normalize)
+            assert first == self.counts[self.rank]
+        self._sync_offsets()
+        assert self.counts == counts, "ranks disagree on the assignment (different blocks passed to add_balanced?)"
+        return labels
+
+    def remove(self, labels) -> None:
+        """Collective delete by label (every rank passes the same labels; the owner tombstones its rows).
+        Unknown or already deleted labels raise on the owning rank, as the reference raises for unknown
+        ids (ref sharded_vector_database.py:213-217)."""
+        labels = np.asarray(labels, dtype=np.int64).reshape(-1)
+        if self.numbering == "stable":
+            mine = labels[(labels >> self.STABLE_SHIFT) == self.rank] & ((1 << self.STABLE_SHIFT) - 1)
+        else:
+            hi = self.offset + self.engine.ntotal
+            mine = labels[(labels >= self.offset) & (labels < hi)] - self.offset
+        if mine.shape[0]:
+            self.engine.remove_rows(mine)
+
+    def set_exchange_timeout(self, ms: int) -> None:
+        """How long a scan waits for a peer's top-k before it gives up (default 2000 ms)."""
+        if self._xchg is not None:
+            N.check(N.lib().mvdb_exchange_set_option(self._xchg, b"timeout_ms", int(ms)))
+
+    def check_exchange(self) -> None:
+        """Raise ExchangeTimeout if any search since the last check gave up on a peer.  Costs one read
+        of pinned host memory; valid after a synchronise that covers the searches."""
+        if self.exchange_timed_out():
+            raise ExchangeTimeout(f"rank {self.rank}: a peer did not deliver its top-k within the exchange timeout")
 
     # -- search ---------------------------------------------------------------------
     def _buffers(self, nq: int, k: int):
@@ -196,6 +264,7 @@ class RowShardedIndex:
                 md = torch.from_numpy(words.view(np.int32)).to(self._tdev)
             D, I = self.search_device(qd, k, md, mrows, normalize)
             torch.cuda.current_stream().synchronize()
+            self.check_exchange()
             return D.cpu().numpy(), I.cpu().numpy()
         # CPU test path: injected engine + injected merge, gloo collectives
         D, I = self.engine.search(q, k, mask=mask_local, normalize=normalize)
@@ -243,6 +312,7 @@ class RowShardedIndex:
         b = self._buffers(nq, k)
         b["out_pin"].copy_(b["out"], non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        self.check_exchange()
         on = nq * k
         host = b["out_pin"].numpy()
         return host[on:].view(np.float32)[:on].reshape(nq, k).copy(), host[:on].reshape(nq, k).copy()

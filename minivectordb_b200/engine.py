@@ -286,6 +286,80 @@ class FlatIPEngine:
             ctypes.c_void_p(stream) if stream else None))
 
 
+class ShardGroup:
+    """Several FlatIPEngines (one per GPU of one box) searched as ONE index by one process
+    (mvdb_group_*): every device scans its shard concurrently, the scans exchange their top-k over
+    NVLink inside the kernel and the merged list comes back from shard 0.  This is what the
+    reference's single in-memory index (ref sharded_vector_database.py:79-84) becomes when
+    `ShardedVectorDatabase(devices=[...])` spreads it over GPUs."""
+
+    SHARD_SHIFT = 40
+    K_MAX = 128
+
+    def __init__(self, engines):
+        self.engines = list(engines)
+        self._h = ctypes.c_void_p()
+        arr = (ctypes.c_void_p * len(self.engines))(*[e.handle for e in self.engines])
+        N.check(N.lib().mvdb_group_create(arr, len(self.engines), ctypes.byref(self._h)))
+
+    def set_option(self, name: str, value: int) -> None:
+        N.check(N.lib().mvdb_group_set_option(self._h, name.encode(), int(value)))
+
+    def search(self, q, k: int, masks=None, normalize: bool = False):
+        """masks: None or one entry per shard -- None, a MaskHandle of that shard's engine, or a bool[n_shard]
+        array.  Returns (D [nq,k], shard [nq,k], row [nq,k]); unfilled slots have shard = row = -1."""
+        d = self.engines[0].d
+        q = _as_f32_2d(q, d, "queries")
+        k = int(k)
+        if k <= 0:
+            raise ValueError("k must be positive")
+        nq, ns = q.shape[0], len(self.engines)
+        D = np.empty((nq, k), dtype=np.float32)
+        I = np.empty((nq, k), dtype=np.int64)
+        hp = mp = rp = None
+        keep = []
+        if masks is not None and any(m is not None for m in masks):
+            handles = (ctypes.c_void_p * ns)()
+            hosts = (ctypes.c_void_p * ns)()
+            rows = (ctypes.c_uint64 * ns)()
+            for i, m in enumerate(masks):
+                if m is None:
+                    continue   # both pointers NULL: this shard is searched unfiltered
+                if isinstance(m, MaskHandle):
+                    handles[i] = m._h.value
+                    keep.append(m)
+                else:
+                    m = np.asarray(m, dtype=bool)
+                    packed = pack_mask(m)
+                    keep.append(packed)
+                    hosts[i] = packed.ctypes.data if packed.size else None
+                    rows[i] = m.shape[0]
+                    if not packed.size:   # an empty mask must still read as "nothing admissible"
+                        z = np.zeros(1, dtype=np.uint8)
+                        keep.append(z)
+                        hosts[i] = z.ctypes.data
+            hp, mp, rp = handles, hosts, rows
+        N.check(N.lib().mvdb_group_search(self._h, q.ctypes.data, nq, k, hp, mp, rp, int(bool(normalize)),
+                                          D.ctypes.data, I.ctypes.data))
+        shard = np.where(I >= 0, I >> self.SHARD_SHIFT, -1)
+        row = np.where(I >= 0, I & ((1 << self.SHARD_SHIFT) - 1), -1)
+        return D, shard, row
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            N.lib().mvdb_group_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+FlatIPEngine.group_class = ShardGroup   # what _store ties several partitions' engines together with
+
+
 class Workspace:
     def __init__(self, engine: FlatIPEngine):
         self._h = ctypes.c_void_p()

@@ -220,6 +220,9 @@ static inline uint64_t mix64(uint64_t z) {
     return z ^ (z >> 31);
 }
 
+/* two clones: AVX-512 (native 64-bit multiplies, 2-3x faster on the hosts that have it) and the
+ * build's baseline; the resolver picks at load time.  Integer arithmetic only: same bits either way. */
+__attribute__((target_clones("arch=x86-64-v4", "default")))
 ORC_API void orc_synth_rows(uint64_t seed, int64_t row0, int64_t n, int64_t d, int dist, float* out) {
 #pragma omp parallel for schedule(static) if (n * d > (1 << 16))
     for (int64_t r = 0; r < n; r++) {

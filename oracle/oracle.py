@@ -189,8 +189,14 @@ def install_as_faiss() -> types.ModuleType:
 DIST_BELL, DIST_UNIFORM = 0, 1
 
 
-def synth_rows(seed: int, row0: int, n: int, d: int, dist: int = DIST_BELL) -> np.ndarray:
-    out = np.empty((n, d), dtype=np.float32)
+def synth_rows(seed: int, row0: int, n: int, d: int, dist: int = DIST_BELL, out=None) -> np.ndarray:
+    """`out`: optional float32 C-contiguous buffer of at least n*d elements to generate into (a
+    streamed scan reuses one chunk buffer instead of faulting in fresh pages per chunk)."""
+    if out is None:
+        out = np.empty((n, d), dtype=np.float32)
+    else:
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.size >= n * d
+        out = out.reshape(-1)[:n * d].reshape(n, d)
     _lib().orc_synth_rows(seed, row0, n, d, dist, _f32p(out))
     return out
 
@@ -279,6 +285,91 @@ def classify_parity(x, q, I_test, D_test, I_ref, D_ref, rel_tol=1e-5, admissible
                 # ||q||*max||x|| to keep the rule meaningful for near-zero scores
                 floor = 0.01 * float(np.linalg.norm(qi)) * xn
                 err = abs(float(D_test[i, j]) - ref) / max(abs(ref), floor, 1e-30)
+                out["max_rel_err"] = max(out["max_rel_err"], err)
+    out["ok"] = out["real_error"] == 0 and out["max_rel_err"] <= rel_tol
+    return out
+
+
+# ---------------------------------------------------------------------------
+# full-size checks: the matrix does not fit (or is not worth keeping) in host memory
+# ---------------------------------------------------------------------------
+
+def merge_topk_lists(parts, k):
+    """Merge per-chunk / per-shard (D [nq,kk], I [nq,kk]) lists whose labels are already global:
+    score descending, label ascending on exact ties (what ONE sequential scan over all rows with a
+    strict '>' keeps); -1 / -FLT_MAX padded."""
+    nq = parts[0][0].shape[0]
+    D = np.full((nq, k), FLT_LOWEST, dtype=np.float32)
+    I = np.full((nq, k), -1, dtype=np.int64)
+    for i in range(nq):
+        d = np.concatenate([p[0][i] for p in parts])
+        l = np.concatenate([p[1][i] for p in parts])
+        keep = l >= 0
+        d, l = d[keep], l[keep]
+        order = np.lexsort((l, -d.astype(np.float64)))[:k]
+        D[i, :len(order)] = d[order]
+        I[i, :len(order)] = l[order]
+    return D, I
+
+
+def search_streamed(make_chunk, n, q, k, chunk_rows=1 << 20, row_offset=0, admissible=None, nthreads=0):
+    """IndexFlatIP.search over a matrix that is PRODUCED chunk by chunk: make_chunk(row0, m) returns
+    rows [row0, row0+m) as float32 [m, d] (already normalised if the index holds normalised rows).
+    Every chunk is scanned by the C restatement and the per-chunk top-k are merged on the host.
+    Labels are row numbers + row_offset.  `admissible` (bool[n]) = the filtered branch."""
+    parts = []
+    for r0 in range(0, n, chunk_rows):
+        m = min(chunk_rows, n - r0)
+        x = make_chunk(r0, m)
+        if admissible is None:
+            D, I = search_flat_ip(x, q, k, nthreads)
+        else:
+            D, I = search_masked(x, admissible[r0:r0 + m], q, k, nthreads)
+        parts.append((D, np.where(I >= 0, I + r0 + row_offset, -1)))
+        if len(parts) >= 8:
+            parts = [merge_topk_lists(parts, k)]
+    if not parts:
+        nq = q.shape[0]
+        return np.full((nq, k), FLT_LOWEST, dtype=np.float32), np.full((nq, k), -1, dtype=np.int64)
+    return merge_topk_lists(parts, k)
+
+
+def classify_parity_lazy(fetch_row, d, q, I_test, D_test, I_ref, D_ref, rel_tol=1e-5, max_norm=1.0,
+                         admissible=None):
+    """`classify_parity` for matrices that are not in memory: fetch_row(label) -> float32 [d] is only
+    called for the two ids of a position-wise mismatch.  `max_norm` = largest row norm (1 for a
+    normalised index).  `admissible(label) -> bool` optional."""
+    q = np.asarray(q, dtype=np.float32)
+    nq, k = I_ref.shape
+    out = dict(positions=int(nq * k), id_equal=0, exact_tie=0, near_tie=0, real_error=0,
+               max_rel_err=0.0, set_equal_queries=0)
+    for i in range(nq):
+        qi = q[i].astype(np.float64)
+        qn = float(np.linalg.norm(qi))
+        bound = 4.0 * d * 2.0 ** -24 * qn * max_norm
+        if set(I_test[i].tolist()) == set(I_ref[i].tolist()):
+            out["set_equal_queries"] += 1
+        for j in range(k):
+            a, b = int(I_test[i, j]), int(I_ref[i, j])
+            if a == b:
+                out["id_equal"] += 1
+            elif a < 0 or b < 0:
+                out["real_error"] += 1
+                continue
+            else:
+                sa = float(np.asarray(fetch_row(a), dtype=np.float64) @ qi)
+                sb = float(np.asarray(fetch_row(b), dtype=np.float64) @ qi)
+                if admissible is not None and not (admissible(a) and admissible(b)):
+                    out["real_error"] += 1
+                elif sa == sb:
+                    out["exact_tie"] += 1
+                elif abs(sa - sb) <= bound:
+                    out["near_tie"] += 1
+                else:
+                    out["real_error"] += 1
+            if a >= 0 and b >= 0:
+                ref = float(D_ref[i, j])
+                err = abs(float(D_test[i, j]) - ref) / max(abs(ref), 0.01 * qn * max_norm, 1e-30)
                 out["max_rel_err"] = max(out["max_rel_err"], err)
     out["ok"] = out["real_error"] == 0 and out["max_rel_err"] <= rel_tol
     return out

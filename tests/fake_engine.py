@@ -62,3 +62,39 @@ class FakeEngine:
 
     def close(self):
         pass
+
+
+class FakeGroup:
+    """CPU stand-in for ShardGroup (mvdb_group_*): every shard searched by the oracle, lists merged by
+    score descending with exact ties ordered by (shard, row) -- the order the fused kernel produces."""
+    K_MAX = 128
+    searches = 0
+
+    def __init__(self, engines):
+        self.engines = list(engines)
+
+    def search(self, q, k, masks=None, normalize=False):
+        FakeGroup.searches += 1
+        q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, self.engines[0].d)
+        nq = q.shape[0]
+        D = np.full((nq, k), O.FLT_LOWEST, dtype=np.float32)
+        S = np.full((nq, k), -1, dtype=np.int64)
+        R = np.full((nq, k), -1, dtype=np.int64)
+        per = []
+        for s, e in enumerate(self.engines):
+            m = None if masks is None else masks[s]
+            if e.ntotal == 0 or (m is not None and len(m) == 0):
+                continue
+            per.append((s, e.search(q, k, mask=m, normalize=normalize)))
+        for i in range(nq):
+            c = [(-float(d), s, int(r)) for s, (Dd, Ii) in per for d, r in zip(Dd[i], Ii[i]) if r >= 0]
+            c.sort()
+            for j, (nd, s, r) in enumerate(c[:k]):
+                D[i, j], S[i, j], R[i, j] = -nd, s, r
+        return D, S, R
+
+    def close(self):
+        pass
+
+
+FakeEngine.group_class = FakeGroup

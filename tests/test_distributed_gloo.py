@@ -70,6 +70,23 @@ def _worker(rank, world, port, ret):
         # a second collective add keeps global numbering contiguous per rank... and is visible
         idx.add(x[:10] if rank == 1 else None, normalize=False)
         assert idx.ntotal_global == n + 10
+        # stable numbering: balanced inserts (rows go to the least-full rank) and deletes by label
+        st = RowShardedIndex(d, engine_factory=FakeEngine, host_merge=merge_numpy, numbering="stable")
+        st.add(x[:7] if rank == 0 else None, normalize=False)        # rank 0 starts 7 rows ahead
+        lab0 = np.arange(7, dtype=np.int64)
+        labels = st.add_balanced(x[7:107], normalize=False)           # same block on every rank
+        owners = labels >> RowShardedIndex.STABLE_SHIFT
+        assert (owners[:7] == 1).all()                                # rank 1 catches up first ...
+        assert abs(int((owners == 0).sum()) + 7 - int((owners == 1).sum())) <= 1   # ... then they alternate
+        assert st.counts == [7 + int((owners == 0).sum()), int((owners == 1).sum())]
+        all_labels = np.concatenate([lab0, labels])
+        D, I = st.search(x[:107][[3, 50, 99]], 1)
+        assert I[:, 0].tolist() == all_labels[[3, 50, 99]].tolist() and np.allclose(D[:, 0], 1.0, atol=1e-5)
+        st.remove(all_labels[[50, 99]])
+        D, I = st.search(x[:107][[50, 99]], 3)
+        assert not (set(I.ravel().tolist()) & set(all_labels[[50, 99]].tolist()))
+        with pytest.raises(ValueError):
+            idx.add_balanced(x[:2])                                   # contiguous numbering cannot do it
         ret[rank] = "ok"
     finally:
         dist.destroy_process_group()

@@ -27,10 +27,18 @@ def test_golden_scenario_svdb_two_partitions(classes, tmp_path):
     C.case_golden_scenario_svdb(classes[1], tmp_path, devices=[0, 1])
 
 
+def test_golden_scenario_svdb_two_partitions_goes_through_the_shard_group(classes, tmp_path):
+    from fake_engine import FakeGroup
+    before = FakeGroup.searches
+    C.case_golden_scenario_svdb(classes[1], tmp_path, devices=[0, 1])
+    assert FakeGroup.searches > before   # several devices: one fused group search per query, no Python merge
+
+
 def test_golden_scenario_svdb_partitions_scanned_in_parallel(classes, tmp_path, monkeypatch):
-    # large multi-GPU databases scan their partitions from worker threads; force that path here
+    # fallback when no shard group can be formed (or k > 128): partitions are scanned from worker threads
     import minivectordb_b200._store as store
     monkeypatch.setattr(store.GpuStore, "PARALLEL_PARTS_BYTES", 0)
+    monkeypatch.setattr(FakeEngine, "group_class", None)
     C.case_golden_scenario_svdb(classes[1], tmp_path, devices=[0, 1])
 
 

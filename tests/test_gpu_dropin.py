@@ -27,17 +27,42 @@ def test_golden_scenario_svdb(classes, tmp_path):
     C.case_golden_scenario_svdb(classes[1], tmp_path)
 
 
-def test_golden_scenario_svdb_two_devices(classes, tmp_path):
-    if _ndev() < 2:
-        pytest.skip("needs 2 GPUs")
-    C.case_golden_scenario_svdb(classes[1], tmp_path, devices=[0, 1])
+def _devices(n):
+    """n partitions over the visible GPUs (several partitions share a GPU on a small box: the fused
+    exchange still runs between them, through the same peer-store code path)."""
+    return [i % _ndev() for i in range(n)]
+
+
+@pytest.mark.parametrize("nparts", [2, 3, 8])
+def test_golden_scenario_svdb_shard_group(classes, tmp_path, nparts):
+    """ShardedVectorDatabase(devices=[...]): ONE fused group search per query (scan + NVLink exchange +
+    merge inside the kernels), same answers as the reference's single in-memory index."""
+    import minivectordb_b200._store as store
+    calls = []
+    real = store.FlatIPEngine.group_class.search
+
+    def spy(self, *a, **kw):
+        calls.append(1)
+        return real(self, *a, **kw)
+
+    store.FlatIPEngine.group_class.search = spy
+    try:
+        C.case_golden_scenario_svdb(classes[1], tmp_path, devices=_devices(nparts))
+    finally:
+        store.FlatIPEngine.group_class.search = real
+    assert calls, "the multi-device class did not use the shard group"
+
+
+def test_sharded_basics_shard_group(classes, tmp_path):
+    C.case_sharded_basics(classes[1], tmp_path, devices=_devices(2))
 
 
 def test_golden_scenario_svdb_partitions_in_parallel(classes, tmp_path, monkeypatch):
-    # two partitions (two GPUs when there are two, else both on GPU 0) scanned from worker threads
+    # fallback without a shard group (also what k > 128 takes): partitions scanned from worker threads
     import minivectordb_b200._store as store
     monkeypatch.setattr(store.GpuStore, "PARALLEL_PARTS_BYTES", 0)
-    C.case_golden_scenario_svdb(classes[1], tmp_path, devices=[0, 1] if _ndev() >= 2 else [0, 0])
+    monkeypatch.setattr(store.FlatIPEngine, "group_class", None)
+    C.case_golden_scenario_svdb(classes[1], tmp_path, devices=_devices(2))
 
 
 def test_loads_reference_pickle(classes, tmp_path):
