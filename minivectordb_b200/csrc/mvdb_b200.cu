@@ -2264,6 +2264,29 @@ int mvdb_index_search_exchange(mvdb_index* ix, mvdb_workspace* ws, mvdb_exchange
     return rc;
 }
 
+// Everything a fused scan of `nq` queries would otherwise set up lazily at launch time (scratch
+// allocations, per-kernel shared-memory opt-in): cudaMalloc synchronises the whole device, which must
+// not happen once a peer's scan -- possibly on the same device -- is already waiting for ours.
+static int prepare_fused_scan(mvdb_index* ix, mvdb_workspace* ws, int64_t nq, int64_t k) {
+    RC_OK(ws_scratch(ws));
+    RC_OK(grow_dev(&ws->partials, &ws->partials_cap, size_t(8) * size_t(ix->sm_count) * 4 * size_t(k)));
+    ScanParams p = {};
+    p.n = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(ix->ntotal.load(std::memory_order_acquire), 0xFFFFFFF0ull)));
+    p.d = ix->d;
+    p.ld4 = ix->ld4;
+    p.k = int(k);
+    for (int g : {8, 4, 2, 1}) {
+        if (nq < g && g != 1) continue;
+        ScanPlan plan;
+        RC_OK(plan_scan(ix, p, g, &plan));   // cudaFuncSetAttribute also forces the (lazily loaded) kernel in
+    }
+    // same for the stand-in kernel of an empty shard: with lazy module loading the FIRST launch of a kernel
+    // may synchronise the device
+    cudaFuncAttributes fa;
+    CU_OK(cudaFuncGetAttributes(&fa, xchg_empty_kernel));
+    return MVDB_OK;
+}
+
 // ---------------------------------------------------------------------------
 // Shard group: the row shards of ONE database on several GPUs of one box, driven by ONE process.
 // Stands in for the single in-memory index of the reference's ShardedVectorDatabase
@@ -2385,7 +2408,7 @@ int mvdb_group_search(mvdb_group* g, const float* q, int64_t nq, int64_t k, cons
             CU_OK(cudaMalloc(&g->D_dev[size_t(s)], std::max(on, g->out_cap) * 4));
             CU_OK(cudaMalloc(&g->I_dev[size_t(s)], std::max(on, g->out_cap) * 8));
         }
-        RC_OK(ws_scratch(ws));
+        RC_OK(prepare_fused_scan(ix, ws, nq, k));
         const mvdb_mask* h = masks ? masks[s] : nullptr;
         const uint8_t* hm = (!h && host_masks) ? host_masks[s] : nullptr;
         if (h && h->ix != ix) return fail(MVDB_ERR_ARG, "mask handle %d belongs to another index", s);

@@ -120,9 +120,38 @@ __device__ __forceinline__ void xchg_merge(const XchgDev* x, uint64_t seq, int q
     const uint64_t* mine = x->recv[x->rank] + size_t(seq & 1) * x->world * size_t(x->nq_max) * x->k_max +
                            size_t(qi) * x->k_max;
     const size_t src_stride = size_t(x->nq_max) * x->k_max;
+    const int total = x->world * k;
+    if (k <= kExtractMaxK && total <= 256) {
+        // small k: the world x k candidates sit in registers (<= 8 per lane) and the k best are pulled out
+        // by warp-wide arg-max rounds -- no shared memory, no sort
+        uint64_t v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int pos = lane + 32 * u;
+            uint64_t key = kEmptyKey;
+            if (pos < total) {
+                const uint64_t orig = __ldcg(mine + size_t(pos / k) * src_stride + (pos % k));
+                if (orig != kEmptyKey) key = (orig & 0xFFFFFFFF00000000ull) | uint64_t(0xFFFFFFFFu - uint32_t(pos));
+            }
+            v[u] = key;
+        }
+        const uint64_t key = warp_extract_topk<8>(v, k, lane);
+        if (lane < k) {
+            if (key == kEmptyKey) {
+                D[lane] = -FLT_MAX;
+                I[lane] = -1;
+            } else {
+                const int pos = int(key_row(key));
+                const int src = pos / k;
+                const uint64_t orig = __ldcg(mine + size_t(src) * src_stride + (pos % k));
+                D[lane] = key_score(orig);
+                I[lane] = int64_t(key_row(orig)) + x->offsets[src];
+            }
+        }
+        return;
+    }
     WarpSelect f;
     f.init(buf, cap, k);
-    const int total = x->world * k;
     // candidate position pos = src * k + i encodes the tie order (rank, then in-list order
     // = ascending global row for contiguous row shards)
     for (int base = 0; base < total; base += kWarp) {
@@ -248,6 +277,105 @@ __device__ __forceinline__ void trace_stamp(const ScanParams& p, int slot, int c
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Small k (<= 16, select buffers of 64 keys): the merge tails run on warp_extract_topk instead of
+// sort-and-cut.  `fast_tail` must give the same answer everywhere in a launch.
+__device__ __forceinline__ bool fast_tail(const ScanParams& p, int ncw) {
+    return p.k <= kExtractMaxK && p.cap == 64 && ncw <= 8 &&
+           uint32_t(gridDim.x) * uint32_t(p.k) <= uint32_t(ncw) * 32u * 16u;
+}
+
+// the per-warp select buffers of query qi (unsorted, lengths in hdr->cnts) -> the CTA's k best, lane j = j-th
+template <int M>
+__device__ __forceinline__ uint64_t cta_extract(const SmemHeader* hdr, const uint64_t* selbuf, int nq, int qi, int ncw,
+                                                int cap, int k, int lane) {
+    uint64_t v[M];
+#pragma unroll
+    for (int u = 0; u < M; u++) {
+        const int w = u >> 1, i = lane + 32 * (u & 1);
+        v[u] = (w < ncw && i < hdr->cnts[w * nq + qi]) ? selbuf[size_t(w * nq + qi) * cap + i] : kEmptyKey;
+    }
+    return warp_extract_topk<M>(v, k, lane);
+}
+
+// `total` keys at src (global memory, other SMs wrote them) split over the CTA's consumer threads -> this
+// warp's k best; all loads are issued before the first use (one L2 round trip)
+template <int M>
+__device__ __forceinline__ uint64_t spread_extract(const uint64_t* src, int total, int t, int nthr, int k, int lane) {
+    uint64_t v[M];
+#pragma unroll
+    for (int u = 0; u < M; u++) {
+        const int i = t + u * nthr;
+        v[u] = (i < total) ? __ldcg(src + i) : kEmptyKey;
+    }
+    return warp_extract_topk<M>(v, k, lane);
+}
+
+__device__ __forceinline__ void finish_scan_fast(const ScanParams& p, SmemHeader* hdr, uint64_t* selbuf, int cw, int ncw,
+                                                 int lane, int bar_id, int bar_threads) {
+    const int nq = p.nq, k = p.k, cap = p.cap;
+    const int G = gridDim.x;
+    // ---- CTA merge: warp (qi % ncw) pulls the k best of query qi out of all warps' buffers ----
+    for (int qi = cw; qi < nq; qi += ncw) {
+        const uint64_t key = (ncw <= 4) ? cta_extract<8>(hdr, selbuf, nq, qi, ncw, cap, k, lane)
+                                        : cta_extract<16>(hdr, selbuf, nq, qi, ncw, cap, k, lane);
+        if (lane < k) p.partials[(size_t(qi) * G + blockIdx.x) * k + lane] = key;
+    }
+    if (blockIdx.x == 0) trace_stamp(p, 4, cw, lane);
+    __threadfence();
+    named_bar_sync(bar_id, bar_threads);
+    if (blockIdx.x == 0) trace_stamp(p, 5, cw, lane);
+    if (cw == 0 && lane == 0) {
+        unsigned t = atomicAdd(p.ticket, 1u);
+        hdr->last_flag = (t == unsigned(G - 1));
+    }
+    named_bar_sync(bar_id, bar_threads);
+    if (blockIdx.x == 0) trace_stamp(p, 6, cw, lane);
+    if (!hdr->last_flag) return;
+    // ---- last CTA: G x k keys per query, every warp takes a slice, then one warp per query finishes ----
+    trace_stamp(p, 8, cw, lane);
+    __threadfence();
+    const int total = G * k, t = cw * kWarp + lane;
+    const int per = (total + bar_threads - 1) / bar_threads;
+    for (int qi = 0; qi < nq; qi++) {
+        const uint64_t* src = p.partials + size_t(qi) * G * k;
+        const uint64_t key = per <= 4    ? spread_extract<4>(src, total, t, bar_threads, k, lane)
+                             : per <= 8  ? spread_extract<8>(src, total, t, bar_threads, k, lane)
+                                         : spread_extract<16>(src, total, t, bar_threads, k, lane);
+        if (lane < k) selbuf[size_t(cw * nq + qi) * cap + lane] = key;   // the warp's own buffer: its candidates are spent
+        if (qi == 0) trace_stamp(p, 10, cw, lane);
+    }
+    named_bar_sync(bar_id, bar_threads);
+    trace_stamp(p, 11, cw, lane);
+    for (int qi = cw; qi < nq; qi += ncw) {
+        uint64_t v[4];   // ncw * k <= 8 * 16 keys
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = lane + 32 * u, w = i / k;
+            v[u] = (w < ncw) ? selbuf[size_t(w * nq + qi) * cap + (i - w * k)] : kEmptyKey;
+        }
+        const uint64_t key = warp_extract_topk<4>(v, k, lane);
+        uint64_t* fin = selbuf + size_t(cw * nq + qi) * cap + 32;   // upper half of the same buffer (k <= 16)
+        __syncwarp();
+        if (lane < k) fin[lane] = key;
+        __syncwarp();
+        if (qi == 0) trace_stamp(p, 12, cw, lane);
+        if (p.xchg) xchg_send(p.xchg, p.xchg_seq, qi, fin, k, k, lane);
+        else write_results(fin, k, k, p.outD + size_t(qi) * k, p.outI + size_t(qi) * k, p.label_offset, lane);
+    }
+    if (cw == 0 && lane == 0) {  // ready for the next launch on this workspace
+        *p.ticket = 0u;
+        if (p.tile_ctr) *p.tile_ctr = 0u;
+    }
+    trace_stamp(p, 13, cw, lane);
+    if (!p.xchg) return;
+    named_bar_sync(bar_id, bar_threads);
+    if (cw == 0) xchg_publish_and_wait(p.xchg, p.xchg_seq, lane);
+    named_bar_sync(bar_id, bar_threads);
+    for (int qi = cw; qi < nq; qi += ncw)
+        xchg_merge(p.xchg, p.xchg_seq, qi, selbuf + size_t(cw * nq + qi) * cap, cap, k, p.outD + size_t(qi) * k,
+                   p.outI + size_t(qi) * k, lane);
+}
+
 __device__ __forceinline__ void finish_scan(const ScanParams& p, uint8_t* smem_base, SmemHeader* hdr,
                                             uint64_t* selbuf, int cw, int ncw, int lane, int bar_id,
                                             int bar_threads) {
@@ -257,6 +385,10 @@ __device__ __forceinline__ void finish_scan(const ScanParams& p, uint8_t* smem_b
     if (blockIdx.x == 0) trace_stamp(p, 3, cw, lane);
     pdl_wait();   // the previous search on this stream is complete: shared scratch and outputs are ours
     if (!p.pdl_early) pdl_launch_dependents();   // ... and once EVERY CTA is here, the next search may start scanning
+    if (fast_tail(p, ncw)) {
+        finish_scan_fast(p, hdr, selbuf, cw, ncw, lane, bar_id, bar_threads);
+        return;
+    }
     // ---- CTA merge: warp (qi % ncw) owns query qi -------------------------
     for (int qi = cw; qi < nq; qi += ncw) {
         WarpSelect m = merge_cta_lists(hdr, selbuf, nq, qi, cw, ncw, cap, k, lane);
@@ -604,7 +736,7 @@ __global__ void __launch_bounds__(kTma ? 288 : 256, kTma ? 1 : 2) scan_q1_kernel
     }
     if (p.all_ord) return;
     if (blockIdx.x == 0) trace_stamp(p, 2, cw, lane);
-    sel.compact(lane);
+    if (!fast_tail(p, ncw)) sel.compact(lane);   // small k: the CTA merge reads the raw buffers (no sort)
     if (lane == 0) hdr->cnts[cw] = sel.cnt;
     finish_scan(p, smem, hdr, selbuf, cw, ncw, lane, 1, ncw * 32);
 }
@@ -749,9 +881,10 @@ __global__ void __launch_bounds__(kTma ? 288 : 256, (kTma || NQ >= 8) ? 1 : 2) s
         }
     }
     if (p.all_ord) return;
+    const bool fast = fast_tail(p, ncw);
 #pragma unroll
     for (int qi = 0; qi < NQ; qi++) {
-        sel[qi].compact(lane);
+        if (!fast) sel[qi].compact(lane);
         if (lane == 0) hdr->cnts[cw * NQ + qi] = sel[qi].cnt;
     }
     finish_scan(p, smem, hdr, selbuf, cw, ncw, lane, 1, ncw * 32);

@@ -164,6 +164,42 @@ struct WarpSelect {
     }
 };
 
+// ---------------------------------------------------------------------------
+// Small-k selection by repeated warp-wide arg-max.  Each lane holds M keys in registers (any order,
+// kEmptyKey = none; real keys are unique).  On return lane j (j < k) holds the j-th best of the 32*M
+// keys (kEmptyKey once they run out).  One round = two 32-bit redux.sync (high word, then low word among
+// the lanes that tie on the high word) and a short fix-up in the single lane that owned the winner --
+// ~100 cycles, no shared memory, no sort.  For k ~ 10 this replaces "bitonic-sort 64..256 keys, then
+// cut": the merge tails of a search are a serial chain, so their latency is what counts.
+// ---------------------------------------------------------------------------
+constexpr int kExtractMaxK = 16;
+template <int M>
+__device__ __forceinline__ uint64_t warp_extract_topk(uint64_t (&v)[M], int k, int lane) {
+    uint64_t mine = kEmptyKey;
+    uint64_t lmax = v[0];
+#pragma unroll
+    for (int i = 1; i < M; i++) lmax = v[i] > lmax ? v[i] : lmax;
+    for (int j = 0; j < k; j++) {
+        const uint32_t hi = uint32_t(lmax >> 32);
+        const uint32_t mhi = __reduce_max_sync(0xFFFFFFFFu, hi);
+        const uint32_t lo = (hi == mhi) ? uint32_t(lmax) : 0u;   // a real key's low word (~row) is never 0
+        const uint32_t mlo = __reduce_max_sync(0xFFFFFFFFu, lo);
+        const uint64_t best = (uint64_t(mhi) << 32) | mlo;
+        if (best == kEmptyKey) break;   // warp-uniform: nothing left
+        if (lane == j) mine = best;
+        if (lmax == best) {             // exactly one lane: drop the winner, refresh the local maximum
+            uint64_t nm = kEmptyKey;
+#pragma unroll
+            for (int i = 0; i < M; i++) {
+                if (v[i] == best) v[i] = kEmptyKey;
+                nm = v[i] > nm ? v[i] : nm;
+            }
+            lmax = nm;
+        }
+    }
+    return mine;
+}
+
 // Buffer capacity for a given k: room for the kept k plus at least one full
 // warp of fresh candidates, rounded to a power of two for the bitonic network.
 __host__ __device__ __forceinline__ int select_cap(int k) {

@@ -3,9 +3,11 @@ import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import minivectordb_b200 as mv
 from minivectordb_b200 import _native as N
-names = {0: "cta0 consumer start", 1: "cta0 query loaded", 2: "cta0 tiles done", 3: "cta0 warps compacted+barrier", 4: "cta0 CTA merge + partials written",
-         5: "cta0 fence+barrier", 6: "cta0 ticket taken", 8: "last: start", 9: "last: partials staged", 10: "last: column merge done",
-         11: "last: compact+barrier", 12: "last: final merge done", 13: "last: results written"}
+# k <= 16 takes the extraction tail (no slot 9): 4 = CTA's k best extracted + written, 10 = this warp's slice of the
+# G x k partial keys loaded + extracted, 12 = final extraction over the warps' lists
+names = {0: "cta0 consumer start", 1: "cta0 query loaded", 2: "cta0 tiles done", 3: "cta0 (compaction+) barrier", 4: "cta0 CTA merge + partials written",
+         5: "cta0 fence+barrier", 6: "cta0 ticket taken", 8: "last: start", 9: "last: partials staged", 10: "last: slice merged",
+         11: "last: barrier", 12: "last: final merge done", 13: "last: results written"}
 for n, d in ((8, 512), (1184, 512), (100_000, 512), (1_000_000, 384)):
     eng = mv.FlatIPEngine(d); eng.add_synthetic(1234, 0, n, 0, True); ws = eng.workspace()
     eng.set_option("trace", 1)
