@@ -19,7 +19,9 @@
  * the scan.  This file therefore restates faiss's
  * published algorithm (faiss/utils/distances.cpp: fvec_renorm_L2,
  * exhaustive_inner_product_seq; faiss/utils/Heap.h: CMin heap with id
- * tie-break; faiss/impl/ResultHandler.h: Top1 / Heap / Reservoir handlers)
+ * tie-break; faiss/impl/ResultHandler.h: Top1 / Heap / Reservoir handlers with
+ * faiss's reservoir capacity (2k+15)&~15 and partition_fuzzy; exhaustive_inner_product_blas:
+ * 4096 x 1024 sgemm blocks feeding the block result handlers for nq >= 20)
  * from its documented behaviour.  It is anchored by (a) a float64 numpy gold
  * scorer (oracle/oracle.py) and (b) fixtures produced by running the
  * reference's own Python classes on top of this file (tests/golden/).
@@ -115,18 +117,119 @@ static void heap_drain_sorted(int64_t k, float* hv, int64_t* hi) {
     }
 }
 
-/* sort helper for the reservoir: best-first by (value desc, id asc) */
-typedef struct { float v; int64_t i; } pair_t;
-static int pair_cmp_desc(const void* a, const void* b) {
-    const pair_t* x = (const pair_t*)a;
-    const pair_t* y = (const pair_t*)b;
-    if (x->v > y->v) return -1;
-    if (x->v < y->v) return 1;
-    return (x->i > y->i) - (x->i < y->i);
+/* heap_push: append (v,id) as element number `k` (1-based) of a heap that holds k-1 and sift it up
+ * (faiss/utils/Heap.h heap_push, min-heap flavour with the cmp2 id tie-break). */
+static void heap_push_up(int64_t k, float* hv, int64_t* hi, float v, int64_t id) {
+    int64_t i = k - 1;
+    while (i > 0) {
+        int64_t f = (i - 1) / 2;
+        if (!pair_lt(v, id, hv[f], hi[f])) break;
+        hv[i] = hv[f];
+        hi[i] = hi[f];
+        i = f;
+    }
+    hv[i] = v;
+    hi[i] = id;
+}
+
+/* ------------------------------------------------------------------ */
+/* ReservoirTopN (faiss/impl/ResultHandler.h) for C = CMin<float,int64>: */
+/* "better" = larger.  Storage of `cap` = (2k+15)&~15 slots; a value is  */
+/* stored iff it is STRICTLY better than the threshold; when the storage */
+/* is full, partition_fuzzy keeps between k and (cap+k)/2 of the best and */
+/* raises the threshold to the partition value.                          */
+/* ------------------------------------------------------------------ */
+ORC_API int64_t orc_reservoir_capacity(int64_t k) { return (2 * k + 15) & ~(int64_t)15; }
+
+static float median3f(float a, float b, float c) {
+    if (a > b) { float t = a; a = b; b = t; }
+    if (c > b) return b;
+    if (c > a) return c;
+    return a;
+}
+
+/* faiss/utils/partitioning.cpp: partition_fuzzy_median3 restated for CMin (threshold found by
+ * bisection over medians of three samples, then the array is compressed in place, order kept).
+ * Keeps every value > thresh plus enough values == thresh to reach q in [q_min, q_max]. */
+static float partition_fuzzy_cmin(float* vals, int64_t* ids, int64_t n, int64_t q_min, int64_t q_max, int64_t* q_out) {
+    if (q_min == 0) { *q_out = 0; return FLT_MAX; }
+    if (q_max >= n) { *q_out = q_max; return -FLT_MAX; }
+    float thresh_inf = FLT_MAX;     /* C::Crev::neutral(): nothing is better than it */
+    float thresh_sup = -FLT_MAX;    /* C::neutral(): everything is better than it   */
+    float thresh = median3f(vals[0], vals[n / 2], vals[n - 1]);
+    int64_t n_eq = 0, n_lt = 0, q = 0;
+    for (int it = 0; it < 200; it++) {
+        n_eq = n_lt = 0;
+        for (int64_t i = 0; i < n; i++) {
+            if (thresh < vals[i]) n_lt++;            /* C::cmp(thresh, v): v is better */
+            else if (vals[i] == thresh) n_eq++;
+        }
+        if (n_lt <= q_min) {
+            if (n_lt + n_eq >= q_min) { q = q_min; break; }
+            thresh_inf = thresh;
+        } else if (n_lt <= q_max) {
+            q = n_lt;
+            break;
+        } else {
+            thresh_sup = thresh;
+        }
+        /* sample_threshold_median3: three values strictly between the bounds, array walked with a prime stride */
+        float v3[3];
+        int vi = 0;
+        for (int64_t i = 0; i < n; i++) {
+            float v = vals[(uint64_t)(i * 6700417ULL) % (uint64_t)n];
+            if (v < thresh_inf && thresh_sup < v) {
+                v3[vi++] = v;
+                if (vi == 3) break;
+            }
+        }
+        float nt = vi == 3 ? median3f(v3[0], v3[1], v3[2]) : vi != 0 ? v3[0] : thresh_inf;
+        if (nt == thresh_inf) break;   /* nothing between the bounds */
+        thresh = nt;
+    }
+    int64_t n_eq_1 = q - n_lt;
+    if (n_eq_1 < 0) {   /* more than q values strictly better even at the bound */
+        q = q_min;
+        thresh = nextafterf(thresh, HUGE_VALF);
+        n_eq_1 = q;
+    }
+    int64_t wp = 0;     /* compress_array */
+    for (int64_t i = 0; i < n; i++) {
+        if (thresh < vals[i]) { vals[wp] = vals[i]; ids[wp] = ids[i]; wp++; }
+        else if (n_eq_1 > 0 && vals[i] == thresh) { vals[wp] = vals[i]; ids[wp] = ids[i]; wp++; n_eq_1--; }
+    }
+    *q_out = wp;
+    return thresh;
+}
+
+typedef struct { float* vals; int64_t* ids; int64_t i, n, cap; float thr; } reservoir_t;
+
+static inline void reservoir_add(reservoir_t* r, float v, int64_t id) {
+    if (r->thr < v) {
+        if (r->i == r->cap) r->thr = partition_fuzzy_cmin(r->vals, r->ids, r->cap, r->n, (r->cap + r->n) / 2, &r->i);
+        r->vals[r->i] = v;
+        r->ids[r->i] = id;
+        r->i++;
+    }
+}
+
+/* ReservoirTopN::to_result: the first min(i,n) stored values are pushed into a heap, the rest replace its
+ * root when strictly better, heap_reorder sorts best-first; missing results are (-FLT_MAX, -1). */
+static void reservoir_to_result(const reservoir_t* r, float* D, int64_t* I) {
+    const int64_t n = r->n, m = r->i < n ? r->i : n;
+    for (int64_t j = 0; j < m; j++) heap_push_up(j + 1, D, I, r->vals[j], r->ids[j]);
+    if (r->i < n) {
+        heap_drain_sorted(m, D, I);
+        for (int64_t j = m; j < n; j++) { D[j] = -FLT_MAX; I[j] = -1; }
+    } else {
+        for (int64_t j = n; j < r->i; j++)
+            if (D[0] < r->vals[j]) heap_replace_root(n, D, I, r->vals[j], r->ids[j]);
+        heap_drain_sorted(n, D, I);
+    }
 }
 
 /* One query against rows [0,n).  Handler choice mirrors faiss:
- * k == 1 -> running maximum, k < 100 -> heap, k >= 100 -> reservoir of 2k
+ * k == 1 -> running maximum, k < 100 -> heap, k >= 100 -> ReservoirTopN
  * (distance_compute_min_k_reservoir = 100).  All three admit a row only if
  * its score is STRICTLY greater than the current threshold, so at an exact
  * tie on the boundary the earlier row is kept. */
@@ -151,24 +254,79 @@ static void search_one(const float* x, int64_t n, int64_t d, const float* q,
         heap_drain_sorted(k, D, I);
         return;
     }
-    /* reservoir */
-    int64_t cap = 2 * k, cnt = 0;
-    pair_t* res = (pair_t*)malloc((size_t)cap * sizeof(pair_t));
-    float thr = -FLT_MAX;
-    for (int64_t r = 0; r < n; r++) {
-        float s = ip_f32(q, x + r * d, (size_t)d);
-        if (s > thr) {
-            res[cnt].v = s; res[cnt].i = r; cnt++;
-            if (cnt == cap) {
-                qsort(res, (size_t)cnt, sizeof(pair_t), pair_cmp_desc);
-                cnt = k;
-                thr = res[k - 1].v;
-            }
+    reservoir_t res;
+    res.n = k;
+    res.cap = orc_reservoir_capacity(k);
+    res.i = 0;
+    res.thr = -FLT_MAX;
+    res.vals = (float*)malloc((size_t)res.cap * sizeof(float));
+    res.ids = (int64_t*)malloc((size_t)res.cap * sizeof(int64_t));
+    for (int64_t r = 0; r < n; r++) reservoir_add(&res, ip_f32(q, x + r * d, (size_t)d), r);
+    reservoir_to_result(&res, D, I);
+    free(res.vals);
+    free(res.ids);
+}
+
+/* ------------------------------------------------------------------ */
+/* Block result handlers for the nq >= 20 path                         */
+/* (faiss/utils/distances.cpp exhaustive_inner_product_blas: blocks of  */
+/* 4096 queries x 1024 rows through sgemm_, every block of inner        */
+/* products handed to Top1 / Heap / Reservoir BlockResultHandler::      */
+/* add_results(j0, j1, ip_block), end_multiple() after the last block). */
+/* The handler state lives in caller-owned arrays so that the sgemm can */
+/* be the host BLAS (oracle.py calls numpy's sgemm, as faiss calls      */
+/* sgemm_): vals [nq][cap], ids [nq][cap], cnt [nq], thr [nq].          */
+/*   kind 0 Top1 (cap 1), 1 Heap (cap k), 2 Reservoir (cap from        */
+/*   orc_reservoir_capacity).  Initialise cnt = 0, thr = -FLT_MAX,      */
+/*   vals = -FLT_MAX, ids = -1.                                         */
+/* ------------------------------------------------------------------ */
+ORC_API int orc_block_add(int kind, int64_t k, int64_t cap, int64_t nq, int64_t j0, int64_t j1, const float* ip,
+                          float* vals, int64_t* ids, int64_t* cnt, float* thr) {
+    if (kind < 0 || kind > 2 || k <= 0 || cap < 1 || j1 < j0) return -1;
+    const int64_t nj = j1 - j0;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < nq; i++) {
+        const float* row = ip + i * nj;
+        float* v = vals + i * cap;
+        int64_t* id = ids + i * cap;
+        if (kind == 0) {
+            for (int64_t j = 0; j < nj; j++)
+                if (row[j] > v[0]) { v[0] = row[j]; id[0] = j0 + j; }
+        } else if (kind == 1) {
+            for (int64_t j = 0; j < nj; j++)
+                if (row[j] > v[0]) heap_replace_root(k, v, id, row[j], j0 + j);
+        } else {
+            reservoir_t r = {v, id, cnt[i], k, cap, thr[i]};
+            for (int64_t j = 0; j < nj; j++) reservoir_add(&r, row[j], j0 + j);
+            cnt[i] = r.i;
+            thr[i] = r.thr;
         }
     }
-    qsort(res, (size_t)cnt, sizeof(pair_t), pair_cmp_desc);
-    for (int64_t j = 0; j < k && j < cnt; j++) { D[j] = res[j].v; I[j] = res[j].i; }
-    free(res);
+    return 0;
+}
+
+ORC_API int orc_block_end(int kind, int64_t k, int64_t cap, int64_t nq, float* vals, int64_t* ids, const int64_t* cnt,
+                          const float* thr, float* D, int64_t* I) {
+    if (kind < 0 || kind > 2 || k <= 0) return -1;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < nq; i++) {
+        float* v = vals + i * cap;
+        int64_t* id = ids + i * cap;
+        float* Di = D + i * k;
+        int64_t* Ii = I + i * k;
+        if (kind == 0) {
+            Di[0] = v[0]; Ii[0] = id[0];
+        } else if (kind == 1) {
+            heap_drain_sorted(k, v, id);
+            memcpy(Di, v, (size_t)k * sizeof(float));
+            memcpy(Ii, id, (size_t)k * sizeof(int64_t));
+        } else {
+            reservoir_t r = {v, id, cnt[i], k, cap, thr[i]};
+            for (int64_t j = 0; j < k; j++) { Di[j] = -FLT_MAX; Ii[j] = -1; }
+            reservoir_to_result(&r, Di, Ii);
+        }
+    }
+    return 0;
 }
 
 /* IndexFlatIP.search for nq queries (exhaustive_inner_product_seq: OpenMP

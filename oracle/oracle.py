@@ -69,6 +69,12 @@ def _lib():
         lib.orc_synth_rows.argtypes = [ctypes.c_uint64, i64, i64, i64, ctypes.c_int, f32p]
         lib.orc_synth_rows.restype = None
         lib.orc_num_threads.restype = ctypes.c_int
+        lib.orc_reservoir_capacity.argtypes = [i64]
+        lib.orc_reservoir_capacity.restype = i64
+        lib.orc_block_add.argtypes = [ctypes.c_int, i64, i64, i64, i64, i64, f32p, f32p, i64p, i64p, f32p]
+        lib.orc_block_add.restype = ctypes.c_int
+        lib.orc_block_end.argtypes = [ctypes.c_int, i64, i64, i64, f32p, i64p, i64p, f32p, f32p, i64p]
+        lib.orc_block_end.restype = ctypes.c_int
         _LIB = lib
     return _LIB
 
@@ -111,6 +117,63 @@ def search_flat_ip(x: np.ndarray, q: np.ndarray, k: int, nthreads: int = 0):
                                    _f32p(D), _i64p(I), nthreads)
     if rc != 0:
         raise RuntimeError(f"orc_search_flat_ip rc={rc}")
+    return D, I
+
+
+BLAS_THRESHOLD = 20          # faiss distance_compute_blas_threshold: nq >= 20 takes the sgemm path
+BLAS_QUERY_BS, BLAS_DB_BS = 4096, 1024   # distance_compute_blas_query_bs / _database_bs
+
+
+class BlockHandler:
+    """faiss's Top1 / Heap / Reservoir BlockResultHandler (k == 1 / k < 100 / k >= 100) for `nq` queries,
+    fed block by block with inner products -- the consumer of the sgemm path."""
+
+    def __init__(self, nq: int, k: int):
+        self.nq, self.k = int(nq), int(k)
+        self.kind = 0 if k == 1 else (1 if k < 100 else 2)
+        self.cap = 1 if k == 1 else (k if k < 100 else int(_lib().orc_reservoir_capacity(k)))
+        self.vals = np.full((nq, self.cap), FLT_LOWEST, dtype=np.float32)
+        self.ids = np.full((nq, self.cap), -1, dtype=np.int64)
+        self.cnt = np.zeros(nq, dtype=np.int64)
+        self.thr = np.full(nq, FLT_LOWEST, dtype=np.float32)
+
+    def add_results(self, j0: int, j1: int, ip: np.ndarray) -> None:
+        ip = np.ascontiguousarray(ip, dtype=np.float32)
+        assert ip.shape == (self.nq, j1 - j0)
+        rc = _lib().orc_block_add(self.kind, self.k, self.cap, self.nq, j0, j1, _f32p(ip), _f32p(self.vals),
+                                  _i64p(self.ids), _i64p(self.cnt), _f32p(self.thr))
+        assert rc == 0
+
+    def end(self):
+        D = np.empty((self.nq, self.k), dtype=np.float32)
+        I = np.empty((self.nq, self.k), dtype=np.int64)
+        rc = _lib().orc_block_end(self.kind, self.k, self.cap, self.nq, _f32p(self.vals), _i64p(self.ids),
+                                  _i64p(self.cnt), _f32p(self.thr), _f32p(D), _i64p(I))
+        assert rc == 0
+        return D, I
+
+
+def search_flat_ip_blas(x: np.ndarray, q: np.ndarray, k: int, make_chunk=None, n: int = 0):
+    """IndexFlatIP.search the way faiss runs it for nq >= 20 (exhaustive_inner_product_blas): for every
+    block of 4096 queries, for every block of 1024 rows, one sgemm (here numpy's float32 matmul = the host
+    BLAS, as faiss calls sgemm_) and the block of inner products goes to the block result handler.
+    `x` may be None with make_chunk(row0, m) + n: the matrix is then produced 1M rows at a time."""
+    q = np.ascontiguousarray(q, dtype=np.float32)
+    nq = q.shape[0]
+    n = x.shape[0] if x is not None else int(n)
+    D = np.empty((nq, k), dtype=np.float32)
+    I = np.empty((nq, k), dtype=np.int64)
+    for i0 in range(0, nq, BLAS_QUERY_BS):
+        i1 = min(nq, i0 + BLAS_QUERY_BS)
+        h = BlockHandler(i1 - i0, k)
+        step = 1 << 20 if x is None else n
+        for c0 in range(0, n, max(step, 1)):
+            c1 = min(n, c0 + step)
+            xc = x if x is not None else make_chunk(c0, c1 - c0)
+            for j0 in range(c0, c1, BLAS_DB_BS):
+                j1 = min(c1, j0 + BLAS_DB_BS)
+                h.add_results(j0, j1, q[i0:i1] @ xc[j0 - c0:j1 - c0].T)
+        D[i0:i1], I[i0:i1] = h.end()
     return D, I
 
 
