@@ -12,6 +12,9 @@ namespace mvdb {
 // (float)(1.0/sqrtf(nr)) when nr > 0); the row is written with zero padding
 // up to the leading dimension.  kSynth generates the row instead of reading it.
 // ---------------------------------------------------------------------------
+// HBM-bound: n*d*4 bytes read + n*ld*4 bytes written.  Rows of up to 1024 floats are held in registers
+// between the norm pass and the write pass (one read of the source, 128-bit loads and stores when the
+// layout allows); wider rows take the two-pass loop (the second read comes from L1/L2).
 template <bool kSynth>
 __global__ void __launch_bounds__(256) append_rows_kernel(const float* __restrict__ src, float* __restrict__ dst,
                                                           uint64_t n, int d, int64_t ld, int normalize,
@@ -20,13 +23,38 @@ __global__ void __launch_bounds__(256) append_rows_kernel(const float* __restric
     const int lane = threadIdx.x & 31;
     const uint64_t warp = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+    const bool vec = !kSynth && (d & 3) == 0 && d <= 1024 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+    const bool regs = kSynth && d <= 1024;
+    float wmax = 0.f;   // largest squared norm this warp has stored (one atomic per warp at the end)
     for (uint64_t r = warp; r < n; r += nwarps) {
         float* out = dst + r * ld;
         const float* in = kSynth ? nullptr : src + r * uint64_t(d);
         float nr = 0.f;
-        for (int c = lane; c < d; c += kWarp) {
-            float v = kSynth ? synth_value(seed, synth_row0 + r, uint32_t(c), dist) : in[c];
-            nr = fmaf(v, v, nr);
+        float4 v4[8];
+        float v1[32];
+        if (vec) {
+            const int d4 = d >> 2;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int c = lane + 32 * j;
+                v4[j] = (c < d4) ? __ldcs(reinterpret_cast<const float4*>(in) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            // same association order as the scalar loop below would give per lane? No: the norm is only
+            // used for the scale, and faiss's own order is build dependent (SIMD lanes); any fp32 order is legal
+#pragma unroll
+            for (int j = 0; j < 8; j++) nr = dot4(v4[j], v4[j], nr);
+        } else if (regs) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const int c = lane + 32 * j;
+                v1[j] = (c < d) ? synth_value(seed, synth_row0 + r, uint32_t(c), dist) : 0.f;
+                nr = fmaf(v1[j], v1[j], nr);
+            }
+        } else {
+            for (int c = lane; c < d; c += kWarp) {
+                float v = kSynth ? synth_value(seed, synth_row0 + r, uint32_t(c), dist) : in[c];
+                nr = fmaf(v, v, nr);
+            }
         }
         float inv = 1.f;
         bool scale = false;
@@ -35,35 +63,38 @@ __global__ void __launch_bounds__(256) append_rows_kernel(const float* __restric
             inv = renorm_scale(nr);
             scale = true;
         }
-        // largest squared norm of any stored row (error bound of the bf16 batched path);
-        // non-negative floats order like their bit patterns
-        if (lane == 0) atomicMax(max_norm2_bits, __float_as_int(scale ? nr * inv * inv : nr));
-        for (int c = lane; c < ld; c += kWarp) {
-            float v = 0.f;
-            if (c < d) {
-                v = kSynth ? synth_value(seed, synth_row0 + r, uint32_t(c), dist) : in[c];
-                if (scale) v *= inv;
+        // largest squared norm of any stored row (error bound of the bf16 batched path)
+        wmax = fmaxf(wmax, scale ? nr * inv * inv : nr);
+        if (vec) {
+            const int ld4 = int(ld >> 2);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int c = lane + 32 * j;
+                if (c < ld4) {
+                    float4 v = v4[j];   // chunks past d/4 are zero (padding)
+                    if (scale) { v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv; }
+                    reinterpret_cast<float4*>(out)[c] = v;
+                }
             }
-            out[c] = v;
+        } else if (regs) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const int c = lane + 32 * j;
+                if (c < ld) out[c] = scale ? v1[j] * inv : v1[j];
+            }
+        } else {
+            for (int c = lane; c < ld; c += kWarp) {
+                float v = 0.f;
+                if (c < d) {
+                    v = kSynth ? synth_value(seed, synth_row0 + r, uint32_t(c), dist) : in[c];
+                    if (scale) v *= inv;
+                }
+                out[c] = v;
+            }
         }
     }
-}
-
-// in-place normalisation of a dense [n][d] buffer (mvdb_normalize_L2)
-__global__ void __launch_bounds__(256) normalize_dense_kernel(float* x, uint64_t n, int d) {
-    const int lane = threadIdx.x & 31;
-    const uint64_t warp = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const uint64_t nwarps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
-    for (uint64_t r = warp; r < n; r += nwarps) {
-        float* row = x + r * uint64_t(d);
-        float nr = 0.f;
-        for (int c = lane; c < d; c += kWarp) nr = fmaf(row[c], row[c], nr);
-        nr = warp_allsum(nr);
-        if (nr > 0.f) {
-            float inv = renorm_scale(nr);
-            for (int c = lane; c < d; c += kWarp) row[c] *= inv;
-        }
-    }
+    // non-negative floats order like their bit patterns
+    if (lane == 0 && wmax > 0.f) atomicMax(max_norm2_bits, __float_as_int(wmax));
 }
 
 // live bitmask maintenance ---------------------------------------------------

@@ -2541,19 +2541,27 @@ int mvdb_normalize_L2(float* x, uint64_t n, int d, int device) {
     }
     if (device < 0 || device >= ndev) return fail(MVDB_ERR_ARG, "device %d out of range", device);
     DeviceGuard guard(device);
-    float* dev = nullptr;
+    // the ingest kernel itself, writing to a second dense buffer (ld = d): a row normalised here is
+    // bit-identical to the same row normalised by mvdb_index_add
+    float *dev = nullptr, *out = nullptr;
+    int* bits = nullptr;
     const size_t bytes = size_t(n) * d * 4;
     CU_OK(cudaMalloc(&dev, bytes));
-    cudaError_t e = cudaMemcpy(dev, x, bytes, cudaMemcpyHostToDevice);
+    cudaError_t e = cudaMalloc(&out, bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&bits, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(bits, 0, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpy(dev, x, bytes, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
         unsigned grid = unsigned(std::min<uint64_t>((n * 32 + 255) / 256, 148ull * 16));
-        normalize_dense_kernel<<<grid, 256>>>(dev, n, d);
+        append_rows_kernel<false><<<grid, 256>>>(dev, out, n, d, int64_t(d), 1, 0, 0, 0, bits);
         LAUNCHED();
         e = cudaGetLastError();
     }
-    if (e == cudaSuccess) e = cudaMemcpy(x, dev, bytes, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(x, out, bytes, cudaMemcpyDeviceToHost);
     cudaFree(dev);
-    if (e != cudaSuccess) return fail(MVDB_ERR_CUDA, "normalize_L2 failed: %s", cudaGetErrorString(e));
+    cudaFree(out);
+    cudaFree(bits);
+    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? MVDB_ERR_OOM : MVDB_ERR_CUDA, "normalize_L2 failed: %s", cudaGetErrorString(e));
     return MVDB_OK;
 }
 

@@ -92,3 +92,39 @@ def test_faiss_shaped_index_object():
     D, I = idx.search(q, 7)
     D2, I2 = O.search_flat_ip(x, q, 7)
     assert np.array_equal(I, I2) and np.array_equal(D, D2)
+
+
+def test_reservoir_and_blocked_sgemm_paths_agree_with_gold():
+    """k >= 100 runs faiss's ReservoirTopN (capacity (2k+15)&~15, partition_fuzzy); nq >= 20 runs the
+    1024-row sgemm blocks feeding the block result handlers.  Both must select what the float64 gold
+    selects (near-ties excused), on random rows and on heavy duplicates (exact ties)."""
+    import numpy as np
+    from oracle import oracle as O
+    n, d = 20000, 64
+    x = O.synth_rows(5, 0, n, d)
+    O.normalize_L2(x)
+    q = O.synth_rows(6, 0, 24, d)
+    O.normalize_L2(q)
+    assert O._lib().orc_reservoir_capacity(100) == 208 and O._lib().orc_reservoir_capacity(128) == 256
+    for k in (1, 10, 99, 100, 128, 500):
+        Dg, Ig = O.gold_topk(x, q, k)
+        for D, I in (O.search_flat_ip(x, q, k), O.search_flat_ip_blas(x, q, k)):
+            rep = O.classify_parity(x, q, I, D, Ig, Dg)
+            assert rep["ok"], (k, rep)
+            assert np.all(np.diff(D, axis=1) <= 0)
+    xd = np.repeat(x[:300], 30, axis=0).copy()
+    for k in (10, 100, 130):
+        Dg, Ig = O.gold_topk(xd, q[:4], k)
+        for D, I in (O.search_flat_ip(xd, q[:4], k), O.search_flat_ip_blas(xd, q[:4], k)):
+            rep = O.classify_parity(xd, q[:4], I, D, Ig, Dg)
+            assert rep["ok"] and rep["real_error"] == 0, (k, rep)
+            assert all(len(set(r.tolist())) == k for r in I)          # no id twice
+    # streamed matrix = resident matrix
+    def chunk(r0, m):
+        return x[r0:r0 + m]
+    Db, Ib = O.search_flat_ip_blas(None, q, 100, make_chunk=chunk, n=n)
+    Dr, Ir = O.search_flat_ip_blas(x, q, 100)
+    assert np.array_equal(Ib, Ir) and np.array_equal(Db, Dr)
+    # fewer rows than k: padding
+    D, I = O.search_flat_ip_blas(x[:50], q, 100)
+    assert (I[:, 50:] == -1).all() and (I[:, :50] >= 0).all() and (D[:, 50:] == O.FLT_LOWEST).all()
