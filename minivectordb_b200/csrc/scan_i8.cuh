@@ -1,0 +1,461 @@
+// scan_i8.cuh -- opt-in low-precision scan mode ("scan_shadow" = 1): single-query search over an int8
+// SHADOW of the matrix, exact fp32 re-scoring of a rigorous candidate superset.
+//
+// Why: the fp32 scan already streams the matrix at the HBM roofline, so the only lever left for the
+// latency of ONE query is bytes.  The reference's own low-precision precedent is its usearch variant
+// (ref minivectordb/sharded_vector_database_usearch.py:621-627, int8 vectors); unlike that variant this
+// mode returns EXACTLY what the fp32 scan returns (ids and distances bit-identical, tested), because
+// the int8 pass only selects a superset of the true top-k and the survivors are re-scored from the fp32
+// master rows with the scan's own summation order.
+//
+// Shadow record of row r (stride rec_bytes = ld8 + 16, ld8 = d rounded up to 16):
+//     [ld8 x int8  xq = rint(x / s_r)] [f32 s_r = max|x| / 127] [f32 e_r >= ||x - s_r xq||_2] [8 B pad]
+// Query: two int8 planes q ~ q^ = s1 qq1 + s2 qq2 (the second plane quantises the residual of the
+// first, so the query-side error rq = ||q - q^||_2 is ~1e-5 and costs only a second dp4a).
+// For every row (Cauchy-Schwarz, all norms computed, not estimated):
+//     | q.x - s_r (s1 dot1 + s2 dot2) |  <=  ||q^|| e_r + rq ||x||  =: B_r            (exact arithmetic)
+// plus eps for the fp32 rounding of the scan's own score.  L_r = approx - B_r - eps is a lower bound of
+// the fp32 scan's score of row r, U_r = approx + B_r + eps an upper bound.
+// Threshold: every consumer warp publishes the best L it has seen (one word per warp, monotone); the
+// k-th largest of those words is a lower bound of the final k-th best score (k distinct rows reach it),
+// so a row with U_r below it can never enter the top-k.  Rows that pass are appended to a candidate
+// list; i8_finish_kernel re-scores them in fp32, drops what falls below the FINAL threshold, sorts the
+// few survivors and writes (D, I).  HBM traffic: N (d + 16) bytes instead of N d 4.
+#pragma once
+#include "scan.cuh"
+
+namespace mvdb {
+
+constexpr int kI8TileRows = 32;      // one word of the bitmasks
+constexpr int kI8MetaBytes = 16;
+constexpr int kI8MaxJ = 4;           // 16-byte chunks per lane: d <= 2048
+constexpr uint32_t kI8SurvCap = 4096;
+
+struct I8Ctl {                // zeroed by i8_prep_kernel before every search
+    unsigned int cand_cnt;    // candidates appended by the scan
+    unsigned int surv_cnt;    // candidates that survived the exact re-scoring
+    unsigned int ticket;      // finish kernel: CTAs done
+    unsigned int overflow;    // 1: a list overflowed -> the caller re-runs the query on the fp32 scan
+    unsigned int pad[4];
+};
+
+struct I8Params {
+    const uint8_t* x8;        // shadow records
+    const float* x;           // fp32 master matrix (re-scoring)
+    const float* qn;          // [ld] normalised fp32 query, zero padded (i8_prep_kernel)
+    const uint32_t* live;
+    const uint32_t* mask;
+    uint32_t* cand;           // [cand_cap] rows
+    uint64_t* surv;           // [kI8SurvCap] exact keys
+    unsigned int* best;       // [nbest] ordered images of the per-warp best lower bounds
+    I8Ctl* ctl;
+    float* outD;
+    int64_t* outI;
+    int64_t label_offset;
+    uint32_t n, cand_cap, nbest, rec_bytes, stage_bytes, stage_off;
+    int d, ld4, ld8, k, stages;
+    float max_norm;           // largest ||x_r|| stored in the index
+};
+
+__device__ __forceinline__ int reduce8i(const int (&a)[8], int lane) {
+    const unsigned full = 0xFFFFFFFFu;
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+    int b[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int mine = h16 ? a[i + 4] : a[i];
+        int give = h16 ? a[i] : a[i + 4];
+        b[i] = mine + __shfl_xor_sync(full, give, 16);
+    }
+    int c[2];
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        int mine = h8 ? b[i + 2] : b[i];
+        int give = h8 ? b[i] : b[i + 2];
+        c[i] = mine + __shfl_xor_sync(full, give, 8);
+    }
+    int mine = h4 ? c[1] : c[0];
+    int give = h4 ? c[0] : c[1];
+    int s = mine + __shfl_xor_sync(full, give, 4);
+    s += __shfl_xor_sync(full, s, 2);
+    s += __shfl_xor_sync(full, s, 1);
+    return s;
+}
+
+// k-th largest of `nvals` 32-bit words spread over the warp (v[i] = word lane + 32 i; 0 = empty):
+// bitwise bisection, 32 rounds of (compare, warp-wide count).  Returns 0 when fewer than k are non-zero.
+template <int M>
+__device__ __forceinline__ uint32_t warp_kth_largest_u32(const uint32_t (&v)[M], int k) {
+    uint32_t t = 0;
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; bit--) {
+        const uint32_t cand = t | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < M; i++) c += (v[i] >= cand) ? 1 : 0;
+        c = __reduce_add_sync(0xFFFFFFFFu, c);
+        if (c >= k) t = cand;
+    }
+    return t;
+}
+
+constexpr int kI8BestM = 40;   // up to 1280 consumer warps in a grid
+
+__device__ __forceinline__ uint32_t i8_threshold(const unsigned int* best, uint32_t nbest, int k, int lane) {
+    uint32_t v[kI8BestM];
+#pragma unroll
+    for (int i = 0; i < kI8BestM; i++) {
+        const uint32_t idx = uint32_t(lane) + 32u * uint32_t(i);
+        v[i] = (idx < nbest) ? __ldcg(best + idx) : 0u;
+    }
+    return warp_kth_largest_u32<kI8BestM>(v, k);
+}
+
+// ---------------------------------------------------------------------------
+// fp32 rows -> int8 shadow records (one warp per row, built lazily like the bf16 shadow)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) to_i8_rows_kernel(const float* __restrict__ in, uint8_t* __restrict__ out, uint64_t n,
+                                                         int ld4, int ld8, uint32_t rec_bytes) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+    const int w8 = ld8 >> 2;   // 32-bit words of int8 per record
+    for (uint64_t r = warp; r < n; r += nwarps) {
+        const float4* src = reinterpret_cast<const float4*>(in) + r * uint64_t(ld4);
+        uint8_t* rec = out + r * uint64_t(rec_bytes);
+        float mx = 0.f;
+        for (int c = lane; c < ld4; c += kWarp) {
+            const float4 v = src[c];
+            mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+        const float s = mx * (1.0f / 127.0f);
+        const float inv = s > 0.f ? 1.0f / s : 0.f;
+        float e2 = 0.f;
+        for (int c = lane; c < w8; c += kWarp) {
+            uint32_t word = 0;
+            if (c < ld4) {
+                const float4 v = src[c];
+                const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    int qv = __float2int_rn(f[t] * inv);
+                    qv = max(-127, min(127, qv));
+                    const float res = fmaf(-s, float(qv), f[t]);   // exact residual of this element (one rounding)
+                    e2 = fmaf(res, res, e2);
+                    word |= uint32_t(uint8_t(int8_t(qv))) << (8 * t);
+                }
+            }
+            reinterpret_cast<uint32_t*>(rec)[c] = word;
+        }
+        e2 = warp_allsum(e2);
+        if (lane == 0) {
+            // rounded UP: the sum of squares and the square root each lose at most a few ulp
+            float e = sqrtf(e2) * 1.00001f + 1e-30f;
+            reinterpret_cast<float*>(rec + ld8)[0] = s;
+            reinterpret_cast<float*>(rec + ld8)[1] = e;
+            reinterpret_cast<float*>(rec + ld8)[2] = 0.f;
+            reinterpret_cast<float*>(rec + ld8)[3] = 0.f;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// prologue launch: q -> normalised, zero-padded fp32 query (EXACTLY the arithmetic of the fp32 scan's
+// load_query_regs, so re-scored distances are bit-identical to it) and a clean control block
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) i8_prep_kernel(const float* __restrict__ q, float* __restrict__ qn, int d, int ld4,
+                                                      int normalize, I8Ctl* ctl, unsigned int* best, uint32_t nbest) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0) {
+        float nr = 0.f;
+        for (int c = lane; c < ld4; c += kWarp) {   // same chunk order as load_query_regs (j ascending)
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int b = 4 * c;
+            if (b + 0 < d) v.x = q[b + 0];
+            if (b + 1 < d) v.y = q[b + 1];
+            if (b + 2 < d) v.z = q[b + 2];
+            if (b + 3 < d) v.w = q[b + 3];
+            nr = dot4(v, v, nr);
+            reinterpret_cast<float4*>(qn)[c] = v;
+        }
+        nr = warp_allsum(nr);
+        if (normalize && nr > 0.f) {
+            const float inv = renorm_scale(nr);
+            __syncwarp();
+            for (int c = lane; c < ld4; c += kWarp) {
+                float4 v = reinterpret_cast<float4*>(qn)[c];
+                v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+                reinterpret_cast<float4*>(qn)[c] = v;
+            }
+        }
+        if (lane == 0) *ctl = I8Ctl{};
+    } else {
+        for (uint32_t i = threadIdx.x - 32; i < nbest; i += blockDim.x - 32) best[i] = 0u;
+    }
+}
+
+// shared-memory header of the int8 scan
+struct I8Header {
+    uint64_t full[16];
+    uint64_t empty[16];
+    unsigned int thr;     // CTA-wide copy of the threshold (ordered image), only ever raised
+};
+
+// ---------------------------------------------------------------------------
+// the scan: warp 0 = TMA producer (one bulk copy of 32 records per tile), warps 1.. = consumers
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(160, 1) scan_i8_kernel(const I8Params p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    I8Header* hdr = reinterpret_cast<I8Header*>(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ncw = (blockDim.x >> 5) - 1;
+    const int cw = warp - 1;
+    const uint32_t G = gridDim.x;
+    const uint32_t T = (p.n + kI8TileRows - 1) / kI8TileRows;
+    const uint32_t iters = (T > blockIdx.x) ? (T - blockIdx.x + G - 1) / G : 0;
+    const int S = p.stages;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; s++) {
+            mbar_init(&hdr->full[s], 1);
+            mbar_init(&hdr->empty[s], 1);
+        }
+        hdr->thr = 0u;
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint64_t pol = policy_evict_first();
+            int s = 0;
+            uint32_t ph = 0;
+            for (uint32_t it = 0; it < iters; it++) {
+                const uint32_t row0 = (blockIdx.x + it * G) * kI8TileRows;
+                const uint32_t bytes = min(uint32_t(kI8TileRows), p.n - row0) * p.rec_bytes;
+                mbar_wait(&hdr->empty[s], ph ^ 1u);
+                mbar_arrive_expect_tx(&hdr->full[s], bytes);
+                bulk_g2s(smem + p.stage_off + size_t(s) * p.stage_bytes, p.x8 + size_t(row0) * p.rec_bytes, bytes,
+                         &hdr->full[s], pol);
+                if (++s == S) {
+                    s = 0;
+                    ph ^= 1u;
+                }
+            }
+        }
+        return;
+    }
+
+    // ---- query: two int8 planes, their scales, ||q||, rq = ||q - q^||  (identical in every warp) ----
+    const int J = (p.ld8 / 16 + 31) / 32;
+    int4 q1[kI8MaxJ], q2[kI8MaxJ];
+    float s1, s2, qnorm, rq;
+    {
+        float f[kI8MaxJ][16];
+        float mx = 0.f, nr = 0.f;
+#pragma unroll
+        for (int j = 0; j < kI8MaxJ; j++) {
+            const int c = lane + 32 * j;   // 16-element chunk
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j < J && 4 * c + t < p.ld4) v = reinterpret_cast<const float4*>(p.qn)[4 * c + t];
+                f[j][4 * t + 0] = v.x; f[j][4 * t + 1] = v.y; f[j][4 * t + 2] = v.z; f[j][4 * t + 3] = v.w;
+                mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+                nr = dot4(v, v, nr);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+        nr = warp_allsum(nr);
+        qnorm = sqrtf(nr) * 1.00001f;
+        s1 = mx * (1.0f / 127.0f);
+        const float inv1 = s1 > 0.f ? 1.0f / s1 : 0.f;
+        float mx2 = 0.f;
+        int qa[kI8MaxJ][16];
+#pragma unroll
+        for (int j = 0; j < kI8MaxJ; j++)
+#pragma unroll
+            for (int t = 0; t < 16; t++) {
+                int qv = max(-127, min(127, __float2int_rn(f[j][t] * inv1)));
+                qa[j][t] = qv;
+                f[j][t] = fmaf(-s1, float(qv), f[j][t]);   // residual of plane 1
+                mx2 = fmaxf(mx2, fabsf(f[j][t]));
+            }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx2 = fmaxf(mx2, __shfl_xor_sync(0xFFFFFFFFu, mx2, o));
+        s2 = mx2 * (1.0f / 127.0f);
+        const float inv2 = s2 > 0.f ? 1.0f / s2 : 0.f;
+        float r2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < kI8MaxJ; j++) {
+            uint32_t w1[4] = {0, 0, 0, 0}, w2[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int t = 0; t < 16; t++) {
+                const int qb = max(-127, min(127, __float2int_rn(f[j][t] * inv2)));
+                const float res = fmaf(-s2, float(qb), f[j][t]);
+                r2 = fmaf(res, res, r2);
+                w1[t >> 2] |= uint32_t(uint8_t(int8_t(qa[j][t]))) << (8 * (t & 3));
+                w2[t >> 2] |= uint32_t(uint8_t(int8_t(qb))) << (8 * (t & 3));
+            }
+            q1[j] = make_int4(int(w1[0]), int(w1[1]), int(w1[2]), int(w1[3]));
+            q2[j] = make_int4(int(w2[0]), int(w2[1]), int(w2[2]), int(w2[3]));
+        }
+        r2 = warp_allsum(r2);
+        rq = sqrtf(r2) * 1.00001f + 1e-30f;
+    }
+    // B_r = qhat_norm * e_r + bconst;  eps covers the fp32 rounding of the scan's own score (gamma_d ||q|| ||x||),
+    // of `approx` below and of this bound's own arithmetic
+    const float qhat_norm = (qnorm + rq) * 1.0001f;
+    const float bconst = (rq * p.max_norm + (float(p.d) * 1.2e-7f + 4e-6f) * qnorm * p.max_norm) * 1.0001f;
+
+    const int my_row = tile_row_of_lane(lane);
+    const bool leader = (lane & 3) == 0;
+    const uint32_t gw = blockIdx.x * uint32_t(ncw) + uint32_t(cw);   // this warp's slot in p.best
+    uint32_t my_best = 0u, thr = 0u;
+    uint32_t done_tiles = 0, next_refresh = 1;
+    for (uint32_t it = cw; it < iters; it += ncw) {
+        const uint32_t tile = blockIdx.x + it * G;
+        const uint32_t row0 = tile * kI8TileRows;
+        uint32_t adm = 0xFFFFFFFFu;
+        if (p.mask) adm &= p.mask[tile];
+        if (p.live) adm &= p.live[tile];
+        thr = max(thr, *reinterpret_cast<volatile unsigned int*>(&hdr->thr));
+        const int s = it % S;
+        mbar_wait(&hdr->full[s], (it / S) & 1u);
+        const uint8_t* st = smem + p.stage_off + size_t(s) * p.stage_bytes;
+        uint32_t pass_rows = 0;   // bit i: row i of the tile is a candidate (built by the leaders, warp-uniform after ballot)
+#pragma unroll 1
+        for (int g = 0; g < 4; g++) {
+            int a1[8], a2[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) a1[r] = a2[r] = 0;
+#pragma unroll
+            for (int j = 0; j < kI8MaxJ; j++) {
+                const int c = lane + 32 * j;
+                if (j < J && c * 16 < p.ld8) {
+#pragma unroll
+                    for (int r = 0; r < 8; r++) {
+                        const int4 v = *reinterpret_cast<const int4*>(st + size_t(g * 8 + r) * p.rec_bytes + c * 16);
+                        a1[r] = __dp4a(v.x, q1[j].x, a1[r]); a1[r] = __dp4a(v.y, q1[j].y, a1[r]);
+                        a1[r] = __dp4a(v.z, q1[j].z, a1[r]); a1[r] = __dp4a(v.w, q1[j].w, a1[r]);
+                        a2[r] = __dp4a(v.x, q2[j].x, a2[r]); a2[r] = __dp4a(v.y, q2[j].y, a2[r]);
+                        a2[r] = __dp4a(v.z, q2[j].z, a2[r]); a2[r] = __dp4a(v.w, q2[j].w, a2[r]);
+                    }
+                }
+            }
+            const int d1 = reduce8i(a1, lane), d2 = reduce8i(a2, lane);
+            const int rt = g * 8 + my_row;   // row of the tile this quad is responsible for
+            const uint32_t row = row0 + uint32_t(rt);
+            bool pass = false;
+            if (leader && row < p.n && ((adm >> rt) & 1u)) {
+                const float2 m = *reinterpret_cast<const float2*>(st + size_t(rt) * p.rec_bytes + p.ld8);
+                const float approx = m.x * fmaf(s1, float(d1), s2 * float(d2));
+                const float B = fmaf(qhat_norm, m.y, bconst);
+                const uint32_t lo = score_to_ord(approx - B), up = score_to_ord(approx + B);
+                my_best = max(my_best, lo);
+                pass = up >= thr;
+            }
+            pass_rows |= (__ballot_sync(0xFFFFFFFFu, pass) & 0x11111111u) ? 0u : 0u;   // (keeps the ballot warp-convergent)
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, pass);
+            if (m) {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(&p.ctl->cand_cnt, unsigned(__popc(m)));
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                const unsigned pos = base + unsigned(__popc(m & ((1u << lane) - 1u)));
+                if (pass && pos < p.cand_cap) p.cand[pos] = row;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&hdr->empty[s]);
+        // publish this warp's best lower bound (monotone; one word per warp, so a reader never sees a torn value)
+        const uint32_t wb = __reduce_max_sync(0xFFFFFFFFu, my_best);
+        if (wb > my_best || (lane == 0 && wb != 0u)) {
+            // every lane adopts the warp's best; lane 0 stores it when it grew
+        }
+        if (lane == 0 && wb > *reinterpret_cast<volatile unsigned int*>(p.best + gw)) *reinterpret_cast<volatile unsigned int*>(p.best + gw) = wb;
+        my_best = wb;
+        // refresh the threshold after 1, 2, 4, ... tiles of this warp, then every 32: k-th largest of all warps' bests
+        if (++done_tiles == next_refresh) {
+            next_refresh = done_tiles < 32 ? done_tiles * 2 : done_tiles + 32;
+            const uint32_t t = i8_threshold(p.best, p.nbest, p.k, lane);
+            if (t > thr) {
+                thr = t;
+                if (lane == 0) atomicMax(&hdr->thr, t);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// finish: exact fp32 re-scoring of the candidates with the scan's summation order (per-lane chunk order
+// + xor butterfly == reduce8's tree, as rescore_kernel), keep what reaches the FINAL threshold, and the
+// last CTA to finish sorts the survivors and writes (D, I).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) i8_finish_kernel(const I8Params p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    float4* qs = reinterpret_cast<float4*>(smem);                       // [ld4]
+    uint64_t* sk = reinterpret_cast<uint64_t*>(smem + size_t(p.ld4) * 16);   // [kI8SurvCap] (last CTA only)
+    __shared__ uint32_t thr_s;
+    __shared__ int last_s;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const unsigned int raw_cnt = p.ctl->cand_cnt;
+    const unsigned int cnt = min(raw_cnt, p.cand_cap);
+    for (int c = threadIdx.x; c < p.ld4; c += blockDim.x) qs[c] = reinterpret_cast<const float4*>(p.qn)[c];
+    if (warp == 0) {
+        const uint32_t t = i8_threshold(p.best, p.nbest, p.k, lane);
+        if (lane == 0) thr_s = t;
+    }
+    __syncthreads();
+    const uint32_t thr = thr_s;
+    const unsigned int gwarp = blockIdx.x * nw + warp, nwarps = gridDim.x * nw;
+    for (unsigned int i = gwarp; i < cnt; i += nwarps) {
+        const uint32_t row = p.cand[i];
+        const float4* xr = reinterpret_cast<const float4*>(p.x) + size_t(row) * p.ld4;
+        float acc = 0.f;
+        for (int c = lane; c < p.ld4; c += kWarp) acc = dot4(ldg_stream(xr + c), qs[c], acc);
+        acc = warp_allsum(acc);
+        if (lane == 0 && acc == acc && score_to_ord(acc) >= thr) {
+            const unsigned pos = atomicAdd(&p.ctl->surv_cnt, 1u);
+            if (pos < kI8SurvCap) p.surv[pos] = make_key(acc, row);
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last_s = (atomicAdd(&p.ctl->ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!last_s) return;
+    __threadfence();
+    const unsigned int ns_raw = *reinterpret_cast<volatile unsigned int*>(&p.ctl->surv_cnt);
+    if (raw_cnt > p.cand_cap || ns_raw > kI8SurvCap) {
+        if (threadIdx.x == 0) p.ctl->overflow = 1u;   // the caller's conditional fp32 scan answers this query instead
+        return;
+    }
+    const unsigned int ns = ns_raw;
+    uint32_t npad = 64;
+    while (npad < ns) npad <<= 1;
+    for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x) sk[i] = i < ns ? __ldcg(p.surv + i) : kEmptyKey;
+    __syncthreads();
+    if (npad <= 256) {
+        if (warp == 0) {
+            if (npad == 64) warp_sort_buffer<2>(sk, int(ns), lane);
+            else if (npad == 128) warp_sort_buffer<4>(sk, int(ns), lane);
+            else warp_sort_buffer<8>(sk, int(ns), lane);
+        }
+    } else {
+        bitonic_sort_desc(sk, int(npad), int(threadIdx.x), int(blockDim.x), BlockSyncer());
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.k; i += blockDim.x) {
+        const uint64_t key = (unsigned(i) < ns) ? sk[i] : kEmptyKey;
+        if (key == kEmptyKey) {
+            p.outD[i] = -FLT_MAX;
+            p.outI[i] = -1;
+        } else {
+            p.outD[i] = key_score(key);
+            p.outI[i] = int64_t(key_row(key)) + p.label_offset;
+        }
+    }
+}
+
+}  // namespace mvdb
