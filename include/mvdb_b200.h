@@ -103,6 +103,14 @@ int mvdb_index_reset(mvdb_index* ix);
  *   "gemm_variant"  tile scheme of the tensor-core batch: 0 one CTA per 128x256 tile, 1 CTA pairs
  *                   (cta_group::2), 2 clusters of 2 sharing the row tile by TMA multicast
  *                   (default), 3 clusters of 4; "gemm_l2_hint" 0/1/2 L2 eviction hints (A/B)
+ *   "scan_shadow"   (default 0) 1 = single-query searches (k <= 128, d <= 1024, >= 16384 rows) stream an int8
+ *                   SHADOW of the matrix (d + 16 bytes per row instead of 4 d; built lazily, kept in step
+ *                   with appends) to select a rigorous candidate superset, and re-score the survivors from
+ *                   the fp32 rows with the scan's own summation order: ids AND distances are bit-identical
+ *                   to the fp32 scan, at ~1/4 of the HBM traffic.  The reference's low-precision precedent
+ *                   is its usearch/int8 variant (sharded_vector_database_usearch.py:621-627); this mode is
+ *                   exact.  A query whose candidate list overflows is answered by the fp32 scan (an on-device
+ *                   conditional launch, no host round trip).
  *   "l2_pin_mb"     experiment: keep the head of the matrix L2-resident across scans (default 0)
  *   test / profiling hooks (see the mvdb_debug_* functions): "trace", "gemm_prof", and
  *   "gemm_debug" (bit mask that switches parts of the GEMM kernel OFF -- results are garbage) */

@@ -31,6 +31,7 @@
 #include "aux_kernels.cuh"
 #include "gemm_tc.cuh"
 #include "scan.cuh"
+#include "scan_i8.cuh"
 
 using namespace mvdb;
 
@@ -314,6 +315,13 @@ struct mvdb_workspace {
     size_t b_lqptr_cap = 0;
     uint32_t* b_lqwords = nullptr;
     size_t b_lqwords_cap = 0;
+    // int8 shadow mode (scan_i8.cuh)
+    uint32_t* i8_cand = nullptr;
+    uint64_t* i8_surv = nullptr;
+    unsigned int* i8_best = nullptr;
+    I8Ctl* i8_ctl = nullptr;
+    float* i8_qn = nullptr;
+    size_t i8_qn_cap = 0;
     // host-buffer path
     float* q_dev = nullptr;
     size_t q_cap = 0;
@@ -391,6 +399,13 @@ struct mvdb_index {
     int64_t ld16 = 0;              // bf16 elements per shadow row (multiple of 8)
     uint64_t shadow_rows = 0;
     std::mutex shadow_mu;
+    // int8 shadow of the matrix for the opt-in low-precision single-query mode (option "scan_shadow"; built lazily)
+    GrowBuf mat8;
+    int ld8 = 0;                    // int8 elements per record (d rounded up to 16)
+    uint32_t rec8 = 0;              // record stride in bytes (ld8 + 16: scale, residual norm, pad)
+    uint64_t shadow8_rows = 0;
+    std::mutex shadow8_mu;
+    int scan_shadow = 0;
     int* max_norm2_bits = nullptr;  // device: bit pattern of the largest squared row norm stored
     std::atomic<float> max_norm2_host{0.f};  // host copy, refreshed at the end of every add
     // options
@@ -927,6 +942,97 @@ static int run_batched(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, i
     return rc;
 }
 
+// bring the int8 shadow up to `n` rows
+static int ensure_shadow8(mvdb_index* ix, uint64_t n) {
+    std::lock_guard<std::mutex> g(ix->shadow8_mu);
+    if (ix->shadow8_rows >= n) return MVDB_OK;
+    cudaStream_t st = ix->mut_stream;
+    RC_OK(ix->mat8.ensure(size_t(n) * ix->rec8, st));
+    const uint64_t r0 = ix->shadow8_rows, m = n - r0;
+    unsigned grid = unsigned(std::min<uint64_t>((m * 32 + 255) / 256, uint64_t(ix->sm_count) * 16));
+    to_i8_rows_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(ix->mat.ptr()) + r0 * ix->ld,
+                                            static_cast<uint8_t*>(ix->mat8.ptr()) + r0 * ix->rec8, m, ix->ld4, ix->ld8, ix->rec8);
+    LAUNCHED();
+    CU_OK(cudaGetLastError());
+    CU_OK(cudaStreamSynchronize(st));
+    ix->shadow8_rows = n;
+    return MVDB_OK;
+}
+
+static constexpr uint32_t kI8CandCap = 16384;
+static constexpr int kI8ConsumerWarps = 4;
+
+// Can this search take the int8 shadow mode?  One query, fused-k range, rows narrow enough for a >= 4-deep
+// ring of 32-record tiles, and enough rows for the shadow pass to pay for its two extra launches.
+static bool i8_eligible(const mvdb_index* ix, int64_t nq, int64_t k, uint32_t n) {
+    if (!ix->scan_shadow || nq != 1 || k > 128 || k > ix->fused_k_max || n < 16384 || ix->d > 1024) return false;
+    const size_t stage = align_up(size_t(kI8TileRows) * ix->rec8, 128);
+    return (ix->smem_optin - 1024) / stage >= size_t(kI8ConsumerWarps);
+}
+
+// prep (normalise the query, clear the control block) -> int8 scan -> exact re-scoring + select.
+// On return *run_if points at the device flag that is raised when a candidate list overflowed: the caller
+// enqueues the fp32 scan behind it as a conditional launch (a no-op otherwise), so the answer is always
+// the fp32 scan's, with no host round trip.
+static int run_i8(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, int64_t k, const uint32_t* mask_dev, uint32_t n,
+                  int normalize_q, int64_t label_offset, float* D_dev, int64_t* I_dev, cudaStream_t stream,
+                  const unsigned int** run_if) {
+    RC_OK(ensure_shadow8(ix, n));
+    if (!ws->i8_ctl) {
+        CU_OK(cudaMalloc(&ws->i8_ctl, sizeof(I8Ctl)));
+        CU_OK(cudaMalloc(&ws->i8_cand, size_t(kI8CandCap) * 4));
+        CU_OK(cudaMalloc(&ws->i8_surv, size_t(kI8SurvCap) * 8));
+        CU_OK(cudaMalloc(&ws->i8_best, size_t(kI8BestM) * 32 * 4));
+    }
+    RC_OK(grow_dev(&ws->i8_qn, &ws->i8_qn_cap, size_t(ix->ld)));
+    I8Params p = {};
+    p.x8 = static_cast<const uint8_t*>(ix->mat8.ptr());
+    p.x = static_cast<const float*>(ix->mat.ptr());
+    p.qn = ws->i8_qn;
+    p.live = ix->ndead.load(std::memory_order_acquire) ? static_cast<const uint32_t*>(ix->live.ptr()) : nullptr;
+    p.mask = mask_dev;
+    p.cand = ws->i8_cand;
+    p.surv = ws->i8_surv;
+    p.best = ws->i8_best;
+    p.ctl = ws->i8_ctl;
+    p.outD = D_dev;
+    p.outI = I_dev;
+    p.label_offset = label_offset;
+    p.n = n;
+    p.cand_cap = kI8CandCap;
+    p.rec_bytes = ix->rec8;
+    p.stage_bytes = uint32_t(align_up(size_t(kI8TileRows) * ix->rec8, 128));
+    p.stage_off = 1024;
+    p.d = ix->d;
+    p.ld4 = ix->ld4;
+    p.ld8 = ix->ld8;
+    p.k = int(k);
+    int stages = int(std::min<size_t>(16, (ix->smem_optin - 1024) / p.stage_bytes));
+    stages = stages / kI8ConsumerWarps * kI8ConsumerWarps;
+    p.stages = stages;
+    p.max_norm = std::sqrt(std::max(ix->max_norm2_host.load(std::memory_order_acquire), 0.f)) * 1.0001f;
+    const uint32_t tiles = (n + kI8TileRows - 1) / kI8TileRows;
+    const int grid = int(std::min<uint32_t>(uint32_t(ix->sm_count), tiles));
+    p.nbest = uint32_t(grid) * kI8ConsumerWarps;
+    if (p.nbest > uint32_t(kI8BestM) * 32) return fail(MVDB_ERR_STATE, "int8 scan: too many consumer warps for the threshold table");
+    const size_t smem = size_t(p.stage_off) + size_t(stages) * p.stage_bytes;
+    static std::once_flag attr_once[16];
+    cudaError_t ae = cudaSuccess;
+    std::call_once(attr_once[ix->device & 15], [&] {
+        ae = cudaFuncSetAttribute(scan_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ix->smem_optin));
+    });
+    CU_OK(ae);
+    i8_prep_kernel<<<1, 256, 0, stream>>>(q_dev, ws->i8_qn, ix->d, ix->ld4, normalize_q, ws->i8_ctl, ws->i8_best, p.nbest);
+    LAUNCHED();
+    scan_i8_kernel<<<grid, 32 * (1 + kI8ConsumerWarps), smem, stream>>>(p);
+    LAUNCHED();
+    i8_finish_kernel<<<64, 256, size_t(ix->ld4) * 16 + size_t(kI8SurvCap) * 8, stream>>>(p);
+    LAUNCHED();
+    CU_OK(cudaGetLastError());
+    *run_if = &ws->i8_ctl->overflow;
+    return MVDB_OK;
+}
+
 // Core search on device buffers.  Caller holds move_mu shared.
 static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, int64_t nq, int64_t k,
                       const uint32_t* mask_dev, uint64_t mask_rows, int normalize_q, int64_t label_offset,
@@ -996,7 +1102,13 @@ static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, in
         return run_batched(ix, ws, q_dev, nq, k, mask_dev, n, normalize_q, label_offset, D_dev, I_dev, stream,
                            ix->batch_mode, nullptr, any_qmask ? qmasks : nullptr);
     RC_OK(ws_scratch(ws));
+    // opt-in int8 shadow mode: the whole query is answered by the shadow pass + exact re-scoring; the fp32
+    // scan below is still enqueued, as a conditional launch that only runs if a candidate list overflowed
+    const unsigned int* run_if = nullptr;
+    if (!xch && !tl_force_scan && !any_qmask && i8_eligible(ix, nq, k, n))
+        RC_OK(run_i8(ix, ws, q_dev, k, mask_dev, n, normalize_q, label_offset, D_dev, I_dev, stream, &run_if));
     ScanParams p = {};
+    p.run_if = run_if;
     p.x = static_cast<const float*>(ix->mat.ptr());
     p.live = ix->ndead.load(std::memory_order_acquire) ? static_cast<const uint32_t*>(ix->live.ptr()) : nullptr;
     p.mask = mask_dev;
@@ -1065,7 +1177,7 @@ static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, in
                 p.tile_ctr = ws->ticket + 32 + 32 * (ws->launch_seq++ & 1u);
             }
             p.pdl_early = 0;
-            if (ix->pdl && tl_allow_pdl) {
+            if (ix->pdl && tl_allow_pdl && !run_if) {
                 // Entry trigger only when this launch AND the previous scan of this workspace fill every SM
                 // with one CTA each: then a CTA of this grid can only start where the previous grid has left,
                 // all of them have started only once the previous grid is complete, and the grid after this
@@ -1169,6 +1281,11 @@ static void ws_free(mvdb_workspace* ws) {
     cudaFree(ws->b_lqmask);
     cudaFree(ws->b_lqptr);
     cudaFree(ws->b_lqwords);
+    cudaFree(ws->i8_cand);
+    cudaFree(ws->i8_surv);
+    cudaFree(ws->i8_best);
+    cudaFree(ws->i8_ctl);
+    cudaFree(ws->i8_qn);
     cudaFree(ws->q_dev);
     cudaFree(ws->mask_dev);
     cudaFree(ws->I_dev);
@@ -1274,6 +1391,9 @@ int mvdb_index_create(int d, int device, uint64_t capacity_hint, mvdb_index** ou
     reserve = std::max(reserve, size_t(1) << 21);
     int rc = ix->mat.init(device, reserve);
     if (rc == MVDB_OK) rc = ix->live.init(device, std::max<size_t>(reserve / (size_t(ix->ld) * 4) / 8 + 4096, size_t(1) << 21));
+    ix->ld8 = int(align_up(size_t(d), 16));
+    ix->rec8 = uint32_t(ix->ld8 + kI8MetaBytes);
+    if (rc == MVDB_OK) rc = ix->mat8.init(device, std::max<size_t>(reserve / (size_t(ix->ld) * 4) * ix->rec8, size_t(1) << 21));
     ix->ld16 = int64_t(align_up(size_t(d), 8));
     if (rc == MVDB_OK) rc = ix->mat16.init(device, std::max<size_t>(reserve / (size_t(ix->ld) * 4) * ix->ld16 * 2, size_t(1) << 21));
     cudaError_t e = cudaStreamCreateWithFlags(&ix->mut_stream, cudaStreamNonBlocking);
@@ -1284,6 +1404,7 @@ int mvdb_index_create(int d, int device, uint64_t capacity_hint, mvdb_index** ou
         ix->mat.destroy();
         ix->live.destroy();
         ix->mat16.destroy();
+        ix->mat8.destroy();
         delete ix;
         return rc != MVDB_OK ? rc : fail(MVDB_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
     }
@@ -1300,6 +1421,7 @@ int mvdb_index_destroy(mvdb_index* ix) {
     ix->mat.destroy();
     ix->live.destroy();
     ix->mat16.destroy();
+    ix->mat8.destroy();
     cudaFree(ix->max_norm2_bits);
     cudaFree(ix->count_dev);
     cudaFree(ix->stage_dev[0]);
@@ -1324,6 +1446,10 @@ int mvdb_index_reset(mvdb_index* ix) {
     {
         std::lock_guard<std::mutex> sg(ix->shadow_mu);
         ix->shadow_rows = 0;
+    }
+    {
+        std::lock_guard<std::mutex> sg(ix->shadow8_mu);
+        ix->shadow8_rows = 0;
     }
     return MVDB_OK;
 }
@@ -1375,6 +1501,9 @@ int mvdb_index_set_option(mvdb_index* ix, const char* name, int64_t value) {
         ix->co_max_leaders = int(value);
     } else if (s == "pdl") {
         ix->pdl = value != 0;
+    } else if (s == "scan_shadow") {
+        if (value < 0 || value > 1) return fail(MVDB_ERR_ARG, "scan_shadow must be 0 (fp32 scan) or 1 (int8 shadow + exact fp32 re-scoring)");
+        ix->scan_shadow = int(value);
     } else if (s == "dyn_tiles") {
         if (value < 0 || value > 100) return fail(MVDB_ERR_ARG, "dyn_tiles is a percentage, 0..100");
         ix->dyn_tiles = int(value);
@@ -1578,6 +1707,10 @@ int mvdb_index_compact(mvdb_index* ix, int64_t* ntotal_out) {
     {
         std::lock_guard<std::mutex> sg(ix->shadow_mu);
         ix->shadow_rows = std::min<uint64_t>(ix->shadow_rows, first);  // rows past the first moved one are stale
+    }
+    {
+        std::lock_guard<std::mutex> sg(ix->shadow8_mu);
+        ix->shadow8_rows = std::min<uint64_t>(ix->shadow8_rows, first);
     }
     if (ntotal_out) *ntotal_out = int64_t(nl);
     return MVDB_OK;

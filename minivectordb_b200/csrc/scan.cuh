@@ -61,6 +61,7 @@ struct ScanParams {
     const uint32_t* qmask[8];    // per-query admissible bitmasks (coalesced searches; nullptr = none); multi kernel only
     uint32_t qmask_bytes[8];     // bytes available behind qmask[i]; rows past them are not admissible
     int has_qmask;
+    const unsigned int* run_if;  // not null: the whole launch is a no-op unless *run_if != 0 (fallback behind the int8 mode)
     const struct XchgDev* xchg;  // fused cross-GPU exchange (nullptr = single GPU)
     uint64_t xchg_seq;           // sequence number of this launch (same on every rank, > 0)
 };
@@ -640,6 +641,7 @@ __global__ void __launch_bounds__(kTma ? 288 : 256, kTma ? 1 : 2) scan_q1_kernel
     const int ncw = (blockDim.x >> 5) - (kTma ? 1 : 0);
     const int cw = warp - (kTma ? 1 : 0);
     const uint32_t G = gridDim.x;
+    if (p.run_if && *p.run_if == 0u) return;    // conditional launch: nothing to redo
     if (p.pdl_early) pdl_launch_dependents();   // one CTA per SM: the next search may take over every SM we leave
     const uint32_t T = (p.n + kRowsPerTile - 1) / kRowsPerTile;
     const uint32_t iters = (T > blockIdx.x) ? (T - blockIdx.x + G - 1) / G : 0;

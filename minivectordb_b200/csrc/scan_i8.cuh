@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(160, 1) scan_i8_kernel(const I8Params p) {
     const int my_row = tile_row_of_lane(lane);
     const bool leader = (lane & 3) == 0;
     const uint32_t gw = blockIdx.x * uint32_t(ncw) + uint32_t(cw);   // this warp's slot in p.best
-    uint32_t my_best = 0u, thr = 0u;
+    uint32_t my_best = 0u, published = 0u, thr = 0u;
     uint32_t done_tiles = 0, next_refresh = 1;
     for (uint32_t it = cw; it < iters; it += ncw) {
         const uint32_t tile = blockIdx.x + it * G;
@@ -324,7 +324,6 @@ __global__ void __launch_bounds__(160, 1) scan_i8_kernel(const I8Params p) {
         const int s = it % S;
         mbar_wait(&hdr->full[s], (it / S) & 1u);
         const uint8_t* st = smem + p.stage_off + size_t(s) * p.stage_bytes;
-        uint32_t pass_rows = 0;   // bit i: row i of the tile is a candidate (built by the leaders, warp-uniform after ballot)
 #pragma unroll 1
         for (int g = 0; g < 4; g++) {
             int a1[8], a2[8];
@@ -352,11 +351,13 @@ __global__ void __launch_bounds__(160, 1) scan_i8_kernel(const I8Params p) {
                 const float2 m = *reinterpret_cast<const float2*>(st + size_t(rt) * p.rec_bytes + p.ld8);
                 const float approx = m.x * fmaf(s1, float(d1), s2 * float(d2));
                 const float B = fmaf(qhat_norm, m.y, bconst);
-                const uint32_t lo = score_to_ord(approx - B), up = score_to_ord(approx + B);
-                my_best = max(my_best, lo);
-                pass = up >= thr;
+                if (approx == approx) {
+                    my_best = max(my_best, score_to_ord(approx - B));
+                    pass = score_to_ord(approx + B) >= thr;
+                } else {
+                    pass = true;   // not a number: let the exact re-scoring decide (the fp32 scan drops NaN scores)
+                }
             }
-            pass_rows |= (__ballot_sync(0xFFFFFFFFu, pass) & 0x11111111u) ? 0u : 0u;   // (keeps the ballot warp-convergent)
             const unsigned m = __ballot_sync(0xFFFFFFFFu, pass);
             if (m) {
                 unsigned base = 0;
@@ -370,10 +371,10 @@ __global__ void __launch_bounds__(160, 1) scan_i8_kernel(const I8Params p) {
         if (lane == 0) mbar_arrive(&hdr->empty[s]);
         // publish this warp's best lower bound (monotone; one word per warp, so a reader never sees a torn value)
         const uint32_t wb = __reduce_max_sync(0xFFFFFFFFu, my_best);
-        if (wb > my_best || (lane == 0 && wb != 0u)) {
-            // every lane adopts the warp's best; lane 0 stores it when it grew
+        if (wb > published) {
+            published = wb;
+            if (lane == 0) *reinterpret_cast<volatile unsigned int*>(p.best + gw) = wb;
         }
-        if (lane == 0 && wb > *reinterpret_cast<volatile unsigned int*>(p.best + gw)) *reinterpret_cast<volatile unsigned int*>(p.best + gw) = wb;
         my_best = wb;
         // refresh the threshold after 1, 2, 4, ... tiles of this warp, then every 32: k-th largest of all warps' bests
         if (++done_tiles == next_refresh) {
