@@ -307,6 +307,11 @@ int mvdb_debug_read_trace(mvdb_index* ix, uint64_t* out16);
  * GemmParams::prof in csrc/gemm_tc.cuh); reads the counters of the most recent launch. */
 int mvdb_debug_read_gemm_prof(mvdb_index* ix, uint64_t* out, int ctas);
 
+/* Test hook: counters of the LAST int8 shadow search ("scan_shadow") run on this workspace through
+ * mvdb_index_search_device: out4 = {candidates the int8 pass selected, candidates that survived the exact
+ * re-scoring, 1 if a list overflowed and the fp32 scan answered instead, 0}. */
+int mvdb_debug_read_shadow_counters(mvdb_workspace* ws, uint32_t* out4);
+
 /* Number of kernel launches issued by this library since load (bench.py's
  * "gpu_launches" claim is read from here). */
 uint64_t mvdb_launch_count(void);

@@ -41,6 +41,7 @@ EXPORTS = [
     "mvdb_mask_create_filled", "mvdb_mask_combine", "mvdb_mask_count", "mvdb_debug_read_trace", "mvdb_debug_read_gemm_prof",
     "mvdb_exchange_connect_local", "mvdb_exchange_set_option",
     "mvdb_group_create", "mvdb_group_destroy", "mvdb_group_set_option", "mvdb_group_search",
+    "mvdb_debug_read_shadow_counters",
 ]
 
 
@@ -156,6 +157,7 @@ def lib():
             "mvdb_group_destroy": (i, [c_vp]),
             "mvdb_group_set_option": (i, [c_vp, ctypes.c_char_p, i64]),
             "mvdb_group_search": (i, [c_vp, c_vp, i64, i64, c_vp, c_vp, c_vp, i, c_vp, c_vp]),
+            "mvdb_debug_read_shadow_counters": (i, [c_vp, c_vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)

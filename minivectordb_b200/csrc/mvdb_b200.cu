@@ -41,6 +41,7 @@ using namespace mvdb;
 static thread_local std::string g_err;
 static thread_local bool tl_allow_pdl = false;    // set by the device-buffer entry points (option "pdl")
 static thread_local bool tl_force_scan = false;   // overflow fallback of the batched path: stay on the fp32 scan
+static thread_local bool tl_host_checks_i8 = false;   // the caller synchronises and re-runs an overflowed int8 search itself
 static std::atomic<uint64_t> g_launches{0};
 
 static int fail(int code, const char* fmt, ...) {
@@ -316,12 +317,11 @@ struct mvdb_workspace {
     uint32_t* b_lqwords = nullptr;
     size_t b_lqwords_cap = 0;
     // int8 shadow mode (scan_i8.cuh)
-    uint32_t* i8_cand = nullptr;
     uint64_t* i8_surv = nullptr;
+    unsigned int* i8_ovf_pin = nullptr;   // pinned + mapped: raised by the kernel when the survivor list overflowed
+    unsigned int* i8_ovf_dev = nullptr;
     unsigned int* i8_best = nullptr;
     I8Ctl* i8_ctl = nullptr;
-    float* i8_qn = nullptr;
-    size_t i8_qn_cap = 0;
     // host-buffer path
     float* q_dev = nullptr;
     size_t q_cap = 0;
@@ -959,77 +959,93 @@ static int ensure_shadow8(mvdb_index* ix, uint64_t n) {
     return MVDB_OK;
 }
 
-static constexpr uint32_t kI8CandCap = 16384;
-static constexpr int kI8ConsumerWarps = 4;
-
-// Can this search take the int8 shadow mode?  One query, fused-k range, rows narrow enough for a >= 4-deep
-// ring of 32-record tiles, and enough rows for the shadow pass to pay for its two extra launches.
-static bool i8_eligible(const mvdb_index* ix, int64_t nq, int64_t k, uint32_t n) {
-    if (!ix->scan_shadow || nq != 1 || k > 128 || k > ix->fused_k_max || n < 16384 || ix->d > 1024) return false;
+// consumer warps of the int8 scan: 8 when the ring can be >= 8 tiles deep, else 4 (rows wider than ~800 bytes)
+static int i8_consumer_warps(const mvdb_index* ix) {
+    const size_t q_bytes = align_up(size_t(ix->ld) * 4, 128);
     const size_t stage = align_up(size_t(kI8TileRows) * ix->rec8, 128);
-    return (ix->smem_optin - 1024) / stage >= size_t(kI8ConsumerWarps);
+    const size_t raw = (ix->smem_optin - 1024 - q_bytes) / stage;
+    return raw >= 8 ? 8 : raw >= 4 ? 4 : 0;
 }
 
-// prep (normalise the query, clear the control block) -> int8 scan -> exact re-scoring + select.
-// On return *run_if points at the device flag that is raised when a candidate list overflowed: the caller
-// enqueues the fp32 scan behind it as a conditional launch (a no-op otherwise), so the answer is always
-// the fp32 scan's, with no host round trip.
-static int run_i8(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, int64_t k, const uint32_t* mask_dev, uint32_t n,
-                  int normalize_q, int64_t label_offset, float* D_dev, int64_t* I_dev, cudaStream_t stream,
-                  const unsigned int** run_if) {
+// Can this search take the int8 shadow mode?  One query, fused-k range, rows narrow enough for a >= 4-deep
+// ring of 32-record tiles, and enough rows for the shadow pass to beat the fp32 scan's fixed costs.
+static bool i8_eligible(const mvdb_index* ix, int64_t nq, int64_t k, uint32_t n) {
+    if (!ix->scan_shadow || nq != 1 || k > 128 || k > ix->fused_k_max || n < 16384 || ix->d > 1024) return false;
+    return i8_consumer_warps(ix) != 0;
+}
+
+// everything the int8 mode sets up lazily (shadow rows, scratch, shared-memory opt-in): all of it may
+// synchronise the device, so a shard group does it before its first launch (prepare_fused_scan)
+static int i8_prepare(mvdb_index* ix, mvdb_workspace* ws, uint64_t n, cudaStream_t stream) {
     RC_OK(ensure_shadow8(ix, n));
     if (!ws->i8_ctl) {
         CU_OK(cudaMalloc(&ws->i8_ctl, sizeof(I8Ctl)));
-        CU_OK(cudaMalloc(&ws->i8_cand, size_t(kI8CandCap) * 4));
         CU_OK(cudaMalloc(&ws->i8_surv, size_t(kI8SurvCap) * 8));
         CU_OK(cudaMalloc(&ws->i8_best, size_t(kI8BestM) * 32 * 4));
+        CU_OK(cudaHostAlloc(reinterpret_cast<void**>(&ws->i8_ovf_pin), sizeof(unsigned int), cudaHostAllocMapped));
+        *ws->i8_ovf_pin = 0u;
+        CU_OK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ws->i8_ovf_dev), ws->i8_ovf_pin, 0));
+        // zero once; from then on every search leaves the control block and the table clean for the next
+        CU_OK(cudaMemsetAsync(ws->i8_ctl, 0, sizeof(I8Ctl), stream));
+        CU_OK(cudaMemsetAsync(ws->i8_best, 0, size_t(kI8BestM) * 32 * 4, stream));
     }
-    RC_OK(grow_dev(&ws->i8_qn, &ws->i8_qn_cap, size_t(ix->ld)));
-    I8Params p = {};
-    p.x8 = static_cast<const uint8_t*>(ix->mat8.ptr());
-    p.x = static_cast<const float*>(ix->mat.ptr());
-    p.qn = ws->i8_qn;
-    p.live = ix->ndead.load(std::memory_order_acquire) ? static_cast<const uint32_t*>(ix->live.ptr()) : nullptr;
-    p.mask = mask_dev;
-    p.cand = ws->i8_cand;
-    p.surv = ws->i8_surv;
-    p.best = ws->i8_best;
-    p.ctl = ws->i8_ctl;
-    p.outD = D_dev;
-    p.outI = I_dev;
-    p.label_offset = label_offset;
-    p.n = n;
-    p.cand_cap = kI8CandCap;
-    p.rec_bytes = ix->rec8;
-    p.stage_bytes = uint32_t(align_up(size_t(kI8TileRows) * ix->rec8, 128));
-    p.stage_off = 1024;
-    p.d = ix->d;
-    p.ld4 = ix->ld4;
-    p.ld8 = ix->ld8;
-    p.k = int(k);
-    int stages = int(std::min<size_t>(16, (ix->smem_optin - 1024) / p.stage_bytes));
-    stages = stages / kI8ConsumerWarps * kI8ConsumerWarps;
-    p.stages = stages;
-    p.max_norm = std::sqrt(std::max(ix->max_norm2_host.load(std::memory_order_acquire), 0.f)) * 1.0001f;
-    const uint32_t tiles = (n + kI8TileRows - 1) / kI8TileRows;
-    const int grid = int(std::min<uint32_t>(uint32_t(ix->sm_count), tiles));
-    p.nbest = uint32_t(grid) * kI8ConsumerWarps;
-    if (p.nbest > uint32_t(kI8BestM) * 32) return fail(MVDB_ERR_STATE, "int8 scan: too many consumer warps for the threshold table");
-    const size_t smem = size_t(p.stage_off) + size_t(stages) * p.stage_bytes;
     static std::once_flag attr_once[16];
     cudaError_t ae = cudaSuccess;
     std::call_once(attr_once[ix->device & 15], [&] {
         ae = cudaFuncSetAttribute(scan_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ix->smem_optin));
     });
     CU_OK(ae);
-    i8_prep_kernel<<<1, 256, 0, stream>>>(q_dev, ws->i8_qn, ix->d, ix->ld4, normalize_q, ws->i8_ctl, ws->i8_best, p.nbest);
-    LAUNCHED();
-    scan_i8_kernel<<<grid, 32 * (1 + kI8ConsumerWarps), smem, stream>>>(p);
-    LAUNCHED();
-    i8_finish_kernel<<<64, 256, size_t(ix->ld4) * 16 + size_t(kI8SurvCap) * 8, stream>>>(p);
+    return MVDB_OK;
+}
+
+// ONE launch: int8 scan + in-warp exact re-scoring of the candidates + last-CTA sort.  If the survivor list
+// overflows (adversarial data: thousands of near-ties) the query is answered by the fp32 scan instead --
+// by the caller when it synchronises anyway (host-buffer API: *redo_host), else by a conditional launch
+// behind this one (*run_if = device flag; a no-op when the flag is clear).
+static int run_i8(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, int64_t k, const uint32_t* mask_dev, uint32_t n,
+                  int normalize_q, int64_t label_offset, float* D_dev, int64_t* I_dev, cudaStream_t stream,
+                  const unsigned int** run_if, mvdb_exchange* xch, uint64_t xch_seq) {
+    RC_OK(i8_prepare(ix, ws, n, stream));
+    I8Params p = {};
+    p.x8 = static_cast<const uint8_t*>(ix->mat8.ptr());
+    p.x = static_cast<const float*>(ix->mat.ptr());
+    p.q = q_dev;
+    p.normalize_q = normalize_q;
+    p.live = ix->ndead.load(std::memory_order_acquire) ? static_cast<const uint32_t*>(ix->live.ptr()) : nullptr;
+    p.mask = mask_dev;
+    p.surv = ws->i8_surv;
+    p.ovf_host = (tl_host_checks_i8 && !xch) ? ws->i8_ovf_dev : nullptr;
+    p.xchg = xch ? xch->dev : nullptr;
+    p.xchg_seq = xch_seq;
+    p.best = ws->i8_best;
+    p.ctl = ws->i8_ctl;
+    p.outD = D_dev;
+    p.outI = I_dev;
+    p.label_offset = label_offset;
+    p.n = n;
+    p.rec_bytes = ix->rec8;
+    p.stage_bytes = uint32_t(align_up(size_t(kI8TileRows) * ix->rec8, 128));
+    p.q_off = 1024;
+    p.stage_off = uint32_t(1024 + align_up(size_t(ix->ld) * 4, 128));
+    p.d = ix->d;
+    p.ld4 = ix->ld4;
+    p.ld8 = ix->ld8;
+    p.k = int(k);
+    const int ncw = i8_consumer_warps(ix);
+    int stages = int(std::min<size_t>(16, (ix->smem_optin - p.stage_off) / p.stage_bytes));
+    stages = stages / ncw * ncw;
+    p.stages = stages;
+    p.max_norm = std::sqrt(std::max(ix->max_norm2_host.load(std::memory_order_acquire), 0.f)) * 1.0001f;
+    const uint32_t tiles = (n + kI8TileRows - 1) / kI8TileRows;
+    const int grid = int(std::min<uint32_t>(uint32_t(ix->sm_count), tiles));
+    p.nbest = k <= 32 ? uint32_t(grid) : uint32_t(grid) * uint32_t(ncw);
+    if (p.nbest > uint32_t(kI8BestM) * 32) return fail(MVDB_ERR_STATE, "int8 scan: too many consumer warps for the threshold table");
+    // the idle ring doubles as the tail's scratch: 4096 survivor keys + the exchange merge's select buffer
+    const size_t smem = std::max(size_t(p.stage_off) + size_t(stages) * p.stage_bytes, size_t(p.stage_off) + size_t(kI8SurvCap) * 8 + 256 * 8);
+    scan_i8_kernel<<<grid, 32 * (1 + ncw), smem, stream>>>(p);
     LAUNCHED();
     CU_OK(cudaGetLastError());
-    *run_if = &ws->i8_ctl->overflow;
+    *run_if = (tl_host_checks_i8 && !xch) ? nullptr : &ws->i8_ctl->overflow;
     return MVDB_OK;
 }
 
@@ -1105,8 +1121,12 @@ static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, in
     // opt-in int8 shadow mode: the whole query is answered by the shadow pass + exact re-scoring; the fp32
     // scan below is still enqueued, as a conditional launch that only runs if a candidate list overflowed
     const unsigned int* run_if = nullptr;
-    if (!xch && !tl_force_scan && !any_qmask && i8_eligible(ix, nq, k, n))
-        RC_OK(run_i8(ix, ws, q_dev, k, mask_dev, n, normalize_q, label_offset, D_dev, I_dev, stream, &run_if));
+    uint64_t i8_seq = 0;   // sharded search: the int8 launch and its conditional fp32 fallback are ONE exchange round
+    if (!tl_force_scan && !any_qmask && i8_eligible(ix, nq, k, n)) {
+        if (xch) i8_seq = ++xch->seq;
+        RC_OK(run_i8(ix, ws, q_dev, k, mask_dev, n, normalize_q, label_offset, D_dev, I_dev, stream, &run_if, xch, i8_seq));
+        if (!run_if) return MVDB_OK;   // the caller synchronises, checks the overflow word and re-runs on the fp32 scan if needed
+    }
     ScanParams p = {};
     p.run_if = run_if;
     p.x = static_cast<const float*>(ix->mat.ptr());
@@ -1130,7 +1150,7 @@ static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, in
             if (xch) {
                 while (g > xch->nq_max) g >>= 1;
                 p.xchg = xch->dev;
-                p.xchg_seq = ++xch->seq;
+                p.xchg_seq = i8_seq ? i8_seq : ++xch->seq;
             }
             p.mask = mask_dev;
             p.n = n;
@@ -1281,11 +1301,10 @@ static void ws_free(mvdb_workspace* ws) {
     cudaFree(ws->b_lqmask);
     cudaFree(ws->b_lqptr);
     cudaFree(ws->b_lqwords);
-    cudaFree(ws->i8_cand);
     cudaFree(ws->i8_surv);
+    if (ws->i8_ovf_pin) cudaFreeHost(ws->i8_ovf_pin);
     cudaFree(ws->i8_best);
     cudaFree(ws->i8_ctl);
-    cudaFree(ws->i8_qn);
     cudaFree(ws->q_dev);
     cudaFree(ws->mask_dev);
     cudaFree(ws->I_dev);
@@ -1843,9 +1862,22 @@ static int search_host_direct(mvdb_index* ix, const float* q, int64_t nq, int64_
         memcpy(ws->q_pin, q, qn * 4);
         CU_OK(cudaMemcpyAsync(ws->q_dev, ws->q_pin, qn * 4, cudaMemcpyHostToDevice, st));
     }
-    RC_OK(run_search(ix, ws, q_dev, nq, k, mask_dev, mask_rows, normalize_queries, 0, D_dev, ws->I_dev, st, nullptr));
+    tl_host_checks_i8 = true;
+    int src = run_search(ix, ws, q_dev, nq, k, mask_dev, mask_rows, normalize_queries, 0, D_dev, ws->I_dev, st, nullptr);
+    tl_host_checks_i8 = false;
+    RC_OK(src);
     CU_OK(cudaMemcpyAsync(ws->I_pin, ws->I_dev, on * 12, cudaMemcpyDeviceToHost, st));
     CU_OK(cudaStreamSynchronize(st));
+    if (ws->i8_ovf_pin && *reinterpret_cast<volatile unsigned int*>(ws->i8_ovf_pin)) {
+        // int8 shadow mode: the survivor list overflowed -- this query is answered by the fp32 scan
+        *ws->i8_ovf_pin = 0u;
+        tl_force_scan = true;
+        src = run_search(ix, ws, q_dev, nq, k, mask_dev, mask_rows, normalize_queries, 0, D_dev, ws->I_dev, st, nullptr);
+        tl_force_scan = false;
+        RC_OK(src);
+        CU_OK(cudaMemcpyAsync(ws->I_pin, ws->I_dev, on * 12, cudaMemcpyDeviceToHost, st));
+        CU_OK(cudaStreamSynchronize(st));
+    }
     memcpy(D, D_pin, on * 4);
     memcpy(I, ws->I_pin, on * 8);
     return MVDB_OK;
@@ -2417,6 +2449,7 @@ static int prepare_fused_scan(mvdb_index* ix, mvdb_workspace* ws, int64_t nq, in
     // may synchronise the device
     cudaFuncAttributes fa;
     CU_OK(cudaFuncGetAttributes(&fa, xchg_empty_kernel));
+    if (i8_eligible(ix, nq, k, p.n)) RC_OK(i8_prepare(ix, ws, p.n, ws->stream));
     return MVDB_OK;
 }
 
@@ -2652,6 +2685,20 @@ int mvdb_debug_read_gemm_prof(mvdb_index* ix, uint64_t* out, int ctas) {
         return fail(MVDB_ERR_STATE, "GEMM profiling is off (set option \"gemm_prof\" = 1) or bad arguments");
     CU_OK(cudaDeviceSynchronize());
     CU_OK(cudaMemcpy(out, ix->gemm_prof_dev, size_t(ctas) * 8 * 8, cudaMemcpyDeviceToHost));
+    return MVDB_OK;
+}
+
+int mvdb_debug_read_shadow_counters(mvdb_workspace* ws, uint32_t* out4) {
+    if (!ws || !out4) return fail(MVDB_ERR_ARG, "null argument");
+    if (!ws->i8_ctl) return fail(MVDB_ERR_STATE, "this workspace has not run an int8 shadow search");
+    DeviceGuard guard(ws->ix->device);
+    CU_OK(cudaDeviceSynchronize());
+    I8Ctl c;
+    CU_OK(cudaMemcpy(&c, ws->i8_ctl, sizeof c, cudaMemcpyDeviceToHost));
+    out4[0] = c.last_cand;
+    out4[1] = c.last_surv;
+    out4[2] = c.overflow;
+    out4[3] = 0;
     return MVDB_OK;
 }
 

@@ -18,9 +18,10 @@
 // the fp32 scan's score of row r, U_r = approx + B_r + eps an upper bound.
 // Threshold: every consumer warp publishes the best L it has seen (one word per warp, monotone); the
 // k-th largest of those words is a lower bound of the final k-th best score (k distinct rows reach it),
-// so a row with U_r below it can never enter the top-k.  Rows that pass are appended to a candidate
-// list; i8_finish_kernel re-scores them in fp32, drops what falls below the FINAL threshold, sorts the
-// few survivors and writes (D, I).  HBM traffic: N (d + 16) bytes instead of N d 4.
+// so a row with U_r below it can never enter the top-k.  Rows that pass are rare (a few hundred per
+// search): the warp that found one re-scores it at once from the fp32 master row and appends the exact
+// key to the survivor list; the last CTA to finish sorts the survivors and writes (D, I) -- one launch.
+// HBM traffic: N (d + 16) bytes instead of N d 4.
 #pragma once
 #include "scan.cuh"
 
@@ -31,30 +32,35 @@ constexpr int kI8MetaBytes = 16;
 constexpr int kI8MaxJ = 4;           // 16-byte chunks per lane: d <= 2048
 constexpr uint32_t kI8SurvCap = 4096;
 
-struct I8Ctl {                // zeroed by i8_prep_kernel before every search
-    unsigned int cand_cnt;    // candidates appended by the scan
-    unsigned int surv_cnt;    // candidates that survived the exact re-scoring
-    unsigned int ticket;      // finish kernel: CTAs done
-    unsigned int overflow;    // 1: a list overflowed -> the caller re-runs the query on the fp32 scan
-    unsigned int pad[4];
+struct I8Ctl {                // zero before the first search; every search leaves it clean for the next one
+    unsigned int cand_cnt;    // rows the int8 pass could not rule out (statistics)
+    unsigned int surv_cnt;    // of those, rows whose exact score reached the threshold: the survivor list
+    unsigned int ticket;      // CTAs done
+    unsigned int overflow;    // 1: a list overflowed -> the conditional fp32 scan behind this search answers instead
+    unsigned int last_cand;   // counters of the search that just finished (test hook)
+    unsigned int last_surv;
+    unsigned int pad[2];
 };
 
 struct I8Params {
     const uint8_t* x8;        // shadow records
     const float* x;           // fp32 master matrix (re-scoring)
-    const float* qn;          // [ld] normalised fp32 query, zero padded (i8_prep_kernel)
+    const float* q;           // [d] the query as given
+    int normalize_q;
     const uint32_t* live;
     const uint32_t* mask;
-    uint32_t* cand;           // [cand_cap] rows
-    uint64_t* surv;           // [kI8SurvCap] exact keys
+    uint64_t* surv;           // [kI8SurvCap] exact keys of the re-scored candidates
+    unsigned int* ovf_host;   // pinned host word raised on overflow, or nullptr (then only ctl->overflow is)
     unsigned int* best;       // [nbest] ordered images of the per-warp best lower bounds
     I8Ctl* ctl;
     float* outD;
     int64_t* outI;
     int64_t label_offset;
-    uint32_t n, cand_cap, nbest, rec_bytes, stage_bytes, stage_off;
+    uint32_t n, nbest, rec_bytes, stage_bytes, stage_off, q_off;
     int d, ld4, ld8, k, stages;
     float max_norm;           // largest ||x_r|| stored in the index
+    const XchgDev* xchg;      // fused cross-GPU exchange (nullptr = single GPU): the last CTA sends this shard's k best
+    uint64_t xchg_seq;        // to every rank and merges, exactly as the fp32 scan's tail does
 };
 
 __device__ __forceinline__ int reduce8i(const int (&a)[8], int lane) {
@@ -82,13 +88,14 @@ __device__ __forceinline__ int reduce8i(const int (&a)[8], int lane) {
     return s;
 }
 
-// k-th largest of `nvals` 32-bit words spread over the warp (v[i] = word lane + 32 i; 0 = empty):
-// bitwise bisection, 32 rounds of (compare, warp-wide count).  Returns 0 when fewer than k are non-zero.
+// k-th largest of the 32-bit words spread over the warp (v[i] = word lane + 32 i; 0 = empty), truncated to
+// its top 24 bits (a slightly LOWER value: still a valid lower bound): bitwise bisection, 24 rounds of
+// (compare, warp-wide count).  Returns 0 when fewer than k words are non-zero.
 template <int M>
 __device__ __forceinline__ uint32_t warp_kth_largest_u32(const uint32_t (&v)[M], int k) {
     uint32_t t = 0;
 #pragma unroll 1
-    for (int bit = 31; bit >= 0; bit--) {
+    for (int bit = 31; bit >= 8; bit--) {
         const uint32_t cand = t | (1u << bit);
         int c = 0;
 #pragma unroll
@@ -101,14 +108,19 @@ __device__ __forceinline__ uint32_t warp_kth_largest_u32(const uint32_t (&v)[M],
 
 constexpr int kI8BestM = 40;   // up to 1280 consumer warps in a grid
 
-__device__ __forceinline__ uint32_t i8_threshold(const unsigned int* best, uint32_t nbest, int k, int lane) {
-    uint32_t v[kI8BestM];
+template <int M>
+__device__ __forceinline__ uint32_t i8_threshold_m(const unsigned int* best, uint32_t nbest, int k, int lane) {
+    uint32_t v[M];
 #pragma unroll
-    for (int i = 0; i < kI8BestM; i++) {
+    for (int i = 0; i < M; i++) {
         const uint32_t idx = uint32_t(lane) + 32u * uint32_t(i);
         v[i] = (idx < nbest) ? __ldcg(best + idx) : 0u;
     }
-    return warp_kth_largest_u32<kI8BestM>(v, k);
+    return warp_kth_largest_u32<M>(v, k);
+}
+__device__ __forceinline__ uint32_t i8_threshold(const unsigned int* best, uint32_t nbest, int k, int lane) {
+    if (nbest <= 160u) return i8_threshold_m<5>(best, nbest, k, lane);
+    return nbest <= 640u ? i8_threshold_m<20>(best, nbest, k, lane) : i8_threshold_m<kI8BestM>(best, nbest, k, lane);
 }
 
 // ---------------------------------------------------------------------------
@@ -161,52 +173,44 @@ __global__ void __launch_bounds__(256) to_i8_rows_kernel(const float* __restrict
     }
 }
 
-// ---------------------------------------------------------------------------
-// prologue launch: q -> normalised, zero-padded fp32 query (EXACTLY the arithmetic of the fp32 scan's
-// load_query_regs, so re-scored distances are bit-identical to it) and a clean control block
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) i8_prep_kernel(const float* __restrict__ q, float* __restrict__ qn, int d, int ld4,
-                                                      int normalize, I8Ctl* ctl, unsigned int* best, uint32_t nbest) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp == 0) {
-        float nr = 0.f;
-        for (int c = lane; c < ld4; c += kWarp) {   // same chunk order as load_query_regs (j ascending)
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int b = 4 * c;
-            if (b + 0 < d) v.x = q[b + 0];
-            if (b + 1 < d) v.y = q[b + 1];
-            if (b + 2 < d) v.z = q[b + 2];
-            if (b + 3 < d) v.w = q[b + 3];
-            nr = dot4(v, v, nr);
-            reinterpret_cast<float4*>(qn)[c] = v;
-        }
-        nr = warp_allsum(nr);
-        if (normalize && nr > 0.f) {
-            const float inv = renorm_scale(nr);
-            __syncwarp();
-            for (int c = lane; c < ld4; c += kWarp) {
-                float4 v = reinterpret_cast<float4*>(qn)[c];
-                v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
-                reinterpret_cast<float4*>(qn)[c] = v;
-            }
-        }
-        if (lane == 0) *ctl = I8Ctl{};
-    } else {
-        for (uint32_t i = threadIdx.x - 32; i < nbest; i += blockDim.x - 32) best[i] = 0u;
+// Scale that faiss.normalize_L2 would apply to the query, computed with EXACTLY the arithmetic of the fp32
+// scan's load_query_regs (per-lane float4 chunks lane + 32 j in ascending j, xor-butterfly warp sum), so that
+// the normalised query -- and with it every re-scored distance -- is bit-identical to the fp32 scan's.
+// Returns 1 when no scaling applies.  q: dense [d] floats (any alignment).
+__device__ __forceinline__ float4 i8_load_q4(const float* q, int d, int c) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int b = 4 * c;
+    if (b + 3 < d && (reinterpret_cast<uintptr_t>(q) & 15) == 0) return reinterpret_cast<const float4*>(q)[c];
+    if (b + 0 < d) v.x = q[b + 0];
+    if (b + 1 < d) v.y = q[b + 1];
+    if (b + 2 < d) v.z = q[b + 2];
+    if (b + 3 < d) v.w = q[b + 3];
+    return v;
+}
+__device__ __forceinline__ float i8_query_scale(const float* q, int d, int ld4, int normalize, int lane, bool* scaled) {
+    float nr = 0.f;
+    for (int c = lane; c < ld4; c += kWarp) {
+        const float4 v = i8_load_q4(q, d, c);
+        nr = dot4(v, v, nr);
     }
+    nr = warp_allsum(nr);
+    *scaled = normalize && nr > 0.f;
+    return *scaled ? renorm_scale(nr) : 1.0f;
 }
 
 // shared-memory header of the int8 scan
 struct I8Header {
     uint64_t full[16];
     uint64_t empty[16];
-    unsigned int thr;     // CTA-wide copy of the threshold (ordered image), only ever raised
+    unsigned int thr;       // CTA-wide copy of the threshold (ordered image), only ever raised
+    unsigned int refreshes; // how many times any warp of the CTA has recomputed it
+    int last_flag;
 };
 
 // ---------------------------------------------------------------------------
 // the scan: warp 0 = TMA producer (one bulk copy of 32 records per tile), warps 1.. = consumers
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(160, 1) scan_i8_kernel(const I8Params p) {
+__global__ void __launch_bounds__(288, 1) scan_i8_kernel(const I8Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
     I8Header* hdr = reinterpret_cast<I8Header*>(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -221,7 +225,9 @@ __global__ void __launch_bounds__(160, 1) scan_i8_kernel(const I8Params p) {
             mbar_init(&hdr->full[s], 1);
             mbar_init(&hdr->empty[s], 1);
         }
+        if (blockIdx.x == 0) p.ctl->overflow = 0u;   // the previous search's conditional fallback has completed (stream order)
         hdr->thr = 0u;
+        hdr->refreshes = 0u;
         mbar_fence_init();
     }
     __syncthreads();
@@ -246,6 +252,18 @@ __global__ void __launch_bounds__(160, 1) scan_i8_kernel(const I8Params p) {
         return;
     }
 
+    // ---- the normalised fp32 query goes to shared memory once (the exact re-scoring reads it) ----
+    float4* qs = reinterpret_cast<float4*>(smem + p.q_off);
+    {
+        bool scaled;
+        const float inv = i8_query_scale(p.q, p.d, p.ld4, p.normalize_q, lane, &scaled);   // same value in every warp
+        for (int c = cw * kWarp + lane; c < p.ld4; c += ncw * kWarp) {
+            float4 v = i8_load_q4(p.q, p.d, c);
+            if (scaled) { v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv; }
+            qs[c] = v;
+        }
+    }
+    named_bar_sync(1, ncw * 32);
     // ---- query: two int8 planes, their scales, ||q||, rq = ||q - q^||  (identical in every warp) ----
     const int J = (p.ld8 / 16 + 31) / 32;
     int4 q1[kI8MaxJ], q2[kI8MaxJ];
@@ -259,7 +277,7 @@ __global__ void __launch_bounds__(160, 1) scan_i8_kernel(const I8Params p) {
 #pragma unroll
             for (int t = 0; t < 4; t++) {
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (j < J && 4 * c + t < p.ld4) v = reinterpret_cast<const float4*>(p.qn)[4 * c + t];
+                if (j < J && 4 * c + t < p.ld4) v = qs[4 * c + t];
                 f[j][4 * t + 0] = v.x; f[j][4 * t + 1] = v.y; f[j][4 * t + 2] = v.z; f[j][4 * t + 3] = v.w;
                 mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
                 nr = dot4(v, v, nr);
@@ -307,24 +325,29 @@ __global__ void __launch_bounds__(160, 1) scan_i8_kernel(const I8Params p) {
     // B_r = qhat_norm * e_r + bconst;  eps covers the fp32 rounding of the scan's own score (gamma_d ||q|| ||x||),
     // of `approx` below and of this bound's own arithmetic
     const float qhat_norm = (qnorm + rq) * 1.0001f;
-    const float bconst = (rq * p.max_norm + (float(p.d) * 1.2e-7f + 4e-6f) * qnorm * p.max_norm) * 1.0001f;
+    const float bconst = (rq * p.max_norm + (float(p.d) * 1.2e-7f + 8e-6f) * qnorm * p.max_norm) * 1.0001f;
 
     const int my_row = tile_row_of_lane(lane);
     const bool leader = (lane & 3) == 0;
-    const uint32_t gw = blockIdx.x * uint32_t(ncw) + uint32_t(cw);   // this warp's slot in p.best
+    // Slot of p.best this warp reports to.  k <= 32: one slot per CTA (the warps of a CTA share it through
+    // atomicMax; 148 slots make the threshold cheap to recompute and the k-th largest of 148 CTA-bests is
+    // still about the k-th best row).  Larger k: one slot per warp (more distinct rows at the top).
+    const bool slot_per_cta = p.k <= 32;
+    const uint32_t gw = slot_per_cta ? blockIdx.x : blockIdx.x * uint32_t(ncw) + uint32_t(cw);
+    uint32_t n_cand = 0;
     uint32_t my_best = 0u, published = 0u, thr = 0u;
-    uint32_t done_tiles = 0, next_refresh = 1;
+    uint32_t done_tiles = 0, next_refresh = 1, seen_refreshes = 0;
     for (uint32_t it = cw; it < iters; it += ncw) {
         const uint32_t tile = blockIdx.x + it * G;
         const uint32_t row0 = tile * kI8TileRows;
         uint32_t adm = 0xFFFFFFFFu;
         if (p.mask) adm &= p.mask[tile];
         if (p.live) adm &= p.live[tile];
-        thr = max(thr, *reinterpret_cast<volatile unsigned int*>(&hdr->thr));
         const int s = it % S;
         mbar_wait(&hdr->full[s], (it / S) & 1u);
         const uint8_t* st = smem + p.stage_off + size_t(s) * p.stage_bytes;
-#pragma unroll 1
+        uint32_t upv[4];   // leaders: upper bound of "their" row of each 8-row group (0 = not admissible)
+#pragma unroll
         for (int g = 0; g < 4; g++) {
             int a1[8], a2[8];
 #pragma unroll
@@ -343,111 +366,140 @@ __global__ void __launch_bounds__(160, 1) scan_i8_kernel(const I8Params p) {
                     }
                 }
             }
-            const int d1 = reduce8i(a1, lane), d2 = reduce8i(a2, lane);
+            // the two planes are combined per lane in fp32 (each partial dot is far below 2^24, so the
+            // conversions are exact; the few roundings of the combination are inside eps) and reduced ONCE
+            float fa[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) fa[r] = fmaf(s1, float(a1[r]), s2 * float(a2[r]));
+            const float dq = reduce8(fa, lane);
             const int rt = g * 8 + my_row;   // row of the tile this quad is responsible for
-            const uint32_t row = row0 + uint32_t(rt);
-            bool pass = false;
-            if (leader && row < p.n && ((adm >> rt) & 1u)) {
+            uint32_t up = 0u;
+            if (leader && row0 + uint32_t(rt) < p.n && ((adm >> rt) & 1u)) {
                 const float2 m = *reinterpret_cast<const float2*>(st + size_t(rt) * p.rec_bytes + p.ld8);
-                const float approx = m.x * fmaf(s1, float(d1), s2 * float(d2));
+                const float approx = m.x * dq;
                 const float B = fmaf(qhat_norm, m.y, bconst);
                 if (approx == approx) {
                     my_best = max(my_best, score_to_ord(approx - B));
-                    pass = score_to_ord(approx + B) >= thr;
+                    up = max(score_to_ord(approx + B), 1u);
                 } else {
-                    pass = true;   // not a number: let the exact re-scoring decide (the fp32 scan drops NaN scores)
+                    up = 0xFFFFFFFFu;   // not a number: let the exact re-scoring decide (the fp32 scan drops NaN scores)
                 }
             }
-            const unsigned m = __ballot_sync(0xFFFFFFFFu, pass);
-            if (m) {
-                unsigned base = 0;
-                if (lane == 0) base = atomicAdd(&p.ctl->cand_cnt, unsigned(__popc(m)));
-                base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                const unsigned pos = base + unsigned(__popc(m & ((1u << lane) - 1u)));
-                if (pass && pos < p.cand_cap) p.cand[pos] = row;
-            }
+            upv[g] = up;
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&hdr->empty[s]);
+        if (lane == 0) mbar_arrive(&hdr->empty[s]);   // the stage is free: everything below works from registers
         // publish this warp's best lower bound (monotone; one word per warp, so a reader never sees a torn value)
         const uint32_t wb = __reduce_max_sync(0xFFFFFFFFu, my_best);
         if (wb > published) {
             published = wb;
-            if (lane == 0) *reinterpret_cast<volatile unsigned int*>(p.best + gw) = wb;
+            if (lane == 0) {
+                if (slot_per_cta) atomicMax(p.best + gw, wb);
+                else *reinterpret_cast<volatile unsigned int*>(p.best + gw) = wb;
+            }
         }
         my_best = wb;
-        // refresh the threshold after 1, 2, 4, ... tiles of this warp, then every 32: k-th largest of all warps' bests
-        if (++done_tiles == next_refresh) {
+        // Threshold = k-th largest of all warps' bests.  Recomputed after 1, 2, 4, ... tiles of this warp, then
+        // every 32 -- unless another warp of the CTA has done it since this warp last looked (the result is
+        // shared through hdr->thr).  After the FIRST tile the other warps are only just publishing: give them a
+        // moment, else every warp's first 32 rows would all become candidates.
+        ++done_tiles;
+        const unsigned int cta_refreshes = *reinterpret_cast<volatile unsigned int*>(&hdr->refreshes);
+        if (done_tiles >= next_refresh) {
             next_refresh = done_tiles < 32 ? done_tiles * 2 : done_tiles + 32;
-            const uint32_t t = i8_threshold(p.best, p.nbest, p.k, lane);
-            if (t > thr) {
-                thr = t;
-                if (lane == 0) atomicMax(&hdr->thr, t);
+            if (done_tiles == 1 || cta_refreshes == seen_refreshes) {
+                uint32_t t = i8_threshold(p.best, p.nbest, p.k, lane);
+                if (done_tiles == 1)
+                    for (int spin = 0; t == 0u && spin < 6; spin++) {
+                        __nanosleep(500);
+                        t = i8_threshold(p.best, p.nbest, p.k, lane);
+                    }
+                if (lane == 0) {
+                    atomicMax(&hdr->thr, t);
+                    atomicAdd(&hdr->refreshes, 1u);
+                }
+                thr = max(thr, t);
+            }
+            seen_refreshes = *reinterpret_cast<volatile unsigned int*>(&hdr->refreshes);
+        }
+        thr = max(thr, *reinterpret_cast<volatile unsigned int*>(&hdr->thr));
+        // Rows the int8 pass cannot rule out (a few hundred per search): re-score them right here from the fp32
+        // master row -- per-lane chunk order + xor butterfly == the fp32 scan's reduce8 tree, so the score is
+        // bit-identical to the scan's -- and keep the exact key if it reaches the threshold.
+#pragma unroll 1
+        for (int g = 0; g < 4; g++) {
+            unsigned m = __ballot_sync(0xFFFFFFFFu, upv[g] != 0u && upv[g] >= thr);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const uint32_t row = row0 + uint32_t(g * 8 + tile_row_of_lane(src));
+                const float4* xr = reinterpret_cast<const float4*>(p.x) + size_t(row) * p.ld4;
+                float acc = 0.f;
+                for (int c = lane; c < p.ld4; c += kWarp) acc = dot4(ldg_stream(xr + c), qs[c], acc);
+                acc = warp_allsum(acc);
+                n_cand++;
+                if (lane == 0 && acc == acc && score_to_ord(acc) >= thr) {
+                    const unsigned pos = atomicAdd(&p.ctl->surv_cnt, 1u);
+                    if (pos < kI8SurvCap) p.surv[pos] = make_key(acc, row);
+                }
             }
         }
     }
-}
-
-// ---------------------------------------------------------------------------
-// finish: exact fp32 re-scoring of the candidates with the scan's summation order (per-lane chunk order
-// + xor butterfly == reduce8's tree, as rescore_kernel), keep what reaches the FINAL threshold, and the
-// last CTA to finish sorts the survivors and writes (D, I).
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) i8_finish_kernel(const I8Params p) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    float4* qs = reinterpret_cast<float4*>(smem);                       // [ld4]
-    uint64_t* sk = reinterpret_cast<uint64_t*>(smem + size_t(p.ld4) * 16);   // [kI8SurvCap] (last CTA only)
-    __shared__ uint32_t thr_s;
-    __shared__ int last_s;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    const unsigned int raw_cnt = p.ctl->cand_cnt;
-    const unsigned int cnt = min(raw_cnt, p.cand_cap);
-    for (int c = threadIdx.x; c < p.ld4; c += blockDim.x) qs[c] = reinterpret_cast<const float4*>(p.qn)[c];
-    if (warp == 0) {
-        const uint32_t t = i8_threshold(p.best, p.nbest, p.k, lane);
-        if (lane == 0) thr_s = t;
+    // ---- tail: the last CTA to finish sorts the survivors and writes (D, I) ----
+    if (lane == 0 && n_cand) atomicAdd(&p.ctl->cand_cnt, n_cand);
+    __threadfence();
+    named_bar_sync(1, ncw * 32);
+    if (cw == 0 && lane == 0) hdr->last_flag = (atomicAdd(&p.ctl->ticket, 1u) == G - 1);
+    named_bar_sync(1, ncw * 32);
+    if (!hdr->last_flag) return;
+    __threadfence();
+    const int tid = cw * kWarp + lane, nthr = ncw * kWarp;
+    const unsigned int ns = *reinterpret_cast<volatile unsigned int*>(&p.ctl->surv_cnt);
+    const unsigned int nc = *reinterpret_cast<volatile unsigned int*>(&p.ctl->cand_cnt);
+    // leave the shared state clean for the next search on this workspace (every other CTA is done with it)
+    for (uint32_t i = tid; i < p.nbest; i += nthr) p.best[i] = 0u;
+    if (tid == 0) {
+        p.ctl->last_cand = nc;
+        p.ctl->last_surv = ns;
+        p.ctl->cand_cnt = 0u;
+        p.ctl->surv_cnt = 0u;
+        p.ctl->ticket = 0u;
     }
-    __syncthreads();
-    const uint32_t thr = thr_s;
-    const unsigned int gwarp = blockIdx.x * nw + warp, nwarps = gridDim.x * nw;
-    for (unsigned int i = gwarp; i < cnt; i += nwarps) {
-        const uint32_t row = p.cand[i];
-        const float4* xr = reinterpret_cast<const float4*>(p.x) + size_t(row) * p.ld4;
-        float acc = 0.f;
-        for (int c = lane; c < p.ld4; c += kWarp) acc = dot4(ldg_stream(xr + c), qs[c], acc);
-        acc = warp_allsum(acc);
-        if (lane == 0 && acc == acc && score_to_ord(acc) >= thr) {
-            const unsigned pos = atomicAdd(&p.ctl->surv_cnt, 1u);
-            if (pos < kI8SurvCap) p.surv[pos] = make_key(acc, row);
+    if (ns > kI8SurvCap) {
+        if (tid == 0) {   // the fp32 scan answers this query instead (conditional launch behind us, or the host re-runs it)
+            p.ctl->overflow = 1u;
+            if (p.ovf_host) {
+                *reinterpret_cast<volatile unsigned int*>(p.ovf_host) = 1u;
+                __threadfence_system();
+            }
         }
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) last_s = (atomicAdd(&p.ctl->ticket, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!last_s) return;
-    __threadfence();
-    const unsigned int ns_raw = *reinterpret_cast<volatile unsigned int*>(&p.ctl->surv_cnt);
-    if (raw_cnt > p.cand_cap || ns_raw > kI8SurvCap) {
-        if (threadIdx.x == 0) p.ctl->overflow = 1u;   // the caller's conditional fp32 scan answers this query instead
         return;
     }
-    const unsigned int ns = ns_raw;
+    uint64_t* sk = reinterpret_cast<uint64_t*>(smem + p.stage_off);   // the ring is idle now
     uint32_t npad = 64;
     while (npad < ns) npad <<= 1;
-    for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x) sk[i] = i < ns ? __ldcg(p.surv + i) : kEmptyKey;
-    __syncthreads();
+    for (uint32_t i = tid; i < npad; i += nthr) sk[i] = i < ns ? __ldcg(p.surv + i) : kEmptyKey;
+    named_bar_sync(1, nthr);
     if (npad <= 256) {
-        if (warp == 0) {
+        if (cw == 0) {
             if (npad == 64) warp_sort_buffer<2>(sk, int(ns), lane);
             else if (npad == 128) warp_sort_buffer<4>(sk, int(ns), lane);
             else warp_sort_buffer<8>(sk, int(ns), lane);
         }
     } else {
-        bitonic_sort_desc(sk, int(npad), int(threadIdx.x), int(blockDim.x), BlockSyncer());
+        bitonic_sort_desc(sk, int(npad), tid, nthr, [&] { named_bar_sync(1, nthr); });
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < p.k; i += blockDim.x) {
+    named_bar_sync(1, nthr);
+    if (p.xchg) {
+        // sharded search: same protocol as the fp32 scan's tail (scan.cuh finish_scan) -- send, publish, wait, merge
+        if (cw == 0) {
+            xchg_send(p.xchg, p.xchg_seq, 0, sk, int(min(ns, unsigned(p.k))), p.k, lane);
+            xchg_publish_and_wait(p.xchg, p.xchg_seq, lane);
+            xchg_merge(p.xchg, p.xchg_seq, 0, sk + 4096, select_cap(p.k), p.k, p.outD, p.outI, lane);
+        }
+        return;
+    }
+    for (int i = tid; i < p.k; i += nthr) {
         const uint64_t key = (unsigned(i) < ns) ? sk[i] : kEmptyKey;
         if (key == kEmptyKey) {
             p.outD[i] = -FLT_MAX;

@@ -366,6 +366,12 @@ class Workspace:
         self._engine = engine  # keep the index alive
         N.check(N.lib().mvdb_index_workspace_create(engine.handle, ctypes.byref(self._h)))
 
+    def shadow_counters(self):
+        """(candidates, survivors, overflowed) of the last int8 shadow search run on this workspace."""
+        out = (ctypes.c_uint32 * 4)()
+        N.check(N.lib().mvdb_debug_read_shadow_counters(self._h, out))
+        return int(out[0]), int(out[1]), bool(out[2])
+
     def close(self):
         if self._h is not None and self._h.value:
             N.lib().mvdb_index_workspace_destroy(self._h)

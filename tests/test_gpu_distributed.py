@@ -78,6 +78,31 @@ def _run_transport(rank, world, transport):
     idx.close()
 
 
+def _run_shadow_mode(rank, world):
+    """int8 shadow mode under the fused exchange: every rank's int8 tail sends / merges; answers are
+    bit-identical to the fp32 sharded search."""
+    from minivectordb_b200.distributed import RowShardedIndex
+    from oracle import oracle as O
+    d, per = 256, 30_000
+    n = per * world
+    idx = RowShardedIndex(d, device=rank, exchange="fused" if world > 1 else "auto")
+    idx.add(synthetic=(77, rank * per, per, 0), normalize=True)
+    q = O.synth_rows(78, 0, 5, d)
+    O.normalize_L2(q)
+    ref = [idx.search(q[i:i + 1], 10) for i in range(5)]
+    idx.engine.set_option("scan_shadow", 1)
+    for rep in range(3):
+        for i in range(5):
+            D, I = idx.search(q[i:i + 1], 10)
+            assert np.array_equal(I, ref[i][1]) and np.array_equal(D, ref[i][0]), (rep, i)
+    x = O.synth_rows(77, 0, n, d)
+    O.normalize_L2(x)
+    Dr, Ir = O.search_flat_ip(x, q, 10)
+    D = np.concatenate([r[0] for r in ref]); I = np.concatenate([r[1] for r in ref])
+    assert O.classify_parity(x, q, I, D, Ir, Dr)["ok"]
+    idx.close()
+
+
 def _run_stable_numbering(rank, world):
     from minivectordb_b200.distributed import RowShardedIndex
     from oracle import oracle as O
@@ -138,6 +163,7 @@ def _worker(rank, world, port, ret):
         for transport in (("fused", "nccl") if world > 1 else ("auto",)):
             _run_transport(rank, world, transport)
         _run_stable_numbering(rank, world)
+        _run_shadow_mode(rank, world)
         if world > 1:
             _run_dead_peer(rank, world)
         ret[rank] = "ok"

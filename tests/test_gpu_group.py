@@ -132,3 +132,32 @@ def test_group_search_from_many_threads():
     for e in engines:
         e.close()
     assert not errs, errs[:1]
+
+
+def test_group_with_the_int8_shadow_mode_is_bit_identical():
+    """Shards in "scan_shadow" mode: the int8 pass + exact re-scoring runs on every device and ITS tail does the
+    NVLink exchange -- the merged answer is bit-identical to the fp32 group search."""
+    from oracle import oracle as O
+    n, d = 120_000, 384
+    x, bounds, engines, grp = _setup(3, n, d, seed=51)
+    try:
+        q = O.synth_rows(52, 0, 6, d)
+        O.normalize_L2(q)
+        adm = np.random.default_rng(4).random(n) < 0.4
+        masks = [adm[bounds[s][0]:bounds[s][1]] for s in range(3)]
+        for k in (1, 10, 100):
+            ref = [grp.search(q[i:i + 1], k) for i in range(6)]
+            refm = [grp.search(q[i:i + 1], k, masks=masks) for i in range(6)]
+            for e in engines:
+                e.set_option("scan_shadow", 1)
+            for rep in range(2):
+                got = [grp.search(q[i:i + 1], k) for i in range(6)]
+                gotm = [grp.search(q[i:i + 1], k, masks=masks) for i in range(6)]
+                for a, b in zip(ref + refm, got + gotm):
+                    assert all(np.array_equal(u, v) for u, v in zip(a, b)), k
+            for e in engines:
+                e.set_option("scan_shadow", 0)
+    finally:
+        grp.close()
+        for e in engines:
+            e.close()
