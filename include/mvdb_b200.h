@@ -69,6 +69,10 @@ int mvdb_device_count(int* count);
  * chunks as rows arrive, so row addresses never move while the index grows
  * (0 = default reservation). */
 int mvdb_index_create(int d, int device, uint64_t capacity_hint, mvdb_index** out);
+/* Mask handles, columns and workspaces made from the index may outlive it: destroying the index releases
+ * their device memory and leaves them inert (every use fails with MVDB_ERR_STATE / MVDB_ERR_ARG, their own
+ * *_destroy stays legal) -- a garbage-collected binding need not order its finalisers.  An index that belongs
+ * to a shard group is refused (MVDB_ERR_STATE): destroy the group first. */
 int mvdb_index_destroy(mvdb_index* ix);
 /* Drop every row (fresh IndexFlatIP, as _build_index does at vector_database.py:43). */
 int mvdb_index_reset(mvdb_index* ix);

@@ -96,8 +96,9 @@ class GpuStore:
     COMPACT_MIN_DEAD = 4096      # do not bother compacting below this many tombstones
     COMPACT_DEAD_FRACTION = 0.25
 
-    def __init__(self, devices=None):
+    def __init__(self, devices=None, scan_shadow=False):
         self.embedding_size = None
+        self._scan_shadow = bool(scan_shadow)   # opt-in int8 shadow scan for single queries (same answers, ~1/4 of the bytes)
         self.lock = threading.Lock()
         self.inverted_index = defaultdict(set)   # metadata key -> set of unique ids (VDB:16, 78-79)
         self._devices = list(devices) if devices else [0]
@@ -303,6 +304,12 @@ class GpuStore:
         self._views = None
         self._version += 1
 
+    def _new_engine(self, device):
+        eng = FlatIPEngine(self.embedding_size, device=device)
+        if self._scan_shadow and hasattr(eng, "set_option"):
+            eng.set_option("scan_shadow", 1)
+        return eng
+
     # ------------------------------------------------------------------ flush
     def _flush(self) -> None:
         """Move staged rows / tombstones to the GPU.  Caller holds the lock."""
@@ -312,14 +319,14 @@ class GpuStore:
             # their top-k over NVLink inside the kernel (no thread pool, no Python merge)
             for part in self._parts:
                 if part.engine is None:
-                    part.engine = FlatIPEngine(self.embedding_size, device=part.device)
+                    part.engine = self._new_engine(part.device)
             group_cls = getattr(type(self._parts[0].engine), "group_class", None)
             if group_cls is not None:
                 self._group = group_cls([p.engine for p in self._parts])
         for part in self._parts:
             if part.pending:
                 if part.engine is None:
-                    part.engine = FlatIPEngine(self.embedding_size, device=part.device)
+                    part.engine = self._new_engine(part.device)
                 # a bulk store arrives as one block and is shipped as it is; np.vstack over a million
                 # row views cost seconds here
                 blocks = part.pending_blocks

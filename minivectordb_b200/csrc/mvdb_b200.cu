@@ -25,6 +25,7 @@
 #include <mutex>
 #include <shared_mutex>
 #include <string>
+#include <unordered_set>
 #include <vector>
 
 #include "../../include/mvdb_b200.h"
@@ -436,6 +437,14 @@ struct mvdb_index {
     std::deque<struct CoalesceReq*> co_queue;
     int co_leaders = 0;
     int co_max_leaders = 0;        // option "coalesce_leaders": 0 = auto (1 for large matrices, else 2)
+    // objects that point back at this index (mask handles, columns, caller-owned workspaces): destroying the
+    // index releases their device memory and orphans them, so that a later *_destroy of theirs (e.g. from a
+    // garbage collector that runs after the index is gone) is harmless
+    std::mutex child_mu;
+    std::unordered_set<mvdb_mask*> child_masks;
+    std::unordered_set<mvdb_column*> child_columns;
+    std::unordered_set<mvdb_workspace*> child_workspaces;
+    struct mvdb_group* group = nullptr;   // the shard group this index belongs to (it must be destroyed first)
     // workspace pool for host-buffer searches
     std::mutex pool_mu;
     std::condition_variable pool_cv;
@@ -474,7 +483,8 @@ struct DeviceGuard {
 #define ENTER(ix)                                                                    \
     if (!(ix)) return fail(MVDB_ERR_ARG, "null index");                              \
     DeviceGuard guard__((ix)->device);                                               \
-    if (!guard__.ok) return fail(MVDB_ERR_CUDA, "cudaSetDevice(%d) failed", (ix)->device)
+    if (!guard__.ok) return fail(MVDB_ERR_CUDA, "cudaSetDevice(%d) failed", (ix)->device); \
+    (void)cudaGetLastError() /* start from a clean per-thread error state: cudaGetLastError() below must report OUR launches */
 
 // ---------------------------------------------------------------------------
 // scan dispatch
@@ -1038,6 +1048,12 @@ static int run_i8(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, int64_
     p.max_norm = std::sqrt(std::max(ix->max_norm2_host.load(std::memory_order_acquire), 0.f)) * 1.0001f;
     const uint32_t tiles = (n + kI8TileRows - 1) / kI8TileRows;
     const int grid = int(std::min<uint32_t>(uint32_t(ix->sm_count), tiles));
+    {
+        // the first (100 - dyn_tiles) % of every CTA's share is a static round-robin, the rest is claimed from a counter
+        const uint32_t per_cta = tiles / uint32_t(grid);
+        p.static_iters = ix->dyn_tiles > 0 ? uint32_t(uint64_t(per_cta) * uint32_t(100 - ix->dyn_tiles) / 100u) : 0xFFFFFFFFu;
+        p.dyn_tile0 = ix->dyn_tiles > 0 ? p.static_iters * uint32_t(grid) : 0xFFFFFFFFu;
+    }
     p.nbest = k <= 32 ? uint32_t(grid) : uint32_t(grid) * uint32_t(ncw);
     if (p.nbest > uint32_t(kI8BestM) * 32) return fail(MVDB_ERR_STATE, "int8 scan: too many consumer warps for the threshold table");
     // the idle ring doubles as the tail's scratch: 4096 survivor keys + the exchange merge's select buffer
@@ -1281,8 +1297,7 @@ static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, in
 // ---------------------------------------------------------------------------
 // workspace handling
 // ---------------------------------------------------------------------------
-static void ws_free(mvdb_workspace* ws) {
-    if (!ws) return;
+static void ws_release(mvdb_workspace* ws) {   // device / pinned memory and the stream; the struct stays
     cudaFree(ws->partials);
     cudaFree(ws->ticket);
     cudaFree(ws->all_ord);
@@ -1312,6 +1327,11 @@ static void ws_free(mvdb_workspace* ws) {
     cudaFreeHost(ws->mask_pin);
     cudaFreeHost(ws->I_pin);
     if (ws->stream) cudaStreamDestroy(ws->stream);
+    *ws = mvdb_workspace();
+}
+static void ws_free(mvdb_workspace* ws) {
+    if (!ws) return;
+    ws_release(ws);
     delete ws;
 }
 
@@ -1433,8 +1453,31 @@ int mvdb_index_create(int d, int device, uint64_t capacity_hint, mvdb_index** ou
 
 int mvdb_index_destroy(mvdb_index* ix) {
     if (!ix) return MVDB_OK;
+    if (ix->group) return fail(MVDB_ERR_STATE, "this index belongs to a shard group: destroy the group first");
     DeviceGuard guard(ix->device);
     cudaDeviceSynchronize();
+    {
+        // orphan everything that points back at us: their memory goes now, their structs when their owner destroys them
+        std::lock_guard<std::mutex> g(ix->child_mu);
+        for (mvdb_mask* m : ix->child_masks) {
+            cudaFree(m->dev);
+            if (m->ready) cudaEventDestroy(m->ready);
+            m->dev = nullptr;
+            m->ready = nullptr;
+            m->ix = nullptr;
+        }
+        for (mvdb_column* c : ix->child_columns) {
+            cudaFree(c->vals);
+            cudaFree(c->has);
+            c->vals = nullptr;
+            c->has = nullptr;
+            c->ix = nullptr;
+        }
+        for (mvdb_workspace* ws : ix->child_workspaces) ws_release(ws);   // resets the struct: ws->ix becomes null
+        ix->child_masks.clear();
+        ix->child_columns.clear();
+        ix->child_workspaces.clear();
+    }
     for (auto* ws : ix->pool_free) ws_free(ws);
     ix->pool_free.clear();
     ix->mat.destroy();
@@ -1773,11 +1816,22 @@ int mvdb_index_device_view(mvdb_index* ix, const float** matrix_dev, int64_t* ld
 int mvdb_index_workspace_create(mvdb_index* ix, mvdb_workspace** out) {
     ENTER(ix);
     if (!out) return fail(MVDB_ERR_ARG, "null out");
-    return ws_new(ix, out);
+    RC_OK(ws_new(ix, out));
+    std::lock_guard<std::mutex> g(ix->child_mu);
+    ix->child_workspaces.insert(*out);
+    return MVDB_OK;
 }
 int mvdb_index_workspace_destroy(mvdb_workspace* ws) {
     if (!ws) return MVDB_OK;
+    if (!ws->ix) {   // orphan: the index went first and took the resources with it
+        delete ws;
+        return MVDB_OK;
+    }
     DeviceGuard guard(ws->ix->device);
+    {
+        std::lock_guard<std::mutex> g(ws->ix->child_mu);
+        ws->ix->child_workspaces.erase(ws);
+    }
     if (ws->stream) cudaStreamSynchronize(ws->stream);
     ws_free(ws);
     return MVDB_OK;
@@ -2051,12 +2105,24 @@ int mvdb_index_mask_create(mvdb_index* ix, const uint8_t* mask, uint64_t mask_ro
         delete m;
         return fail(e == cudaErrorMemoryAllocation ? MVDB_ERR_OOM : MVDB_ERR_CUDA, "mask upload failed: %s", cudaGetErrorString(e));
     }
+    {
+        std::lock_guard<std::mutex> g(ix->child_mu);
+        ix->child_masks.insert(m);
+    }
     *out = m;
     return MVDB_OK;
 }
 
 int mvdb_mask_destroy(mvdb_mask* m) {
     if (!m) return MVDB_OK;
+    if (!m->ix) {   // orphan: the index was destroyed first and released the device memory
+        delete m;
+        return MVDB_OK;
+    }
+    {
+        std::lock_guard<std::mutex> g(m->ix->child_mu);
+        m->ix->child_masks.erase(m);
+    }
     DeviceGuard guard(m->ix->device);
     cudaFree(m->dev);   // synchronises the device: no filter kernel or search still reads it
     if (m->ready) cudaEventDestroy(m->ready);
@@ -2072,11 +2138,21 @@ int mvdb_column_create(mvdb_index* ix, mvdb_column** out) {
     if (!ix || !out) return fail(MVDB_ERR_ARG, "null argument");
     *out = new mvdb_column();
     (*out)->ix = ix;
+    std::lock_guard<std::mutex> g(ix->child_mu);
+    ix->child_columns.insert(*out);
     return MVDB_OK;
 }
 
 int mvdb_column_destroy(mvdb_column* c) {
     if (!c) return MVDB_OK;
+    if (!c->ix) {   // orphan
+        delete c;
+        return MVDB_OK;
+    }
+    {
+        std::lock_guard<std::mutex> g(c->ix->child_mu);
+        c->ix->child_columns.erase(c);
+    }
     DeviceGuard guard(c->ix->device);
     cudaFree(c->vals);
     cudaFree(c->has);
@@ -2086,6 +2162,7 @@ int mvdb_column_destroy(mvdb_column* c) {
 
 int mvdb_column_append(mvdb_column* c, const double* values, const uint8_t* present, uint64_t n) {
     if (!c) return fail(MVDB_ERR_ARG, "null column");
+    if (!c->ix) return fail(MVDB_ERR_STATE, "the column's index has been destroyed");
     if (n == 0) return MVDB_OK;
     if (!values || !present) return fail(MVDB_ERR_ARG, "null data");
     ENTER(c->ix);
@@ -2141,6 +2218,10 @@ static int new_mask(mvdb_index* ix, uint64_t rows, mvdb_mask** out) {
         delete m;
         return fail(MVDB_ERR_OOM, "mask allocation failed: %s", cudaGetErrorString(e));
     }
+    {
+        std::lock_guard<std::mutex> g(ix->child_mu);
+        ix->child_masks.insert(m);
+    }
     *out = m;
     return MVDB_OK;
 }
@@ -2185,7 +2266,7 @@ int mvdb_mask_create_filled(mvdb_index* ix, uint64_t rows, mvdb_mask** out) {
 }
 
 int mvdb_mask_combine(mvdb_mask* dst, const mvdb_mask* src, int how) {
-    if (!dst || !src || dst->ix != src->ix) return fail(MVDB_ERR_ARG, "bad masks");
+    if (!dst || !src || dst->ix != src->ix || !dst->ix) return fail(MVDB_ERR_ARG, "bad masks");
     if (how < 0 || how > 2) return fail(MVDB_ERR_ARG, "bad combine mode");
     ENTER(dst->ix);
     if (dst->words) {
@@ -2200,6 +2281,7 @@ int mvdb_mask_combine(mvdb_mask* dst, const mvdb_mask* src, int how) {
 
 int mvdb_mask_count(const mvdb_mask* m, uint64_t* count) {
     if (!m || !count) return fail(MVDB_ERR_ARG, "null argument");
+    if (!m->ix) return fail(MVDB_ERR_STATE, "the mask's index has been destroyed");
     mvdb_index* ix = m->ix;
     ENTER(ix);
     // one 8-byte counter per index, serialised by a mutex (a cudaMalloc per count would dominate)
@@ -2227,7 +2309,7 @@ int mvdb_mask_count(const mvdb_mask* m, uint64_t* count) {
 
 int mvdb_index_search_with_mask(mvdb_index* ix, const float* q, int64_t nq, int64_t k, const mvdb_mask* m,
                                 int normalize_queries, float* D, int64_t* I) {
-    if (m && m->ix != ix) return fail(MVDB_ERR_ARG, "mask handle belongs to another index");
+    if (m && m->ix != ix) return fail(MVDB_ERR_ARG, "mask handle belongs to another index (or its index has been destroyed)");
     return search_entry(ix, q, nq, k, nullptr, 0, m, normalize_queries, D, I);
 }
 
@@ -2479,6 +2561,7 @@ int mvdb_group_create(mvdb_index* const* shards, int n, mvdb_group** out) {
     if (!shards || n < 1 || n > kMaxWorld) return fail(MVDB_ERR_ARG, "need 1..%d shards", kMaxWorld);
     for (int i = 0; i < n; i++) {
         if (!shards[i]) return fail(MVDB_ERR_ARG, "null shard");
+        if (shards[i]->group) return fail(MVDB_ERR_STATE, "shard %d already belongs to a group", i);
         if (shards[i]->d != shards[0]->d) return fail(MVDB_ERR_ARG, "shards differ in dimension");
         for (int j = 0; j < i; j++)
             if (shards[j] == shards[i]) return fail(MVDB_ERR_ARG, "shard %d listed twice", i);
@@ -2507,6 +2590,7 @@ int mvdb_group_create(mvdb_index* const* shards, int n, mvdb_group** out) {
         g_err = keep;
         return rc;
     }
+    for (int i = 0; i < n; i++) shards[i]->group = g;   // a member cannot be destroyed before its group
     *out = g;
     return MVDB_OK;
 }
@@ -2520,6 +2604,7 @@ int mvdb_group_destroy(mvdb_group* g) {
     }
     for (int i = 0; i < g->n; i++) {
         DeviceGuard guard(g->shards[size_t(i)]->device);
+        if (g->shards[size_t(i)]->group == g) g->shards[size_t(i)]->group = nullptr;
         if (g->xch[size_t(i)]) mvdb_exchange_destroy(g->xch[size_t(i)]);
         if (g->ws[size_t(i)]) ws_free(g->ws[size_t(i)]);
         cudaFree(g->D_dev[size_t(i)]);

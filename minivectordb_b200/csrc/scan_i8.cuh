@@ -30,16 +30,18 @@ namespace mvdb {
 constexpr int kI8TileRows = 32;      // one word of the bitmasks
 constexpr int kI8MetaBytes = 16;
 constexpr int kI8MaxJ = 4;           // 16-byte chunks per lane: d <= 2048
+constexpr uint32_t kI8DynChunk = 4;  // tiles per claim of the counter-claimed tail
 constexpr uint32_t kI8SurvCap = 4096;
 
 struct I8Ctl {                // zero before the first search; every search leaves it clean for the next one
     unsigned int cand_cnt;    // rows the int8 pass could not rule out (statistics)
     unsigned int surv_cnt;    // of those, rows whose exact score reached the threshold: the survivor list
     unsigned int ticket;      // CTAs done
+    unsigned int tile_ctr;    // counter-claimed tail of the tile schedule
     unsigned int overflow;    // 1: a list overflowed -> the conditional fp32 scan behind this search answers instead
     unsigned int last_cand;   // counters of the search that just finished (test hook)
     unsigned int last_surv;
-    unsigned int pad[2];
+    unsigned int pad[1];
 };
 
 struct I8Params {
@@ -57,6 +59,8 @@ struct I8Params {
     int64_t* outI;
     int64_t label_offset;
     uint32_t n, nbest, rec_bytes, stage_bytes, stage_off, q_off;
+    uint32_t static_iters;    // iterations of every CTA served by the static round-robin (tile = cta + it * grid) ...
+    uint32_t dyn_tile0;       // ... the tiles from here on are claimed from ctl->tile_ctr, one at a time (= one mask word)
     int d, ld4, ld8, k, stages;
     float max_norm;           // largest ||x_r|| stored in the index
     const XchgDev* xchg;      // fused cross-GPU exchange (nullptr = single GPU): the last CTA sends this shard's k best
@@ -205,6 +209,8 @@ struct I8Header {
     unsigned int thr;       // CTA-wide copy of the threshold (ordered image), only ever raised
     unsigned int refreshes; // how many times any warp of the CTA has recomputed it
     int last_flag;
+    uint32_t tile_of[16];   // counter-claimed tiles: tile held by ring stage s (kNoTile = stop) ...
+    uint32_t adm_of[16];    // ... and its admissible word (mask & live)
 };
 
 // ---------------------------------------------------------------------------
@@ -233,16 +239,68 @@ __global__ void __launch_bounds__(288, 1) scan_i8_kernel(const I8Params p) {
     __syncthreads();
     if (warp == 0) {
         if (lane == 0) {
+            // Same two-phase schedule as the fp32 scan: a static round-robin first (no atomics, no start-up
+            // latency), then the last share of the tiles claimed from a global counter so that the SMs finish
+            // together.  Claims (and the claimed tile's mask word) run two ahead of their use.
             const uint64_t pol = policy_evict_first();
             int s = 0;
             uint32_t ph = 0;
-            for (uint32_t it = 0; it < iters; it++) {
-                const uint32_t row0 = (blockIdx.x + it * G) * kI8TileRows;
+            const uint32_t n_static = min(iters, p.static_iters);
+            // claims are chunks of kI8DynChunk consecutive tiles (an atomic's latency is ~2 tiles of streaming)
+            const uint32_t n_dyn = T > p.dyn_tile0 ? (T - p.dyn_tile0 + kI8DynChunk - 1) / kI8DynChunk : 0u;
+            uint32_t c0 = n_dyn, c1 = n_dyn;
+            if (n_dyn) {
+                c0 = atomicAdd(&p.ctl->tile_ctr, 1u);
+                c1 = atomicAdd(&p.ctl->tile_ctr, 1u);
+            }
+            auto admissible = [&](uint32_t tile) {
+                uint32_t adm = 0xFFFFFFFFu;
+                if (tile >= T) return 0u;
+                if (p.mask) adm &= p.mask[tile];
+                if (p.live) adm &= p.live[tile];
+                return adm;
+            };
+            auto issue = [&](uint32_t tile) {
+                const uint32_t row0 = tile * kI8TileRows;
                 const uint32_t bytes = min(uint32_t(kI8TileRows), p.n - row0) * p.rec_bytes;
-                mbar_wait(&hdr->empty[s], ph ^ 1u);
                 mbar_arrive_expect_tx(&hdr->full[s], bytes);
                 bulk_g2s(smem + p.stage_off + size_t(s) * p.stage_bytes, p.x8 + size_t(row0) * p.rec_bytes, bytes,
                          &hdr->full[s], pol);
+                if (++s == S) {
+                    s = 0;
+                    ph ^= 1u;
+                }
+            };
+            for (uint32_t it = 0; it < n_static; it++) {
+                mbar_wait(&hdr->empty[s], ph ^ 1u);
+                issue(blockIdx.x + it * G);
+            }
+            uint32_t a0[kI8DynChunk], a1[kI8DynChunk];
+#pragma unroll
+            for (uint32_t t = 0; t < kI8DynChunk; t++) a0[t] = (c0 < n_dyn) ? admissible(p.dyn_tile0 + c0 * kI8DynChunk + t) : 0u;
+            while (c0 < n_dyn) {
+                const uint32_t c2 = (c1 < n_dyn) ? atomicAdd(&p.ctl->tile_ctr, 1u) : n_dyn;
+#pragma unroll
+                for (uint32_t t = 0; t < kI8DynChunk; t++) a1[t] = (c1 < n_dyn) ? admissible(p.dyn_tile0 + c1 * kI8DynChunk + t) : 0u;
+#pragma unroll
+                for (uint32_t t = 0; t < kI8DynChunk; t++) {
+                    const uint32_t tile = p.dyn_tile0 + c0 * kI8DynChunk + t;
+                    if (tile >= T) break;
+                    mbar_wait(&hdr->empty[s], ph ^ 1u);
+                    hdr->tile_of[s] = tile;
+                    hdr->adm_of[s] = a0[t];
+                    issue(tile);
+                }
+                c0 = c1;
+                c1 = c2;
+#pragma unroll
+                for (uint32_t t = 0; t < kI8DynChunk; t++) a0[t] = a1[t];
+            }
+            asm volatile("" ::"r"(c1));
+            for (int i = 0; i < ncw; i++) {   // one stop marker per consumer warp (warp w owns the stages s % ncw == w)
+                mbar_wait(&hdr->empty[s], ph ^ 1u);
+                hdr->tile_of[s] = kNoTile;
+                mbar_arrive(&hdr->full[s]);
                 if (++s == S) {
                     s = 0;
                     ph ^= 1u;
@@ -337,14 +395,22 @@ __global__ void __launch_bounds__(288, 1) scan_i8_kernel(const I8Params p) {
     uint32_t n_cand = 0;
     uint32_t my_best = 0u, published = 0u, thr = 0u;
     uint32_t done_tiles = 0, next_refresh = 1, seen_refreshes = 0;
-    for (uint32_t it = cw; it < iters; it += ncw) {
-        const uint32_t tile = blockIdx.x + it * G;
-        const uint32_t row0 = tile * kI8TileRows;
-        uint32_t adm = 0xFFFFFFFFu;
-        if (p.mask) adm &= p.mask[tile];
-        if (p.live) adm &= p.live[tile];
+    const uint32_t n_static = min(iters, p.static_iters);
+    for (uint32_t it = cw;; it += ncw) {
         const int s = it % S;
-        mbar_wait(&hdr->full[s], (it / S) & 1u);
+        uint32_t tile, adm = 0xFFFFFFFFu;
+        if (it < n_static) {
+            tile = blockIdx.x + it * G;
+            if (p.mask) adm &= p.mask[tile];   // issued before the data wait
+            if (p.live) adm &= p.live[tile];
+            mbar_wait(&hdr->full[s], (it / S) & 1u);
+        } else {
+            mbar_wait(&hdr->full[s], (it / S) & 1u);
+            tile = hdr->tile_of[s];
+            if (tile == kNoTile) break;
+            adm = hdr->adm_of[s];
+        }
+        const uint32_t row0 = tile * kI8TileRows;
         const uint8_t* st = smem + p.stage_off + size_t(s) * p.stage_bytes;
         uint32_t upv[4];   // leaders: upper bound of "their" row of each 8-row group (0 = not admissible)
 #pragma unroll
@@ -464,6 +530,7 @@ __global__ void __launch_bounds__(288, 1) scan_i8_kernel(const I8Params p) {
         p.ctl->cand_cnt = 0u;
         p.ctl->surv_cnt = 0u;
         p.ctl->ticket = 0u;
+        p.ctl->tile_ctr = 0u;
     }
     if (ns > kI8SurvCap) {
         if (tid == 0) {   // the fp32 scan answers this query instead (conditional launch behind us, or the host re-runs it)

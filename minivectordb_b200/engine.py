@@ -135,8 +135,10 @@ class FlatIPEngine:
 
     # -- lifetime ----------------------------------------------------------
     def close(self) -> None:
+        """Destroy the index.  Mask handles, columns and workspaces made from it become inert (their own
+        close() stays legal).  An engine that belongs to a ShardGroup cannot be closed before the group."""
         if getattr(self, "_h", None) is not None and self._h.value:
-            N.lib().mvdb_index_destroy(self._h)
+            N.check(N.lib().mvdb_index_destroy(self._h))
             self._h = ctypes.c_void_p()
 
     def __del__(self):

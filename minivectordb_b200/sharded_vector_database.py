@@ -26,8 +26,8 @@ from ._store import GpuStore
 
 
 class ShardedVectorDatabase(GpuStore):
-    def __init__(self, storage_dir='db_shards', shard_size=5000, devices=None, persist=True):
-        super().__init__(devices=devices or [0])
+    def __init__(self, storage_dir='db_shards', shard_size=5000, devices=None, persist=True, scan_shadow=False):
+        super().__init__(devices=devices or [0], scan_shadow=scan_shadow)
         self.hash_vectorizer = HashingVectorizer(ngram_range=(1, 6), analyzer='char', n_features=64)
         self.storage_dir = storage_dir
         self.shard_size = shard_size

@@ -214,3 +214,26 @@ def test_device_filter_evaluation_matches_host_evaluation(classes, tmp_path):
     check_all()
     with pytest.raises(ValueError):
         db.find_most_similar(q, metadata_filter={"value": {"$regex": 1}})
+
+
+def test_golden_scenarios_with_the_int8_shadow_mode(classes, tmp_path):
+    """scan_shadow=True is an exact mode: the golden scenarios (recorded from the reference's own classes) still
+    hold, on one device and on a shard group (rows below the mode's 16384-row floor simply take the fp32 scan)."""
+    C.case_golden_scenario_vdb(lambda **kw: classes[0](scan_shadow=True, **kw), tmp_path)
+    C.case_golden_scenario_svdb(lambda **kw: classes[1](scan_shadow=True, **kw), tmp_path, devices=_devices(2))
+    # a database large enough for the shadow pass to engage
+    import numpy as np
+    rng = np.random.default_rng(0)
+    emb = rng.standard_normal((40_000, 96)).astype(np.float32)
+    a = classes[0](storage_file=str(tmp_path / "a.pkl"))
+    b = classes[0](storage_file=str(tmp_path / "b.pkl"), scan_shadow=True)
+    for db in (a, b):
+        db.store_embeddings_batch(list(range(40_000)), emb, [{"v": i % 7} for i in range(40_000)])
+    for i in (0, 17, 39_999):
+        ra = a.find_most_similar(emb[i] + 0.01, k=10)
+        rb = b.find_most_similar(emb[i] + 0.01, k=10)
+        assert ra[0] == rb[0] and np.array_equal(np.asarray(ra[1]), np.asarray(rb[1]))
+        ra = a.find_most_similar(emb[i], k=5, metadata_filter={"v": {"$gt": 3}})
+        rb = b.find_most_similar(emb[i], k=5, metadata_filter={"v": {"$gt": 3}})
+        assert ra[0] == rb[0] and np.array_equal(np.asarray(ra[1]), np.asarray(rb[1]))
+    a.close(); b.close()

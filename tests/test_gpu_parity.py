@@ -550,3 +550,34 @@ def test_mask_handles_and_coalesced_filtered_batches(mv):
         assert rep["ok"], (i, rep)
     [h.close() for h in handles]
     eng.close()
+
+
+def test_children_may_outlive_their_index(mv):
+    """Mask handles, columns and workspaces destroyed AFTER their index (what a garbage collector does) are inert,
+    not dangling: no crash, no stale CUDA error leaking into the next call; a grouped index cannot go first."""
+    import torch
+    eng = mv.FlatIPEngine(64)
+    eng.add_synthetic(1, 0, 5000, dist=0, normalize=True)
+    adm = np.zeros(5000, dtype=bool)
+    adm[::3] = True
+    handle = eng.mask_handle(adm)
+    col = eng.column()
+    col.append(np.arange(5000, dtype=np.float64), np.ones(5000, dtype=np.uint8))
+    pred = col.predicate("$gt", 10.0)
+    ws = eng.workspace()
+    q = O.synth_rows(2, 0, 1, 64)
+    eng.search(q, 5, mask=handle)
+    eng.close()                      # the index goes FIRST
+    with pytest.raises(Exception):
+        handle.count()
+    for child in (handle, pred, col, ws):
+        child.close()                # ... and its children afterwards: harmless
+    eng2 = mv.FlatIPEngine(64)       # the next calls in this thread start from a clean error state
+    eng2.add_synthetic(1, 0, 5000, dist=0, normalize=True)
+    D, I = eng2.search(q, 5)
+    assert I[0, 0] >= 0
+    grp = mv.ShardGroup([eng2])
+    with pytest.raises(Exception):
+        eng2.close()                 # a member of a group cannot be destroyed before the group
+    grp.close()
+    eng2.close()
