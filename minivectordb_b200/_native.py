@@ -56,11 +56,26 @@ def sources():
                   if f.endswith((".cu", ".cuh"))) + [os.path.join(_ROOT, "include", "mvdb_b200.h")]
 
 
+HASH_PATH = LIB_PATH + ".srchash"
+
+
+def source_hash() -> str:
+    """Content hash of every source the library is built from plus the compiler flags: what decides
+    whether the in-tree .so is current (file times do not survive a checkout or a snapshot)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for path in sources():
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(LIB_PATH) or not os.path.exists(HASH_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    return any(os.path.getmtime(s) > t for s in sources())
+    with open(HASH_PATH) as f:
+        return f.read().strip() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -76,6 +91,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     os.replace(LIB_PATH + ".tmp", LIB_PATH)
+    with open(HASH_PATH, "w") as f:
+        f.write(source_hash() + "\n")
     if verbose:
         print(res.stderr)
     return LIB_PATH

@@ -48,3 +48,14 @@ def test_library_has_no_libcuda_link_dependency():
     import subprocess
     out = subprocess.run(["ldd", N.LIB_PATH], capture_output=True, text=True).stdout
     assert "libcuda.so" not in out
+
+
+def test_build_decision_follows_source_content_not_file_times(tmp_path, monkeypatch):
+    """build() recompiles when (and only when) the sources or flags differ from what the shipped .so was
+    built from -- a content hash next to the library, not mtimes."""
+    assert os.path.exists(N.HASH_PATH), "run __graft_entry__.build() first"
+    assert not N.needs_build()
+    os.utime(os.path.join(N.SRC_DIR, "scan.cuh"))          # a newer mtime alone changes nothing
+    assert not N.needs_build()
+    monkeypatch.setattr(N, "NVCC_FLAGS", N.NVCC_FLAGS + ["-DX"])
+    assert N.needs_build()                                   # different flags (or sources) do
