@@ -547,26 +547,26 @@ __global__ void __launch_bounds__(288, 1) scan_i8_kernel(const I8Params p) {
     while (npad < ns) npad <<= 1;
     for (uint32_t i = tid; i < npad; i += nthr) sk[i] = i < ns ? __ldcg(p.surv + i) : kEmptyKey;
     named_bar_sync(1, nthr);
+    // from here on one warp is enough unless the list is long; the other warps leave (no barrier is executed
+    // on one side of a warp-level branch only)
     if (npad <= 256) {
-        if (cw == 0) {
-            if (npad == 64) warp_sort_buffer<2>(sk, int(ns), lane);
-            else if (npad == 128) warp_sort_buffer<4>(sk, int(ns), lane);
-            else warp_sort_buffer<8>(sk, int(ns), lane);
-        }
+        if (cw != 0) return;
+        if (npad == 64) warp_sort_buffer<2>(sk, int(ns), lane);
+        else if (npad == 128) warp_sort_buffer<4>(sk, int(ns), lane);
+        else warp_sort_buffer<8>(sk, int(ns), lane);
     } else {
         bitonic_sort_desc(sk, int(npad), tid, nthr, [&] { named_bar_sync(1, nthr); });
+        if (cw != 0) return;
     }
-    named_bar_sync(1, nthr);
+    __syncwarp();
     if (p.xchg) {
         // sharded search: same protocol as the fp32 scan's tail (scan.cuh finish_scan) -- send, publish, wait, merge
-        if (cw == 0) {
-            xchg_send(p.xchg, p.xchg_seq, 0, sk, int(min(ns, unsigned(p.k))), p.k, lane);
-            xchg_publish_and_wait(p.xchg, p.xchg_seq, lane);
-            xchg_merge(p.xchg, p.xchg_seq, 0, sk + 4096, select_cap(p.k), p.k, p.outD, p.outI, lane);
-        }
+        xchg_send(p.xchg, p.xchg_seq, 0, sk, int(min(ns, unsigned(p.k))), p.k, lane);
+        xchg_publish_and_wait(p.xchg, p.xchg_seq, lane);
+        xchg_merge(p.xchg, p.xchg_seq, 0, sk + 4096, select_cap(p.k), p.k, p.outD, p.outI, lane);
         return;
     }
-    for (int i = tid; i < p.k; i += nthr) {
+    for (int i = lane; i < p.k; i += kWarp) {
         const uint64_t key = (unsigned(i) < ns) ? sk[i] : kEmptyKey;
         if (key == kEmptyKey) {
             p.outD[i] = -FLT_MAX;
