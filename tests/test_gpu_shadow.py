@@ -138,3 +138,37 @@ def test_shadow_overflow_falls_back_on_the_device_and_on_the_host_path(mv):
     Dr2, Ir2 = eng2.search(q2, 10)
     assert np.array_equal(I.cpu().numpy(), Ir2) and np.array_equal(D.cpu().numpy(), Dr2)
     ws.close(); ws2.close(); eng.close(); eng2.close()
+
+
+@pytest.mark.parametrize("coalesce", [0, 1])
+def test_shadow_mode_from_many_host_threads(mv, coalesce):
+    """Concurrent single-query callers in shadow mode: every call runs on its own pooled workspace (own int8
+    state); with the coalescer on, lone calls take the shadow pass and shared passes take the batch paths --
+    every caller still gets the fp32 scan's answer."""
+    import threading
+    n, d, k = 150_000, 256, 10
+    eng = mv.FlatIPEngine(d)
+    eng.add_synthetic(61, 0, n, dist=0, normalize=True)
+    q = O.synth_rows(62, 0, 16, d)
+    O.normalize_L2(q)
+    adm = np.random.default_rng(6).random(n) < 0.5
+    eng.set_option("coalesce", 0)
+    eng.set_option("scan_shadow", 0)
+    ref = [eng.search(q[i:i + 1], k, mask=adm if i % 2 else None) for i in range(16)]
+    eng.set_option("scan_shadow", 1)
+    eng.set_option("coalesce", coalesce)
+    errs = []
+
+    def run(i):
+        try:
+            for _ in range(25):
+                D, I = eng.search(q[i:i + 1], k, mask=adm if i % 2 else None)
+                assert np.array_equal(I, ref[i][1]) and np.array_equal(D, ref[i][0])
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=run, args=(i,)) for i in range(16)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    eng.close()
+    assert not errs, errs[:1]

@@ -18,15 +18,18 @@ d = int(sys.argv[2]) if len(sys.argv) > 2 else 768
 secs = float(sys.argv[3]) if len(sys.argv) > 3 else 20.0
 k = 10
 out = []
-# lines: (coalesce, query threads, filters as mask handles, coalesce_leaders [0 = auto]); override with
-# CONFIGS="1:8:1:2,1:8:1:0"
-lines = ((0, 8, 0, 0), (1, 8, 0, 0), (1, 8, 1, 0), (1, 32, 1, 0), (1, 64, 1, 0))
+# lines: (coalesce, query threads, filters as mask handles, coalesce_leaders [0 = auto][, scan_shadow]); override with
+# CONFIGS="1:8:1:2,1:8:1:0" ; a fifth field 1 runs the line in the opt-in int8 shadow mode
+lines = ((0, 8, 0, 0), (1, 8, 0, 0), (1, 8, 1, 0), (1, 32, 1, 0), (1, 64, 1, 0), (0, 8, 1, 0, 1), (0, 2, 1, 0, 1))
 if os.environ.get("CONFIGS"):
     lines = tuple(tuple(int(x) for x in c.split(":")) for c in os.environ["CONFIGS"].split(","))
-for coalesce, nthreads, handles, leaders in lines:
+for line in lines:
+    coalesce, nthreads, handles, leaders = line[:4]
+    shadow = line[4] if len(line) > 4 else 0
     eng = mv.FlatIPEngine(d, capacity_hint=n + 2_000_000)
     eng.add_synthetic(1234, 0, n, 0, True)
     eng.set_option("coalesce", coalesce)
+    eng.set_option("scan_shadow", shadow)
     eng.set_option("coalesce_leaders", leaders)
     masks = [mv.pack_mask(synth.synth_mask(100 + i, n, 0.5)) for i in range(4)]
     if handles:
@@ -81,7 +84,7 @@ for coalesce, nthreads, handles, leaders in lines:
     [t.join() for t in ts]
     dt = time.perf_counter() - t0
     all_lat = np.concatenate([np.asarray(x) for x in lat if x])
-    rec = dict(rows=n, dim=d, k=k, query_threads=nthreads, coalesce=coalesce, mask_handles=handles, leaders=leaders, seconds=dt, queries=int(all_lat.size),
+    rec = dict(rows=n, dim=d, k=k, query_threads=nthreads, coalesce=coalesce, mask_handles=handles, leaders=leaders, scan_shadow=shadow, seconds=dt, queries=int(all_lat.size),
                qps=all_lat.size / dt, p50_ms=float(np.median(all_lat) * 1e3), p99_ms=float(np.percentile(all_lat, 99) * 1e3),
                inserted=counts["ins"], deleted=counts["dele"], ntotal=eng.ntotal, nlive=eng.nlive, errors=len(errs),
                scan_bytes=n * eng.device_view()[1] * 4)

@@ -12,11 +12,16 @@ for key, rep, rows, dim, raw in (("c4", "r02_prof_scan_c4", 12_500_000, 512, "r0
                                  ("c2", "r02_prof_scan_c2", 1_000_000, 384, "r02_scan_q1_c2_full_raw.csv"),
                                  ("c4_shadow", "r02_prof_scan_i8_c4", 12_500_000, 512, "r02_scan_i8_c4_full_raw.csv")):
     src = os.path.join(ROOT, "gpurun_out", rep + ".ncu-rep")
-    if not os.path.exists(src):
-        continue
+    csv_src = os.path.join(ROOT, "gpurun_out", rep + ".raw.csv")
     dst = os.path.join(ROOT, "profiles", raw)
-    with open(dst, "w") as f:
-        subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], stdout=f, check=True)
+    if os.path.exists(csv_src):          # tools/ncu_refresh.sh exports the raw page on the GPU box (the reports are too big to travel)
+        import shutil
+        shutil.copy(csv_src, dst)
+    elif os.path.exists(src):
+        with open(dst, "w") as f:
+            subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], stdout=f, check=True)
+    else:
+        continue
     rws = list(csv.reader(open(dst)))
     hdr, units = rws[0], rws[1]
     idx = {k: i for i, k in enumerate(hdr)}
