@@ -16,6 +16,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <thread>
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
@@ -437,6 +439,8 @@ struct mvdb_index {
     std::deque<struct CoalesceReq*> co_queue;
     int co_leaders = 0;
     int co_max_leaders = 0;        // option "coalesce_leaders": 0 = auto (1 for large matrices, else 2)
+    size_t co_last_batch = 0;      // size of the batch that ran last: how much company a new leader may expect
+    int co_wait_pct = 5;           // option "coalesce_wait_pct": a leader waits at most this % of a pass for that company (0 = never)
     // objects that point back at this index (mask handles, columns, caller-owned workspaces): destroying the
     // index releases their device memory and orphans them, so that a later *_destroy of theirs (e.g. from a
     // garbage collector that runs after the index is gone) is harmless
@@ -1531,6 +1535,9 @@ int mvdb_index_set_option(mvdb_index* ix, const char* name, int64_t value) {
     } else if (s == "coalesce") {
         if (value < 0 || value > 1) return fail(MVDB_ERR_ARG, "coalesce must be 0 or 1");
         ix->coalesce = int(value);
+    } else if (s == "coalesce_wait_pct") {
+        if (value < 0 || value > 50) return fail(MVDB_ERR_ARG, "coalesce_wait_pct must be 0..50");
+        ix->co_wait_pct = int(value);
     } else if (s == "coalesce_max") {
         if (value < 1 || value > 1024) return fail(MVDB_ERR_ARG, "coalesce_max must be 1..1024");
         ix->coalesce_max = int(value);
@@ -1640,6 +1647,40 @@ static int add_common(mvdb_index* ix, const float* x_host, const float* x_dev, b
         LAUNCHED();
     }
     CU_OK(cudaGetLastError());
+    // int8 shadow mode: keep an up-to-date shadow up to date HERE (same stream, same synchronise) -- otherwise
+    // every search that follows an insert would have to extend it first and wait on this busy stream
+    bool shadow8_extended = false;
+    if (ix->scan_shadow) {
+        std::lock_guard<std::mutex> sg(ix->shadow8_mu);
+        if (ix->shadow8_rows > 0 && ix->shadow8_rows <= n0) {
+            // from wherever the shadow ends (adds that raced a search's own extension leave a gap) up to the new end
+            const uint64_t r0 = ix->shadow8_rows, m = n0 + n - r0;
+            RC_OK(ix->mat8.ensure(size_t(n0 + n) * ix->rec8, st));
+            unsigned grid8 = unsigned(std::min<uint64_t>((m * 32 + 255) / 256, uint64_t(ix->sm_count) * 16));
+            to_i8_rows_kernel<<<grid8, 256, 0, st>>>(static_cast<const float*>(ix->mat.ptr()) + r0 * ix->ld,
+                                                     static_cast<uint8_t*>(ix->mat8.ptr()) + r0 * ix->rec8, m, ix->ld4, ix->ld8, ix->rec8);
+            LAUNCHED();
+            CU_OK(cudaGetLastError());
+            shadow8_extended = true;
+        }
+    }
+    // same for the bf16 shadow of the tensor-core batch path: under insert churn every coalesced batch used to
+    // extend it first and wait for this (busy) stream -- more than doubling the time of a pass
+    bool shadow16_extended = false;
+    {
+        std::lock_guard<std::mutex> sg(ix->shadow_mu);
+        if (ix->shadow_rows > 0 && ix->shadow_rows <= n0) {
+            const uint64_t r0 = ix->shadow_rows, m = n0 + n - r0;
+            RC_OK(ix->mat16.ensure(size_t(n0 + n) * ix->ld16 * 2, st));
+            unsigned grid16 = unsigned(std::min<uint64_t>((m * 32 + 255) / 256, uint64_t(ix->sm_count) * 16));
+            to_bf16_rows_kernel<<<grid16, 256, 0, st>>>(static_cast<const float*>(ix->mat.ptr()) + r0 * ix->ld,
+                                                        static_cast<__nv_bfloat16*>(ix->mat16.ptr()) + r0 * ix->ld16, m, ix->d,
+                                                        ix->ld, ix->ld16);
+            LAUNCHED();
+            CU_OK(cudaGetLastError());
+            shadow16_extended = true;
+        }
+    }
     {
         int bits = 0;
         CU_OK(cudaMemcpyAsync(&bits, ix->max_norm2_bits, sizeof bits, cudaMemcpyDeviceToHost, st));
@@ -1657,6 +1698,14 @@ static int add_common(mvdb_index* ix, const float* x_host, const float* x_dev, b
             ix->live_host[r >> 5] |= 1u << (r & 31);
             r++;
         }
+    }
+    if (shadow16_extended) {
+        std::lock_guard<std::mutex> sg(ix->shadow_mu);
+        if (ix->shadow_rows > 0 && ix->shadow_rows <= n0 + n) ix->shadow_rows = n0 + n;
+    }
+    if (shadow8_extended) {
+        std::lock_guard<std::mutex> sg(ix->shadow8_mu);
+        if (ix->shadow8_rows > 0 && ix->shadow8_rows <= n0 + n) ix->shadow8_rows = n0 + n;
     }
     ix->ntotal.store(n0 + n, std::memory_order_release);
     return MVDB_OK;
@@ -2032,6 +2081,22 @@ static int coalesced_search(mvdb_index* ix, CoalesceReq& req) {
     }
     if (seat) {
         while (!req.done) {
+            // Callers that were served by one shared pass come back TOGETHER: the first of them to arrive would
+            // otherwise run a pass for itself alone while the others queue up behind it, and batches would
+            // alternate between 1 and B-1 queries.  So a leader that can expect company (the previous batch had
+            // several queries) gives it a moment: at most co_wait_pct % of one pass over the matrix, i.e.
+            // nothing for small indexes and ~0.1 ms when a pass takes milliseconds.
+            if (ix->co_wait_pct > 0 && ix->co_last_batch > 1 && !ix->co_queue.empty() && ix->co_queue.size() < ix->co_last_batch) {
+                const double pass_s = double(ix->ntotal.load(std::memory_order_acquire)) * double(ix->ld) * 2.0 / 6.0e12;
+                const auto deadline = std::chrono::steady_clock::now() +
+                                      std::chrono::nanoseconds(int64_t(pass_s * 1e9 * ix->co_wait_pct / 100.0));
+                const size_t want = std::min(ix->co_last_batch, size_t(ix->coalesce_max));
+                while (ix->co_queue.size() < want && std::chrono::steady_clock::now() < deadline) {
+                    lk.unlock();
+                    std::this_thread::yield();
+                    lk.lock();
+                }
+            }
             if (ix->co_queue.empty()) {
                 // our own request is in flight inside the other leader's batch
                 req.cv.wait(lk, [&] { return req.done; });
@@ -2057,6 +2122,7 @@ static int coalesced_search(mvdb_index* ix, CoalesceReq& req) {
                     ++it;
                 }
             }
+            ix->co_last_batch = batch.size();
             lk.unlock();
             int rc = exec_coalesced(ix, batch);
             std::string err = rc != MVDB_OK ? g_err : std::string();

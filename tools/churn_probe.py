@@ -18,6 +18,9 @@ d = int(sys.argv[2]) if len(sys.argv) > 2 else 768
 secs = float(sys.argv[3]) if len(sys.argv) > 3 else 20.0
 k = 10
 out = []
+# the probe's own threads are Python: with the default 5 ms GIL switch interval a query thread that comes back from
+# the C ABI can wait milliseconds for the interpreter while an insert thread builds its next block
+sys.setswitchinterval(float(os.environ.get("SWITCH_INTERVAL", "0.0002")))
 # lines: (coalesce, query threads, filters as mask handles, coalesce_leaders [0 = auto][, scan_shadow]); override with
 # CONFIGS="1:8:1:2,1:8:1:0" ; a fifth field 1 runs the line in the opt-in int8 shadow mode
 lines = ((0, 8, 0, 0), (1, 8, 0, 0), (1, 8, 1, 0), (1, 32, 1, 0), (1, 64, 1, 0), (0, 8, 1, 0, 1), (0, 2, 1, 0, 1))
