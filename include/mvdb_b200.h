@@ -104,9 +104,10 @@ int mvdb_index_reset(mvdb_index* ix);
  *                   the matrix (leader/follower, no added latency when idle); "coalesce_max"
  *                   caps a shared pass (default 64 queries); "coalesce_leaders" 0 (default) =
  *                   one batch in flight for matrices >= 256 MB, two below; 1 / 2 force it;
- *                   "coalesce_wait_pct" (default 5): callers served by one shared pass come back together, so a
- *                   leader that can expect that company waits for it for at most this % of one pass over the
- *                   matrix before it starts the next pass (0 = never wait)
+ *                   "coalesce_wait_pct" (default 40): callers served by one shared pass come back together, so a
+ *                   leader that can expect that company (the previous batch had several queries) waits for it
+ *                   -- while callers keep arriving, and for at most this % of one pass over the matrix --
+ *                   before it starts the next pass (0 = never wait; a lone caller never waits)
  *   "gemm_variant"  tile scheme of the tensor-core batch: 0 one CTA per 128x256 tile, 1 CTA pairs
  *                   (cta_group::2), 2 clusters of 2 sharing the row tile by TMA multicast
  *                   (default), 3 clusters of 4; "gemm_l2_hint" 0/1/2 L2 eviction hints (A/B)

@@ -440,7 +440,7 @@ struct mvdb_index {
     int co_leaders = 0;
     int co_max_leaders = 0;        // option "coalesce_leaders": 0 = auto (1 for large matrices, else 2)
     size_t co_last_batch = 0;      // size of the batch that ran last: how much company a new leader may expect
-    int co_wait_pct = 5;           // option "coalesce_wait_pct": a leader waits at most this % of a pass for that company (0 = never)
+    int co_wait_pct = 40;          // option "coalesce_wait_pct": a leader waits at most this % of a pass for that company (0 = never)
     // objects that point back at this index (mask handles, columns, caller-owned workspaces): destroying the
     // index releases their device memory and orphans them, so that a later *_destroy of theirs (e.g. from a
     // garbage collector that runs after the index is gone) is harmless
@@ -2081,17 +2081,28 @@ static int coalesced_search(mvdb_index* ix, CoalesceReq& req) {
     }
     if (seat) {
         while (!req.done) {
-            // Callers that were served by one shared pass come back TOGETHER: the first of them to arrive would
-            // otherwise run a pass for itself alone while the others queue up behind it, and batches would
-            // alternate between 1 and B-1 queries.  So a leader that can expect company (the previous batch had
-            // several queries) gives it a moment: at most co_wait_pct % of one pass over the matrix, i.e.
-            // nothing for small indexes and ~0.1 ms when a pass takes milliseconds.
+            // Callers that were served by one shared pass come back TOGETHER (within the time their host code
+            // needs to issue the next call): the first of them to arrive would otherwise run a pass for itself
+            // alone while the others queue up behind it, and every round of B callers would cost two passes.  So a
+            // leader that can expect company (the previous batch had several queries) gives it a moment --
+            // nothing measurable for small indexes, a fraction of a millisecond when a pass takes milliseconds.
             if (ix->co_wait_pct > 0 && ix->co_last_batch > 1 && !ix->co_queue.empty() && ix->co_queue.size() < ix->co_last_batch) {
-                const double pass_s = double(ix->ntotal.load(std::memory_order_acquire)) * double(ix->ld) * 2.0 / 6.0e12;
-                const auto deadline = std::chrono::steady_clock::now() +
-                                      std::chrono::nanoseconds(int64_t(pass_s * 1e9 * ix->co_wait_pct / 100.0));
+                // wait while callers keep arriving: until the previous company is back, or nobody has arrived for
+                // a short gap (2 % of a pass, >= 20 us), or co_wait_pct % of a pass has gone by
+                const double pass_ns = double(ix->ntotal.load(std::memory_order_acquire)) * double(ix->ld) * 2.0 / 6.0e12 * 1e9;
+                const auto t_start = std::chrono::steady_clock::now();
+                const auto deadline = t_start + std::chrono::nanoseconds(int64_t(pass_ns * ix->co_wait_pct / 100.0));
+                const auto gap = std::chrono::nanoseconds(std::max<int64_t>(20000, int64_t(pass_ns * 0.02)));
                 const size_t want = std::min(ix->co_last_batch, size_t(ix->coalesce_max));
-                while (ix->co_queue.size() < want && std::chrono::steady_clock::now() < deadline) {
+                size_t seen = ix->co_queue.size();
+                auto last_growth = t_start;
+                for (;;) {
+                    const auto now = std::chrono::steady_clock::now();
+                    if (ix->co_queue.size() > seen) {
+                        seen = ix->co_queue.size();
+                        last_growth = now;
+                    }
+                    if (seen >= want || now >= deadline || now - last_growth > gap) break;
                     lk.unlock();
                     std::this_thread::yield();
                     lk.lock();
