@@ -79,7 +79,8 @@ for line in lines:
             errs.append(e)
 
     ts = [threading.Thread(target=querier, args=(t,)) for t in range(nthreads)]
-    ts += [threading.Thread(target=inserter, args=(t,)) for t in range(2)] + [threading.Thread(target=deleter)]
+    ts += [threading.Thread(target=inserter, args=(t,)) for t in range(int(os.environ.get("INSERTERS", "2")))]
+    ts += [threading.Thread(target=deleter)] * int(os.environ.get("DELETER", "1"))
     t0 = time.perf_counter()
     [t.start() for t in ts]
     time.sleep(secs)
