@@ -439,7 +439,8 @@ struct mvdb_index {
     std::deque<struct CoalesceReq*> co_queue;
     int co_leaders = 0;
     int co_max_leaders = 0;        // option "coalesce_leaders": 0 = auto (1 for large matrices, else 2)
-    size_t co_last_batch = 0;      // size of the batch that ran last: how much company a new leader may expect
+    size_t co_last_batch = 0;      // sizes of the last two batches: how much company a new leader may expect (their SUM --
+    size_t co_prev_batch = 0;      // a round of callers that split into two batches must be able to merge again)
     int co_wait_pct = 40;          // option "coalesce_wait_pct": a leader waits at most this % of a pass for that company (0 = never)
     // objects that point back at this index (mask handles, columns, caller-owned workspaces): destroying the
     // index releases their device memory and orphans them, so that a later *_destroy of theirs (e.g. from a
@@ -2086,14 +2087,15 @@ static int coalesced_search(mvdb_index* ix, CoalesceReq& req) {
             // alone while the others queue up behind it, and every round of B callers would cost two passes.  So a
             // leader that can expect company (the previous batch had several queries) gives it a moment --
             // nothing measurable for small indexes, a fraction of a millisecond when a pass takes milliseconds.
-            if (ix->co_wait_pct > 0 && ix->co_last_batch > 1 && !ix->co_queue.empty() && ix->co_queue.size() < ix->co_last_batch) {
+            if (ix->co_wait_pct > 0 && ix->co_last_batch + ix->co_prev_batch > 2 && !ix->co_queue.empty() &&
+                ix->co_queue.size() < ix->co_last_batch + ix->co_prev_batch) {
                 // wait while callers keep arriving: until the previous company is back, or nobody has arrived for
                 // a short gap (2 % of a pass, >= 20 us), or co_wait_pct % of a pass has gone by
                 const double pass_ns = double(ix->ntotal.load(std::memory_order_acquire)) * double(ix->ld) * 2.0 / 6.0e12 * 1e9;
                 const auto t_start = std::chrono::steady_clock::now();
                 const auto deadline = t_start + std::chrono::nanoseconds(int64_t(pass_ns * ix->co_wait_pct / 100.0));
                 const auto gap = std::chrono::nanoseconds(std::max<int64_t>(20000, int64_t(pass_ns * 0.02)));
-                const size_t want = std::min(ix->co_last_batch, size_t(ix->coalesce_max));
+                const size_t want = std::min(ix->co_last_batch + ix->co_prev_batch, size_t(ix->coalesce_max));
                 size_t seen = ix->co_queue.size();
                 auto last_growth = t_start;
                 for (;;) {
@@ -2133,6 +2135,7 @@ static int coalesced_search(mvdb_index* ix, CoalesceReq& req) {
                     ++it;
                 }
             }
+            ix->co_prev_batch = ix->co_last_batch;
             ix->co_last_batch = batch.size();
             lk.unlock();
             int rc = exec_coalesced(ix, batch);
