@@ -111,6 +111,10 @@ int mvdb_index_reset(mvdb_index* ix);
  *   "gemm_variant"  tile scheme of the tensor-core batch: 0 one CTA per 128x256 tile, 1 CTA pairs
  *                   (cta_group::2), 2 clusters of 2 sharing the row tile by TMA multicast
  *                   (default), 3 clusters of 4; "gemm_l2_hint" 0/1/2 L2 eviction hints (A/B)
+ *   "survivor_tail" (default 1) single-query scans with 16 < k <= 128 keep no per-warp top-k lists: a shared
+ *                   threshold (k-th largest of the per-warp best scores) and one global list of the keys that
+ *                   pass it, sorted by the last CTA -- same results, a much shorter serial tail; 0 = the
+ *                   per-warp selects + merge tree (also the automatic fallback when the list overflows)
  *   "scan_shadow"   (default 0) 1 = single-query searches (k <= 128, d <= 1024, >= 16384 rows) stream an int8
  *                   SHADOW of the matrix (d + 16 bytes per row instead of 4 d; built lazily, kept in step
  *                   with appends) to select a rigorous candidate superset, and re-score the survivors from

@@ -498,6 +498,14 @@ class GpuStore:
                 metadatas = [v for i, v in enumerate(metadatas) if i not in drop]
         return ids, distances, metadatas
 
+    def __del__(self):
+        # finalisers run in no particular order: release the native objects in THE order they need
+        # (mask handles and columns, then the shard group, then the engines)
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
     def close(self) -> None:
         if self._pool is not None:
             self._pool.shutdown(wait=True)

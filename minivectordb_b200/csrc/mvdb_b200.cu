@@ -319,6 +319,10 @@ struct mvdb_workspace {
     size_t b_lqptr_cap = 0;
     uint32_t* b_lqwords = nullptr;
     size_t b_lqwords_cap = 0;
+    // survivor mode of the fp32 scan (16 < k <= 128)
+    uint64_t* sv_surv = nullptr;
+    unsigned int* sv_best = nullptr;
+    SurvCtl* sv_ctl = nullptr;
     // int8 shadow mode (scan_i8.cuh)
     uint64_t* i8_surv = nullptr;
     unsigned int* i8_ovf_pin = nullptr;   // pinned + mapped: raised by the kernel when the survivor list overflowed
@@ -409,6 +413,7 @@ struct mvdb_index {
     uint64_t shadow8_rows = 0;
     std::mutex shadow8_mu;
     int scan_shadow = 0;
+    int survivor_tail = 1;          // 16 < k <= 128 single-query scans: shared threshold + global survivor list (0 = per-warp selects + merge tree)
     int* max_norm2_bits = nullptr;  // device: bit pattern of the largest squared row norm stored
     std::atomic<float> max_norm2_host{0.f};  // host copy, refreshed at the end of every add
     // options
@@ -507,6 +512,19 @@ static ScanKernel q1_kernel(int d4) {
         case 6: return scan_q1_kernel<6, kTma>;
         case 7: return scan_q1_kernel<7, kTma>;
         case 8: return scan_q1_kernel<8, kTma>;
+        default: return nullptr;
+    }
+}
+static ScanKernel q1_survivor_kernel(int d4) {
+    switch (d4) {
+        case 1: return scan_q1_kernel<1, true, true>;
+        case 2: return scan_q1_kernel<2, true, true>;
+        case 3: return scan_q1_kernel<3, true, true>;
+        case 4: return scan_q1_kernel<4, true, true>;
+        case 5: return scan_q1_kernel<5, true, true>;
+        case 6: return scan_q1_kernel<6, true, true>;
+        case 7: return scan_q1_kernel<7, true, true>;
+        case 8: return scan_q1_kernel<8, true, true>;
         default: return nullptr;
     }
 }
@@ -989,17 +1007,57 @@ static bool i8_eligible(const mvdb_index* ix, int64_t nq, int64_t k, uint32_t n)
     return i8_consumer_warps(ix) != 0;
 }
 
+static constexpr uint32_t kSurvCap = 4096;
+
+// pinned + mapped word a kernel raises when its candidate / survivor list overflowed (host-buffer callers check it
+// after their synchronise and re-run the query on the classic scan)
+static int ws_overflow_flag(mvdb_workspace* ws) {
+    if (ws->i8_ovf_pin) return MVDB_OK;
+    CU_OK(cudaHostAlloc(reinterpret_cast<void**>(&ws->i8_ovf_pin), sizeof(unsigned int), cudaHostAllocMapped));
+    *ws->i8_ovf_pin = 0u;
+    CU_OK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ws->i8_ovf_dev), ws->i8_ovf_pin, 0));
+    return MVDB_OK;
+}
+
+// scratch of the survivor mode (allocations synchronise the device: a shard group does this before its first launch)
+static int sv_prepare(mvdb_index* ix, mvdb_workspace* ws, int d4, cudaStream_t stream) {
+    RC_OK(ws_overflow_flag(ws));
+    if (!ws->sv_ctl) {
+        CU_OK(cudaMalloc(&ws->sv_ctl, sizeof(SurvCtl)));
+        CU_OK(cudaMalloc(&ws->sv_surv, size_t(kSurvCap) * 8));
+        CU_OK(cudaMalloc(&ws->sv_best, size_t(kI8BestM) * 32 * 4));
+        CU_OK(cudaMemsetAsync(ws->sv_ctl, 0, sizeof(SurvCtl), stream));
+        CU_OK(cudaMemsetAsync(ws->sv_best, 0, size_t(kI8BestM) * 32 * 4, stream));
+    }
+    static std::mutex mu;
+    static std::vector<std::pair<void*, int>> done;
+    std::lock_guard<std::mutex> g(mu);
+    void* fn = reinterpret_cast<void*>(q1_survivor_kernel(d4));
+    bool seen = false;
+    for (auto& e : done) seen |= (e.first == fn && e.second == ix->device);
+    if (!seen) {
+        CU_OK(cudaFuncSetAttribute(q1_survivor_kernel(d4), cudaFuncAttributeMaxDynamicSharedMemorySize, int(ix->smem_optin)));
+        done.push_back({fn, ix->device});
+    }
+    return MVDB_OK;
+}
+
+// Survivor mode applies to: one query, 16 < k <= 128, the TMA single-query kernel, enough rows to amortise the
+// threshold refreshes, and a ring large enough to sort the survivor list in.
+static bool sv_eligible(const mvdb_index* ix, const ScanPlan& plan, const ScanParams& p, int g) {
+    return ix->survivor_tail && g == 1 && plan.tma && plan.q1 && p.k > 16 && p.k <= 128 && p.n >= 16384 &&
+           size_t(p.merge_bytes) >= (size_t(kSurvCap) + 256) * 8 && !p.all_ord;
+}
+
 // everything the int8 mode sets up lazily (shadow rows, scratch, shared-memory opt-in): all of it may
 // synchronise the device, so a shard group does it before its first launch (prepare_fused_scan)
 static int i8_prepare(mvdb_index* ix, mvdb_workspace* ws, uint64_t n, cudaStream_t stream) {
     RC_OK(ensure_shadow8(ix, n));
+    RC_OK(ws_overflow_flag(ws));
     if (!ws->i8_ctl) {
         CU_OK(cudaMalloc(&ws->i8_ctl, sizeof(I8Ctl)));
         CU_OK(cudaMalloc(&ws->i8_surv, size_t(kI8SurvCap) * 8));
         CU_OK(cudaMalloc(&ws->i8_best, size_t(kI8BestM) * 32 * 4));
-        CU_OK(cudaHostAlloc(reinterpret_cast<void**>(&ws->i8_ovf_pin), sizeof(unsigned int), cudaHostAllocMapped));
-        *ws->i8_ovf_pin = 0u;
-        CU_OK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ws->i8_ovf_dev), ws->i8_ovf_pin, 0));
         // zero once; from then on every search leaves the control block and the table clean for the next
         CU_OK(cudaMemsetAsync(ws->i8_ctl, 0, sizeof(I8Ctl), stream));
         CU_OK(cudaMemsetAsync(ws->i8_best, 0, size_t(kI8BestM) * 32 * 4, stream));
@@ -1218,7 +1276,33 @@ static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, in
                 p.tile_ctr = ws->ticket + 32 + 32 * (ws->launch_seq++ & 1u);
             }
             p.pdl_early = 0;
-            if (ix->pdl && tl_allow_pdl && !run_if) {
+            const unsigned int* launch_if = run_if;
+            if (!run_if && !tl_force_scan && sv_eligible(ix, plan, p, g)) {
+                // 16 < k <= 128: shared threshold + global survivor list, the last CTA sorts; the classic kernel is
+                // only its overflow fallback (conditional launch, or the host caller re-runs the query)
+                const int d4 = (ix->ld4 + 31) / 32;
+                RC_OK(sv_prepare(ix, ws, d4, stream));
+                ScanParams sp = p;
+                sp.surv = ws->sv_surv;
+                sp.sctl = ws->sv_ctl;
+                sp.best = ws->sv_best;
+                sp.surv_cap = kSurvCap;
+                sp.nbest = p.k <= 32 ? uint32_t(plan.grid) : uint32_t(plan.grid) * uint32_t(plan.threads / 32 - 1);
+                sp.ovf_host = (tl_host_checks_i8 && !xch) ? ws->i8_ovf_dev : nullptr;
+                if (sp.nbest <= uint32_t(kI8BestM) * 32) {
+                    q1_survivor_kernel(d4)<<<plan.grid, plan.threads, plan.smem, stream>>>(sp);
+                    LAUNCHED();
+                    CU_OK(cudaGetLastError());
+                    if (tl_host_checks_i8 && !xch) {   // the caller checks the pinned flag after its synchronise
+                        done += g;
+                        continue;
+                    }
+                    launch_if = &ws->sv_ctl->overflow;
+                    if (p.tile_ctr) p.tile_ctr = ws->ticket + 32 + 32 * (ws->launch_seq++ & 1u);   // the fallback's own counter slot
+                }
+            }
+            p.run_if = launch_if;
+            if (ix->pdl && tl_allow_pdl && !launch_if) {
                 // Entry trigger only when this launch AND the previous scan of this workspace fill every SM
                 // with one CTA each: then a CTA of this grid can only start where the previous grid has left,
                 // all of them have started only once the previous grid is complete, and the grid after this
@@ -1321,6 +1405,9 @@ static void ws_release(mvdb_workspace* ws) {   // device / pinned memory and the
     cudaFree(ws->b_lqmask);
     cudaFree(ws->b_lqptr);
     cudaFree(ws->b_lqwords);
+    cudaFree(ws->sv_surv);
+    cudaFree(ws->sv_best);
+    cudaFree(ws->sv_ctl);
     cudaFree(ws->i8_surv);
     if (ws->i8_ovf_pin) cudaFreeHost(ws->i8_ovf_pin);
     cudaFree(ws->i8_best);
@@ -1571,6 +1658,8 @@ int mvdb_index_set_option(mvdb_index* ix, const char* name, int64_t value) {
         ix->co_max_leaders = int(value);
     } else if (s == "pdl") {
         ix->pdl = value != 0;
+    } else if (s == "survivor_tail") {
+        ix->survivor_tail = value != 0;
     } else if (s == "scan_shadow") {
         if (value < 0 || value > 1) return fail(MVDB_ERR_ARG, "scan_shadow must be 0 (fp32 scan) or 1 (int8 shadow + exact fp32 re-scoring)");
         ix->scan_shadow = int(value);
@@ -2612,6 +2701,7 @@ static int prepare_fused_scan(mvdb_index* ix, mvdb_workspace* ws, int64_t nq, in
     cudaFuncAttributes fa;
     CU_OK(cudaFuncGetAttributes(&fa, xchg_empty_kernel));
     if (i8_eligible(ix, nq, k, p.n)) RC_OK(i8_prepare(ix, ws, p.n, ws->stream));
+    if (ix->survivor_tail && k > 16 && k <= 128 && (ix->ld4 + 31) / 32 <= 8) RC_OK(sv_prepare(ix, ws, (ix->ld4 + 31) / 32, ws->stream));
     return MVDB_OK;
 }
 

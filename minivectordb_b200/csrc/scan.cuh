@@ -61,7 +61,15 @@ struct ScanParams {
     const uint32_t* qmask[8];    // per-query admissible bitmasks (coalesced searches; nullptr = none); multi kernel only
     uint32_t qmask_bytes[8];     // bytes available behind qmask[i]; rows past them are not admissible
     int has_qmask;
-    const unsigned int* run_if;  // not null: the whole launch is a no-op unless *run_if != 0 (fallback behind the int8 mode)
+    const unsigned int* run_if;  // not null: the whole launch is a no-op unless *run_if != 0 (fallback behind the int8 / survivor modes)
+    // survivor mode (scan_q1_kernel<.., kSurv = true>, 16 < k <= 128): no per-warp selects and no merge tree --
+    // a shared threshold (k-th largest of the per-warp best scores, see select.cuh) and ONE global list of the keys
+    // that pass it, sorted by the last CTA
+    uint64_t* surv;              // [surv_cap] keys
+    struct SurvCtl* sctl;
+    unsigned int* best;          // [nbest] ordered images of the per-warp (k <= 32: per-CTA) best scores, zero before launch
+    uint32_t nbest, surv_cap;
+    unsigned int* ovf_host;      // pinned host word raised when the list overflows (the caller re-runs the classic scan), or nullptr
     const struct XchgDev* xchg;  // fused cross-GPU exchange (nullptr = single GPU)
     uint64_t xchg_seq;           // sequence number of this launch (same on every rank, > 0)
 };
@@ -202,6 +210,10 @@ __device__ __forceinline__ void xchg_publish_and_wait(const XchgDev* x, uint64_t
     __syncwarp();
 }
 
+struct SurvCtl {                 // zero before the first launch; every launch leaves it clean
+    unsigned int count, ticket, overflow, last_count;
+};
+
 // shared-memory header (first 1024 bytes)
 struct SmemHeader {
     uint64_t full[16];
@@ -210,6 +222,7 @@ struct SmemHeader {
     int last_flag;
     uint32_t tile_of[16];  // dynamic tile scheduler: tile held by ring stage s (kNoTile = stop)
     uint32_t adm_of[16];   // ... and its admissible byte (mask & live)
+    unsigned int surv_thr, surv_refreshes;   // survivor mode: CTA-wide threshold (ordered image) and how often it was recomputed
 };
 static_assert(sizeof(SmemHeader) <= 1024, "header too large");
 
@@ -629,10 +642,67 @@ __device__ __forceinline__ void scan_producer(const ScanParams& p, SmemHeader* h
 }
 
 // ---------------------------------------------------------------------------
+// Survivor mode tail: the last CTA to finish sorts the survivor list (in the idle ring) and writes (D, I) -- or
+// sends / merges over NVLink exactly as finish_scan does.  Leaves best[], the counters and the tile counter clean.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void finish_survivors(const ScanParams& p, uint8_t* smem_base, SmemHeader* hdr, int cw, int ncw,
+                                                 int lane) {
+    const uint32_t G = gridDim.x;
+    const int tid = cw * kWarp + lane, nthr = ncw * kWarp;
+    __threadfence();
+    named_bar_sync(1, nthr);
+    if (tid == 0) hdr->last_flag = (atomicAdd(&p.sctl->ticket, 1u) == G - 1);
+    named_bar_sync(1, nthr);
+    if (!hdr->last_flag) return;
+    __threadfence();
+    const unsigned int ns = *reinterpret_cast<volatile unsigned int*>(&p.sctl->count);
+    for (uint32_t i = tid; i < p.nbest; i += nthr) p.best[i] = 0u;
+    if (tid == 0) {
+        p.sctl->last_count = ns;
+        p.sctl->count = 0u;
+        p.sctl->ticket = 0u;
+        if (p.tile_ctr) *p.tile_ctr = 0u;
+    }
+    if (ns > p.surv_cap) {   // the classic scan answers instead (conditional launch behind this one, or the host re-runs it)
+        if (tid == 0) {
+            p.sctl->overflow = 1u;
+            if (p.ovf_host) {
+                *reinterpret_cast<volatile unsigned int*>(p.ovf_host) = 1u;
+                __threadfence_system();
+            }
+        }
+        return;
+    }
+    uint64_t* sk = reinterpret_cast<uint64_t*>(smem_base + p.merge_off);
+    uint32_t npad = 64;
+    while (npad < ns) npad <<= 1;
+    for (uint32_t i = tid; i < npad; i += nthr) sk[i] = i < ns ? __ldcg(p.surv + i) : kEmptyKey;
+    named_bar_sync(1, nthr);
+    if (npad <= 256) {
+        if (cw != 0) return;
+        if (npad == 64) warp_sort_buffer<2>(sk, int(ns), lane);
+        else if (npad == 128) warp_sort_buffer<4>(sk, int(ns), lane);
+        else warp_sort_buffer<8>(sk, int(ns), lane);
+    } else {
+        bitonic_sort_desc(sk, int(npad), tid, nthr, [&] { named_bar_sync(1, nthr); });
+        if (cw != 0) return;
+    }
+    __syncwarp();
+    const int cnt = int(min(ns, unsigned(p.k)));
+    if (p.xchg) {
+        xchg_send(p.xchg, p.xchg_seq, 0, sk, cnt, p.k, lane);
+        xchg_publish_and_wait(p.xchg, p.xchg_seq, lane);
+        xchg_merge(p.xchg, p.xchg_seq, 0, sk + p.surv_cap, select_cap(p.k), p.k, p.outD, p.outI, lane);
+    } else {
+        write_results(sk, cnt, p.k, p.outD, p.outI, p.label_offset, lane);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Kernel A: one query, query chunks in registers, D4 = ceil(ld4 / 32) known at
 // compile time.  kTma selects the producer/consumer ring or direct loads.
 // ---------------------------------------------------------------------------
-template <int D4, bool kTma>
+template <int D4, bool kTma, bool kSurv = false>
 __global__ void __launch_bounds__(kTma ? 288 : 256, kTma ? 1 : 2) scan_q1_kernel(const ScanParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem);
@@ -653,6 +723,11 @@ __global__ void __launch_bounds__(kTma ? 288 : 256, kTma ? 1 : 2) scan_q1_kernel
                 mbar_init(&hdr->full[s], 1);
                 mbar_init(&hdr->empty[s], 1);
             }
+            if (kSurv) {
+                hdr->surv_thr = 0u;
+                hdr->surv_refreshes = 0u;
+                if (blockIdx.x == 0) p.sctl->overflow = 0u;   // the previous search's conditional fallback has completed
+            }
             mbar_fence_init();
         }
         __syncthreads();
@@ -672,6 +747,12 @@ __global__ void __launch_bounds__(kTma ? 288 : 256, kTma ? 1 : 2) scan_q1_kernel
     const int my_row = tile_row_of_lane(lane);
     const bool leader = (lane & 3) == 0;
     const int ld4 = p.ld4;
+
+    // survivor mode state: slot of p.best this warp reports to (k <= 32: one per CTA), its best score image so far,
+    // the threshold, and the refresh schedule (after 1, 2, 4, ... 256 tiles, then every 256)
+    const bool slot_per_cta = p.k <= 32;
+    const uint32_t gw = slot_per_cta ? blockIdx.x : blockIdx.x * uint32_t(ncw) + uint32_t(cw);
+    uint32_t my_best = 0u, published = 0u, thr = 0u, done_tiles = 0, next_refresh = 1, seen_refreshes = 0;
 
     const bool dyn = kTma && p.tile_ctr != nullptr;
     const uint32_t n_static = dyn ? p.static_iters : iters;
@@ -727,7 +808,50 @@ __global__ void __launch_bounds__(kTma ? 288 : 256, kTma ? 1 : 2) scan_q1_kernel
         const float score = reduce8(acc, lane);
         const uint32_t row = row0 + my_row;
         const bool ok = leader && row < p.n && ((adm >> my_row) & 1u);
-        if (p.all_ord) {
+        if (kSurv) {
+            // publish this warp's best score, refresh the shared threshold on schedule, THEN test this tile's rows
+            // (so that not even the first tile floods the list) and append the keys that pass
+            const uint32_t o = (ok && score == score) ? max(score_to_ord(score), 1u) : 0u;
+            my_best = max(my_best, o);
+            const uint32_t wb = __reduce_max_sync(0xFFFFFFFFu, my_best);
+            if (wb > published) {
+                published = wb;
+                if (lane == 0) {
+                    if (slot_per_cta) atomicMax(p.best + gw, wb);
+                    else *reinterpret_cast<volatile unsigned int*>(p.best + gw) = wb;
+                }
+            }
+            my_best = wb;
+            ++done_tiles;
+            const unsigned int cta_refreshes = *reinterpret_cast<volatile unsigned int*>(&hdr->surv_refreshes);
+            if (done_tiles >= next_refresh) {
+                next_refresh = done_tiles < 256 ? done_tiles * 2 : done_tiles + 256;
+                if (done_tiles == 1 || cta_refreshes == seen_refreshes) {
+                    uint32_t t = i8_threshold(p.best, p.nbest, p.k, lane);
+                    if (done_tiles == 1)
+                        for (int spin = 0; t == 0u && spin < 6; spin++) {
+                            __nanosleep(500);
+                            t = i8_threshold(p.best, p.nbest, p.k, lane);
+                        }
+                    if (lane == 0) {
+                        atomicMax(&hdr->surv_thr, t);
+                        atomicAdd(&hdr->surv_refreshes, 1u);
+                    }
+                    thr = max(thr, t);
+                }
+                seen_refreshes = *reinterpret_cast<volatile unsigned int*>(&hdr->surv_refreshes);
+            }
+            thr = max(thr, *reinterpret_cast<volatile unsigned int*>(&hdr->surv_thr));
+            const bool pass = o != 0u && o >= thr;
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, pass);
+            if (m) {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(&p.sctl->count, unsigned(__popc(m)));
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                const unsigned pos = base + unsigned(__popc(m & ((1u << lane) - 1u)));
+                if (pass && pos < p.surv_cap) p.surv[pos] = make_key(score, row);
+            }
+        } else if (p.all_ord) {
             if (leader && row < p.n) {
                 uint32_t o = (ok && score == score) ? score_to_ord(score) : 0u;
                 p.all_ord[row] = o;
@@ -735,6 +859,10 @@ __global__ void __launch_bounds__(kTma ? 288 : 256, kTma ? 1 : 2) scan_q1_kernel
         } else {
             sel.push(ok, make_key(score, row), lane);
         }
+    }
+    if (kSurv) {
+        finish_survivors(p, smem, hdr, cw, ncw, lane);
+        return;
     }
     if (p.all_ord) return;
     if (blockIdx.x == 0) trace_stamp(p, 2, cw, lane);

@@ -200,6 +200,46 @@ __device__ __forceinline__ uint64_t warp_extract_topk(uint64_t (&v)[M], int k, i
     return mine;
 }
 
+// ---------------------------------------------------------------------------
+// Shared threshold without a merge (int8 shadow scan, fp32 survivor scan): every warp (or CTA) publishes
+// the ordered image of the best lower bound / score it has seen in one 32-bit word; the k-th largest of
+// those words is a lower bound of the final k-th best score (k distinct rows reach it).
+// ---------------------------------------------------------------------------
+// k-th largest of the 32-bit words spread over the warp (v[i] = word lane + 32 i; 0 = empty), truncated to
+// its top 24 bits (a slightly LOWER value: still a valid lower bound): bitwise bisection, 24 rounds of
+// (compare, warp-wide count).  Returns 0 when fewer than k words are non-zero.
+template <int M>
+__device__ __forceinline__ uint32_t warp_kth_largest_u32(const uint32_t (&v)[M], int k) {
+    uint32_t t = 0;
+#pragma unroll 1
+    for (int bit = 31; bit >= 8; bit--) {
+        const uint32_t cand = t | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < M; i++) c += (v[i] >= cand) ? 1 : 0;
+        c = __reduce_add_sync(0xFFFFFFFFu, c);
+        if (c >= k) t = cand;
+    }
+    return t;
+}
+
+constexpr int kI8BestM = 40;   // up to 1280 consumer warps in a grid
+
+template <int M>
+__device__ __forceinline__ uint32_t i8_threshold_m(const unsigned int* best, uint32_t nbest, int k, int lane) {
+    uint32_t v[M];
+#pragma unroll
+    for (int i = 0; i < M; i++) {
+        const uint32_t idx = uint32_t(lane) + 32u * uint32_t(i);
+        v[i] = (idx < nbest) ? __ldcg(best + idx) : 0u;
+    }
+    return warp_kth_largest_u32<M>(v, k);
+}
+__device__ __forceinline__ uint32_t i8_threshold(const unsigned int* best, uint32_t nbest, int k, int lane) {
+    if (nbest <= 160u) return i8_threshold_m<5>(best, nbest, k, lane);
+    return nbest <= 640u ? i8_threshold_m<20>(best, nbest, k, lane) : i8_threshold_m<kI8BestM>(best, nbest, k, lane);
+}
+
 // Buffer capacity for a given k: room for the kept k plus at least one full
 // warp of fresh candidates, rounded to a power of two for the bitonic network.
 __host__ __device__ __forceinline__ int select_cap(int k) {

@@ -581,3 +581,44 @@ def test_children_may_outlive_their_index(mv):
         eng2.close()                 # a member of a group cannot be destroyed before the group
     grp.close()
     eng2.close()
+
+
+@pytest.mark.parametrize("n,d", [(20_000, 64), (100_000, 384), (60_000, 1000)])
+def test_survivor_tail_is_result_neutral(mv, n, d):
+    """16 < k <= 128: the survivor-list scan (shared threshold, one global list, last-CTA sort) returns exactly
+    what the per-warp-select scan returns -- with filters, tombstones, duplicates (list overflow -> fallback),
+    through the host API and the stream API."""
+    import torch
+    x, q = _data(n, d, 5, seed=71)
+    eng = mv.FlatIPEngine(d)
+    eng.set_option("coalesce", 0)
+    eng.add(x)
+    adm = np.random.default_rng(2).random(n) < 0.3
+    for k in (17, 32, 33, 100, 128):
+        eng.set_option("survivor_tail", 0)
+        ref = [eng.search(q[i:i + 1], k) for i in range(5)] + [eng.search(q[i:i + 1], k, mask=adm) for i in range(5)]
+        eng.set_option("survivor_tail", 1)
+        for rep in range(2):
+            got = [eng.search(q[i:i + 1], k) for i in range(5)] + [eng.search(q[i:i + 1], k, mask=adm) for i in range(5)]
+            for (Dr, Ir), (Dg, Ig) in zip(ref, got):
+                assert np.array_equal(Ir, Ig) and np.array_equal(Dr, Dg), (k, rep)
+        _check(x, q[:1], k, *eng.search(q[:1], k))
+    # overflow: 6000 copies of one row all tie at the top -> the list overflows -> the classic scan answers
+    eng.add(np.repeat(x[7:8], 6000, axis=0))
+    eng.remove_rows(np.arange(0, 2000, 3))
+    ws = eng.workspace()
+    qd = torch.from_numpy(np.ascontiguousarray(x[7:8])).cuda()
+    for k in (20, 100):
+        eng.set_option("survivor_tail", 0)
+        Dr, Ir = eng.search(x[7:8], k)
+        eng.set_option("survivor_tail", 1)
+        Dh, Ih = eng.search(x[7:8], k)                          # host API: re-run after the pinned flag
+        assert np.array_equal(Ir, Ih) and np.array_equal(Dr, Dh)
+        D = torch.empty(1, k, device="cuda")
+        I = torch.empty(1, k, dtype=torch.int64, device="cuda")
+        for _ in range(3):                                      # stream API: conditional launch; state resets itself
+            eng.search_device(ws, qd.data_ptr(), 1, k, D.data_ptr(), I.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            assert np.array_equal(I.cpu().numpy(), Ir) and np.array_equal(D.cpu().numpy(), Dr)
+    ws.close()
+    eng.close()
