@@ -111,7 +111,7 @@ int mvdb_index_reset(mvdb_index* ix);
  *   "gemm_variant"  tile scheme of the tensor-core batch: 0 one CTA per 128x256 tile, 1 CTA pairs
  *                   (cta_group::2), 2 clusters of 2 sharing the row tile by TMA multicast
  *                   (default), 3 clusters of 4; "gemm_l2_hint" 0/1/2 L2 eviction hints (A/B)
- *   "survivor_tail" (default 1) single-query scans with 16 < k <= 128 keep no per-warp top-k lists: a shared
+ *   "survivor_tail" (default 1) single-query scans with 32 < k <= 128 keep no per-warp top-k lists: a shared
  *                   threshold (k-th largest of the per-warp best scores) and one global list of the keys that
  *                   pass it, sorted by the last CTA -- same results, a much shorter serial tail; 0 = the
  *                   per-warp selects + merge tree (also the automatic fallback when the list overflows)
@@ -321,7 +321,8 @@ int mvdb_debug_read_gemm_prof(mvdb_index* ix, uint64_t* out, int ctas);
 
 /* Test hook: counters of the LAST int8 shadow search ("scan_shadow") run on this workspace through
  * mvdb_index_search_device: out4 = {candidates the int8 pass selected, candidates that survived the exact
- * re-scoring, 1 if a list overflowed and the fp32 scan answered instead, 0}. */
+ * re-scoring, bit 0: the int8 lists overflowed / bit 1: the survivor list of the fp32 survivor-tail scan overflowed
+ * (the classic scan answered instead), length of the survivor list of the last survivor-tail scan}. */
 int mvdb_debug_read_shadow_counters(mvdb_workspace* ws, uint32_t* out4);
 
 /* Number of kernel launches issued by this library since load (bench.py's

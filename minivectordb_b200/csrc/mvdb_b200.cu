@@ -319,7 +319,7 @@ struct mvdb_workspace {
     size_t b_lqptr_cap = 0;
     uint32_t* b_lqwords = nullptr;
     size_t b_lqwords_cap = 0;
-    // survivor mode of the fp32 scan (16 < k <= 128)
+    // survivor mode of the fp32 scan (32 < k <= 128)
     uint64_t* sv_surv = nullptr;
     unsigned int* sv_best = nullptr;
     SurvCtl* sv_ctl = nullptr;
@@ -413,7 +413,7 @@ struct mvdb_index {
     uint64_t shadow8_rows = 0;
     std::mutex shadow8_mu;
     int scan_shadow = 0;
-    int survivor_tail = 1;          // 16 < k <= 128 single-query scans: shared threshold + global survivor list (0 = per-warp selects + merge tree)
+    int survivor_tail = 1;          // 32 < k <= 128 single-query scans: shared threshold + global survivor list (0 = per-warp selects + merge tree)
     int* max_norm2_bits = nullptr;  // device: bit pattern of the largest squared row norm stored
     std::atomic<float> max_norm2_host{0.f};  // host copy, refreshed at the end of every add
     // options
@@ -1007,7 +1007,7 @@ static bool i8_eligible(const mvdb_index* ix, int64_t nq, int64_t k, uint32_t n)
     return i8_consumer_warps(ix) != 0;
 }
 
-static constexpr uint32_t kSurvCap = 4096;
+static constexpr uint32_t kSurvCap = 8192;   // = kSelectMax (scan.cuh)
 
 // pinned + mapped word a kernel raises when its candidate / survivor list overflowed (host-buffer callers check it
 // after their synchronise and re-run the query on the classic scan)
@@ -1042,11 +1042,13 @@ static int sv_prepare(mvdb_index* ix, mvdb_workspace* ws, int d4, cudaStream_t s
     return MVDB_OK;
 }
 
-// Survivor mode applies to: one query, 16 < k <= 128, the TMA single-query kernel, enough rows to amortise the
+// Survivor mode applies to: one query, 32 < k <= 128 (below that the per-warp selects are as fast: measured), the TMA
+// single-query kernel, enough rows to amortise the
 // threshold refreshes, and a ring large enough to sort the survivor list in.
 static bool sv_eligible(const mvdb_index* ix, const ScanPlan& plan, const ScanParams& p, int g) {
-    return ix->survivor_tail && g == 1 && plan.tma && plan.q1 && p.k > 16 && p.k <= 128 && p.n >= 16384 &&
-           size_t(p.merge_bytes) >= (size_t(kSurvCap) + 256) * 8 && !p.all_ord;
+    // (the grid must have more CTAs than k: the threshold is the k-th largest of the per-CTA bests)
+    return ix->survivor_tail && g == 1 && plan.tma && plan.q1 && p.k > 32 && p.k <= 128 && p.n >= 16384 && plan.grid > p.k &&
+           size_t(p.merge_bytes) >= (size_t(kSurvCap) + 512) * 8 && !p.all_ord;
 }
 
 // everything the int8 mode sets up lazily (shadow rows, scratch, shared-memory opt-in): all of it may
@@ -1278,7 +1280,7 @@ static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, in
             p.pdl_early = 0;
             const unsigned int* launch_if = run_if;
             if (!run_if && !tl_force_scan && sv_eligible(ix, plan, p, g)) {
-                // 16 < k <= 128: shared threshold + global survivor list, the last CTA sorts; the classic kernel is
+                // 32 < k <= 128: shared threshold + global survivor list, the last CTA sorts; the classic kernel is
                 // only its overflow fallback (conditional launch, or the host caller re-runs the query)
                 const int d4 = (ix->ld4 + 31) / 32;
                 RC_OK(sv_prepare(ix, ws, d4, stream));
@@ -1287,7 +1289,7 @@ static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, in
                 sp.sctl = ws->sv_ctl;
                 sp.best = ws->sv_best;
                 sp.surv_cap = kSurvCap;
-                sp.nbest = p.k <= 32 ? uint32_t(plan.grid) : uint32_t(plan.grid) * uint32_t(plan.threads / 32 - 1);
+                sp.nbest = uint32_t(plan.grid);   // one slot per CTA
                 sp.ovf_host = (tl_host_checks_i8 && !xch) ? ws->i8_ovf_dev : nullptr;
                 if (sp.nbest <= uint32_t(kI8BestM) * 32) {
                     q1_survivor_kernel(d4)<<<plan.grid, plan.threads, plan.smem, stream>>>(sp);
@@ -2701,7 +2703,7 @@ static int prepare_fused_scan(mvdb_index* ix, mvdb_workspace* ws, int64_t nq, in
     cudaFuncAttributes fa;
     CU_OK(cudaFuncGetAttributes(&fa, xchg_empty_kernel));
     if (i8_eligible(ix, nq, k, p.n)) RC_OK(i8_prepare(ix, ws, p.n, ws->stream));
-    if (ix->survivor_tail && k > 16 && k <= 128 && (ix->ld4 + 31) / 32 <= 8) RC_OK(sv_prepare(ix, ws, (ix->ld4 + 31) / 32, ws->stream));
+    if (ix->survivor_tail && k > 32 && k <= 128 && (ix->ld4 + 31) / 32 <= 8) RC_OK(sv_prepare(ix, ws, (ix->ld4 + 31) / 32, ws->stream));
     return MVDB_OK;
 }
 
@@ -2945,15 +2947,24 @@ int mvdb_debug_read_gemm_prof(mvdb_index* ix, uint64_t* out, int ctas) {
 
 int mvdb_debug_read_shadow_counters(mvdb_workspace* ws, uint32_t* out4) {
     if (!ws || !out4) return fail(MVDB_ERR_ARG, "null argument");
-    if (!ws->i8_ctl) return fail(MVDB_ERR_STATE, "this workspace has not run an int8 shadow search");
+    if (!ws->ix) return fail(MVDB_ERR_STATE, "the workspace's index has been destroyed");
+    if (!ws->i8_ctl && !ws->sv_ctl) return fail(MVDB_ERR_STATE, "this workspace has run neither an int8 shadow nor a survivor-list search");
     DeviceGuard guard(ws->ix->device);
     CU_OK(cudaDeviceSynchronize());
-    I8Ctl c;
-    CU_OK(cudaMemcpy(&c, ws->i8_ctl, sizeof c, cudaMemcpyDeviceToHost));
-    out4[0] = c.last_cand;
-    out4[1] = c.last_surv;
-    out4[2] = c.overflow;
-    out4[3] = 0;
+    out4[0] = out4[1] = out4[2] = out4[3] = 0;
+    if (ws->i8_ctl) {
+        I8Ctl c;
+        CU_OK(cudaMemcpy(&c, ws->i8_ctl, sizeof c, cudaMemcpyDeviceToHost));
+        out4[0] = c.last_cand;
+        out4[1] = c.last_surv;
+        out4[2] = c.overflow;
+    }
+    if (ws->sv_ctl) {
+        SurvCtl c;
+        CU_OK(cudaMemcpy(&c, ws->sv_ctl, sizeof c, cudaMemcpyDeviceToHost));
+        out4[3] = c.last_count;
+        out4[2] |= c.overflow << 1;
+    }
     return MVDB_OK;
 }
 

@@ -62,7 +62,7 @@ struct ScanParams {
     uint32_t qmask_bytes[8];     // bytes available behind qmask[i]; rows past them are not admissible
     int has_qmask;
     const unsigned int* run_if;  // not null: the whole launch is a no-op unless *run_if != 0 (fallback behind the int8 / survivor modes)
-    // survivor mode (scan_q1_kernel<.., kSurv = true>, 16 < k <= 128): no per-warp selects and no merge tree --
+    // survivor mode (scan_q1_kernel<.., kSurv = true>, 32 < k <= 128): no per-warp selects and no merge tree --
     // a shared threshold (k-th largest of the per-warp best scores, see select.cuh) and ONE global list of the keys
     // that pass it, sorted by the last CTA
     uint64_t* surv;              // [surv_cap] keys
@@ -642,6 +642,88 @@ __device__ __forceinline__ void scan_producer(const ScanParams& p, SmemHeader* h
 }
 
 // ---------------------------------------------------------------------------
+// Best k of the `ns` unsorted keys in sk[0, ns) (shared memory), by ALL `nthr` consumer threads of the CTA:
+// a 32-round block-wide bisection finds the k-th largest score image (every thread keeps the high words of
+// its <= 32 keys in registers; one warp redux + one shared atomic + one barrier per round), the keys at or
+// above it (k plus ties) are gathered behind the list and warp 0 sorts those few in registers.  Replaces a
+// full bitonic sort of 1-4 k keys (14-30 us in the trace) by ~5 us.  On return warp 0 (cw == 0) holds the
+// sorted list at the returned pointer, every other warp gets nullptr and may leave.  ns <= kSelectMax; keys beyond
+// the first 32 per thread are counted from shared memory (only very long lists get there).
+// Scratch: 4 words of hdr->cnts, sk[kSelectMax ...) for the gathered keys.
+// ---------------------------------------------------------------------------
+constexpr uint32_t kSelectMax = 8192;
+__device__ __forceinline__ uint64_t* block_select_topk(uint64_t* sk, unsigned int ns, int k, SmemHeader* hdr, int tid, int nthr,
+                                                       int cw, int lane, int* out_cnt) {
+    uint32_t npad = 64;
+    while (npad < ns) npad <<= 1;
+    if (npad <= 256) {   // short list: one register sort
+        if (cw != 0) return nullptr;
+        for (uint32_t i = ns + lane; i < npad; i += kWarp) sk[i] = kEmptyKey;
+        __syncwarp();
+        if (npad == 64) warp_sort_buffer<2>(sk, int(ns), lane);
+        else if (npad == 128) warp_sort_buffer<4>(sk, int(ns), lane);
+        else warp_sort_buffer<8>(sk, int(ns), lane);
+        __syncwarp();
+        *out_cnt = int(min(ns, unsigned(k)));
+        return sk;
+    }
+    uint32_t hi[32];
+#pragma unroll
+    for (int u = 0; u < 32; u++) {
+        const uint32_t i = uint32_t(tid) + uint32_t(u) * uint32_t(nthr);
+        hi[u] = (i < ns) ? uint32_t(sk[i] >> 32) : 0u;
+    }
+    volatile int* cnt = hdr->cnts;   // cnts[0..2]: rotating counters, cnts[3]: gather cursor
+    if (tid == 0) cnt[0] = cnt[1] = cnt[2] = cnt[3] = 0;
+    named_bar_sync(1, nthr);
+    uint32_t t = 0;
+    int above = 0;   // keys with image >= t
+#pragma unroll 1
+    for (int r = 0; r < 32; r++) {
+        const uint32_t cand = t | (1u << (31 - r));
+        int c = 0;
+#pragma unroll
+        for (int u = 0; u < 32; u++) c += (hi[u] >= cand) ? 1 : 0;
+        for (uint32_t i = uint32_t(tid) + 32u * uint32_t(nthr); i < ns; i += uint32_t(nthr)) c += (uint32_t(sk[i] >> 32) >= cand) ? 1 : 0;
+        c = __reduce_add_sync(0xFFFFFFFFu, c);
+        if (lane == 0 && c) atomicAdd(&hdr->cnts[r % 3], c);
+        named_bar_sync(1, nthr);
+        const int total = cnt[r % 3];
+        if (tid == 0) cnt[(r + 2) % 3] = 0;   // used next in round r + 2: everybody is past its last read (round r - 1)
+        if (total >= k) {
+            t = cand;
+            above = total;
+        }
+    }
+    if (t == 0u) above = int(ns);   // fewer than k keys: everything counts
+    if (above > 256) {   // a crowd of exact score ties: sort everything (rare)
+        for (uint32_t i = ns + tid; i < npad; i += nthr) sk[i] = kEmptyKey;
+        named_bar_sync(1, nthr);
+        bitonic_sort_desc(sk, int(npad), tid, nthr, [&] { named_bar_sync(1, nthr); });
+        if (cw != 0) return nullptr;
+        *out_cnt = int(min(ns, unsigned(k)));
+        return sk;
+    }
+    uint64_t* out = sk + kSelectMax;
+#pragma unroll
+    for (int u = 0; u < 32; u++) {
+        const uint32_t i = uint32_t(tid) + uint32_t(u) * uint32_t(nthr);
+        if (i < ns && hi[u] >= t) out[atomicAdd(&hdr->cnts[3], 1)] = sk[i];
+    }
+    for (uint32_t i = uint32_t(tid) + 32u * uint32_t(nthr); i < ns; i += uint32_t(nthr))
+        if (uint32_t(sk[i] >> 32) >= t) out[atomicAdd(&hdr->cnts[3], 1)] = sk[i];
+    named_bar_sync(1, nthr);
+    if (cw != 0) return nullptr;
+    const int m = cnt[3];
+    if (m <= 64) warp_sort_buffer<2>(out, m, lane);
+    else if (m <= 128) warp_sort_buffer<4>(out, m, lane);
+    else warp_sort_buffer<8>(out, m, lane);
+    __syncwarp();
+    *out_cnt = min(m, k);
+    return out;
+}
+
+// ---------------------------------------------------------------------------
 // Survivor mode tail: the last CTA to finish sorts the survivor list (in the idle ring) and writes (D, I) -- or
 // sends / merges over NVLink exactly as finish_scan does.  Leaves best[], the counters and the tile counter clean.
 // ---------------------------------------------------------------------------
@@ -653,7 +735,9 @@ __device__ __forceinline__ void finish_survivors(const ScanParams& p, uint8_t* s
     named_bar_sync(1, nthr);
     if (tid == 0) hdr->last_flag = (atomicAdd(&p.sctl->ticket, 1u) == G - 1);
     named_bar_sync(1, nthr);
+    if (blockIdx.x == 0) trace_stamp(p, 6, cw, lane);
     if (!hdr->last_flag) return;
+    trace_stamp(p, 8, cw, lane);
     __threadfence();
     const unsigned int ns = *reinterpret_cast<volatile unsigned int*>(&p.sctl->count);
     for (uint32_t i = tid; i < p.nbest; i += nthr) p.best[i] = 0u;
@@ -674,28 +758,21 @@ __device__ __forceinline__ void finish_survivors(const ScanParams& p, uint8_t* s
         return;
     }
     uint64_t* sk = reinterpret_cast<uint64_t*>(smem_base + p.merge_off);
-    uint32_t npad = 64;
-    while (npad < ns) npad <<= 1;
-    for (uint32_t i = tid; i < npad; i += nthr) sk[i] = i < ns ? __ldcg(p.surv + i) : kEmptyKey;
+    for (uint32_t i = tid; i < ns; i += nthr) sk[i] = __ldcg(p.surv + i);
     named_bar_sync(1, nthr);
-    if (npad <= 256) {
-        if (cw != 0) return;
-        if (npad == 64) warp_sort_buffer<2>(sk, int(ns), lane);
-        else if (npad == 128) warp_sort_buffer<4>(sk, int(ns), lane);
-        else warp_sort_buffer<8>(sk, int(ns), lane);
-    } else {
-        bitonic_sort_desc(sk, int(npad), tid, nthr, [&] { named_bar_sync(1, nthr); });
-        if (cw != 0) return;
-    }
-    __syncwarp();
-    const int cnt = int(min(ns, unsigned(p.k)));
+    trace_stamp(p, 9, cw, lane);
+    int cnt = 0;
+    uint64_t* fin = block_select_topk(sk, ns, p.k, hdr, tid, nthr, cw, lane, &cnt);
+    if (!fin) return;
+    trace_stamp(p, 10, cw, lane);
     if (p.xchg) {
-        xchg_send(p.xchg, p.xchg_seq, 0, sk, cnt, p.k, lane);
+        xchg_send(p.xchg, p.xchg_seq, 0, fin, cnt, p.k, lane);
         xchg_publish_and_wait(p.xchg, p.xchg_seq, lane);
-        xchg_merge(p.xchg, p.xchg_seq, 0, sk + p.surv_cap, select_cap(p.k), p.k, p.outD, p.outI, lane);
+        xchg_merge(p.xchg, p.xchg_seq, 0, fin == sk ? sk + kSelectMax : sk, select_cap(p.k), p.k, p.outD, p.outI, lane);
     } else {
-        write_results(sk, cnt, p.k, p.outD, p.outI, p.label_offset, lane);
+        write_results(fin, cnt, p.k, p.outD, p.outI, p.label_offset, lane);
     }
+    trace_stamp(p, 13, cw, lane);
 }
 
 // ---------------------------------------------------------------------------
@@ -750,9 +827,12 @@ __global__ void __launch_bounds__(kTma ? 288 : 256, kTma ? 1 : 2) scan_q1_kernel
 
     // survivor mode state: slot of p.best this warp reports to (k <= 32: one per CTA), its best score image so far,
     // the threshold, and the refresh schedule (after 1, 2, 4, ... 256 tiles, then every 256)
-    const bool slot_per_cta = p.k <= 32;
-    const uint32_t gw = slot_per_cta ? blockIdx.x : blockIdx.x * uint32_t(ncw) + uint32_t(cw);
-    uint32_t my_best = 0u, published = 0u, thr = 0u, done_tiles = 0, next_refresh = 1, seen_refreshes = 0;
+    // One slot per CTA: 148 words make the threshold cheap to recompute (per-warp slots were measured: the k = 100
+    // search at 1 M x 384 took 278 us instead of 241), and the k-th largest of 148 CTA-bests is still about the
+    // 1.5 k ... 2.5 k-th best row -- the list holds a few thousand keys at most (cap 8192).
+    const bool slot_per_cta = true;
+    const uint32_t gw = blockIdx.x;
+    uint32_t my_best = 0u, published = 0u, thr = 0u, done_tiles = 0, next_refresh = 2, seen_refreshes = 0;
 
     const bool dyn = kTma && p.tile_ctr != nullptr;
     const uint32_t n_static = dyn ? p.static_iters : iters;
@@ -823,16 +903,27 @@ __global__ void __launch_bounds__(kTma ? 288 : 256, kTma ? 1 : 2) scan_q1_kernel
             }
             my_best = wb;
             ++done_tiles;
-            const unsigned int cta_refreshes = *reinterpret_cast<volatile unsigned int*>(&hdr->surv_refreshes);
-            if (done_tiles >= next_refresh) {
-                next_refresh = done_tiles < 256 ? done_tiles * 2 : done_tiles + 256;
-                if (done_tiles == 1 || cta_refreshes == seen_refreshes) {
+            if (done_tiles == 1) {
+                // the first threshold: warp 0 of the CTA computes it as soon as k CTAs have reported their first tile,
+                // the other warps wait on shared memory (cheap) -- nobody tests a row against "no threshold"
+                if (cw == 0) {
                     uint32_t t = i8_threshold(p.best, p.nbest, p.k, lane);
-                    if (done_tiles == 1)
-                        for (int spin = 0; t == 0u && spin < 6; spin++) {
-                            __nanosleep(500);
-                            t = i8_threshold(p.best, p.nbest, p.k, lane);
-                        }
+                    for (int spin = 0; t == 0u && spin < 40; spin++) {
+                        __nanosleep(200);
+                        t = i8_threshold(p.best, p.nbest, p.k, lane);
+                    }
+                    if (lane == 0) {
+                        atomicMax(&hdr->surv_thr, max(t, 1u));
+                        atomicAdd(&hdr->surv_refreshes, 1u);
+                    }
+                } else {
+                    for (int spin = 0; *reinterpret_cast<volatile unsigned int*>(&hdr->surv_thr) == 0u && spin < 400; spin++) __nanosleep(100);
+                }
+                seen_refreshes = *reinterpret_cast<volatile unsigned int*>(&hdr->surv_refreshes);
+            } else if (done_tiles >= next_refresh) {
+                next_refresh = done_tiles < 256 ? done_tiles + max(1u, done_tiles / 2) : done_tiles + 256;
+                if (*reinterpret_cast<volatile unsigned int*>(&hdr->surv_refreshes) == seen_refreshes) {
+                    const uint32_t t = i8_threshold(p.best, p.nbest, p.k, lane);
                     if (lane == 0) {
                         atomicMax(&hdr->surv_thr, t);
                         atomicAdd(&hdr->surv_refreshes, 1u);
@@ -861,6 +952,7 @@ __global__ void __launch_bounds__(kTma ? 288 : 256, kTma ? 1 : 2) scan_q1_kernel
         }
     }
     if (kSurv) {
+        if (blockIdx.x == 0) trace_stamp(p, 2, cw, lane);
         finish_survivors(p, smem, hdr, cw, ncw, lane);
         return;
     }

@@ -372,7 +372,13 @@ class Workspace:
         """(candidates, survivors, overflowed) of the last int8 shadow search run on this workspace."""
         out = (ctypes.c_uint32 * 4)()
         N.check(N.lib().mvdb_debug_read_shadow_counters(self._h, out))
-        return int(out[0]), int(out[1]), bool(out[2])
+        return int(out[0]), int(out[1]), bool(out[2] & 1)
+
+    def survivor_counters(self):
+        """(length of the survivor list, overflowed) of the last survivor-tail scan (fp32, 32 < k <= 128) on this workspace."""
+        out = (ctypes.c_uint32 * 4)()
+        N.check(N.lib().mvdb_debug_read_shadow_counters(self._h, out))
+        return int(out[3]), bool(out[2] & 2)
 
     def close(self):
         if self._h is not None and self._h.value:

@@ -585,7 +585,7 @@ def test_children_may_outlive_their_index(mv):
 
 @pytest.mark.parametrize("n,d", [(20_000, 64), (100_000, 384), (60_000, 1000)])
 def test_survivor_tail_is_result_neutral(mv, n, d):
-    """16 < k <= 128: the survivor-list scan (shared threshold, one global list, last-CTA sort) returns exactly
+    """32 < k <= 128: the survivor-list scan (shared threshold, one global list, last-CTA sort) returns exactly
     what the per-warp-select scan returns -- with filters, tombstones, duplicates (list overflow -> fallback),
     through the host API and the stream API."""
     import torch
@@ -603,8 +603,15 @@ def test_survivor_tail_is_result_neutral(mv, n, d):
             for (Dr, Ir), (Dg, Ig) in zip(ref, got):
                 assert np.array_equal(Ir, Ig) and np.array_equal(Dr, Dg), (k, rep)
         _check(x, q[:1], k, *eng.search(q[:1], k))
-    # overflow: 6000 copies of one row all tie at the top -> the list overflows -> the classic scan answers
-    eng.add(np.repeat(x[7:8], 6000, axis=0))
+    # a crowd of exact ties: 3000 copies of one row all tie at the top (the tail's selection falls back to a full sort) ...
+    eng.add(np.repeat(x[3:4], 3000, axis=0))
+    eng.set_option("survivor_tail", 0)
+    Dr, Ir = eng.search(x[3:4], 100)
+    eng.set_option("survivor_tail", 1)
+    Dg, Ig = eng.search(x[3:4], 100)
+    assert np.array_equal(Ir, Ig) and np.array_equal(Dr, Dg)
+    # ... and overflow: 9000 copies -> the list overflows -> the classic scan answers
+    eng.add(np.repeat(x[7:8], 9000, axis=0))
     eng.remove_rows(np.arange(0, 2000, 3))
     ws = eng.workspace()
     qd = torch.from_numpy(np.ascontiguousarray(x[7:8])).cuda()
