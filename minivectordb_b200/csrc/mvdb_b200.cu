@@ -1122,7 +1122,7 @@ static int run_i8(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, int64_
     p.nbest = k <= 32 ? uint32_t(grid) : uint32_t(grid) * uint32_t(ncw);
     if (p.nbest > uint32_t(kI8BestM) * 32) return fail(MVDB_ERR_STATE, "int8 scan: too many consumer warps for the threshold table");
     // the idle ring doubles as the tail's scratch: 4096 survivor keys + the exchange merge's select buffer
-    const size_t smem = std::max(size_t(p.stage_off) + size_t(stages) * p.stage_bytes, size_t(p.stage_off) + size_t(kI8SurvCap) * 8 + 256 * 8);
+    const size_t smem = std::max(size_t(p.stage_off) + size_t(stages) * p.stage_bytes, size_t(p.stage_off) + (size_t(kSelectMax) + 512) * 8);
     scan_i8_kernel<<<grid, 32 * (1 + ncw), smem, stream>>>(p);
     LAUNCHED();
     CU_OK(cudaGetLastError());

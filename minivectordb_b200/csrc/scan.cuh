@@ -649,10 +649,10 @@ __device__ __forceinline__ void scan_producer(const ScanParams& p, SmemHeader* h
 // full bitonic sort of 1-4 k keys (14-30 us in the trace) by ~5 us.  On return warp 0 (cw == 0) holds the
 // sorted list at the returned pointer, every other warp gets nullptr and may leave.  ns <= kSelectMax; keys beyond
 // the first 32 per thread are counted from shared memory (only very long lists get there).
-// Scratch: 4 words of hdr->cnts, sk[kSelectMax ...) for the gathered keys.
+// Scratch: cnts4 (4 words of shared memory), sk[kSelectMax ...) for the gathered keys.
 // ---------------------------------------------------------------------------
 constexpr uint32_t kSelectMax = 8192;
-__device__ __forceinline__ uint64_t* block_select_topk(uint64_t* sk, unsigned int ns, int k, SmemHeader* hdr, int tid, int nthr,
+__device__ __forceinline__ uint64_t* block_select_topk(uint64_t* sk, unsigned int ns, int k, int* cnts4, int tid, int nthr,
                                                        int cw, int lane, int* out_cnt) {
     uint32_t npad = 64;
     while (npad < ns) npad <<= 1;
@@ -673,7 +673,7 @@ __device__ __forceinline__ uint64_t* block_select_topk(uint64_t* sk, unsigned in
         const uint32_t i = uint32_t(tid) + uint32_t(u) * uint32_t(nthr);
         hi[u] = (i < ns) ? uint32_t(sk[i] >> 32) : 0u;
     }
-    volatile int* cnt = hdr->cnts;   // cnts[0..2]: rotating counters, cnts[3]: gather cursor
+    volatile int* cnt = cnts4;   // [0..2]: rotating counters, [3]: gather cursor
     if (tid == 0) cnt[0] = cnt[1] = cnt[2] = cnt[3] = 0;
     named_bar_sync(1, nthr);
     uint32_t t = 0;
@@ -686,7 +686,7 @@ __device__ __forceinline__ uint64_t* block_select_topk(uint64_t* sk, unsigned in
         for (int u = 0; u < 32; u++) c += (hi[u] >= cand) ? 1 : 0;
         for (uint32_t i = uint32_t(tid) + 32u * uint32_t(nthr); i < ns; i += uint32_t(nthr)) c += (uint32_t(sk[i] >> 32) >= cand) ? 1 : 0;
         c = __reduce_add_sync(0xFFFFFFFFu, c);
-        if (lane == 0 && c) atomicAdd(&hdr->cnts[r % 3], c);
+        if (lane == 0 && c) atomicAdd(&cnts4[r % 3], c);
         named_bar_sync(1, nthr);
         const int total = cnt[r % 3];
         if (tid == 0) cnt[(r + 2) % 3] = 0;   // used next in round r + 2: everybody is past its last read (round r - 1)
@@ -708,10 +708,10 @@ __device__ __forceinline__ uint64_t* block_select_topk(uint64_t* sk, unsigned in
 #pragma unroll
     for (int u = 0; u < 32; u++) {
         const uint32_t i = uint32_t(tid) + uint32_t(u) * uint32_t(nthr);
-        if (i < ns && hi[u] >= t) out[atomicAdd(&hdr->cnts[3], 1)] = sk[i];
+        if (i < ns && hi[u] >= t) out[atomicAdd(&cnts4[3], 1)] = sk[i];
     }
     for (uint32_t i = uint32_t(tid) + 32u * uint32_t(nthr); i < ns; i += uint32_t(nthr))
-        if (uint32_t(sk[i] >> 32) >= t) out[atomicAdd(&hdr->cnts[3], 1)] = sk[i];
+        if (uint32_t(sk[i] >> 32) >= t) out[atomicAdd(&cnts4[3], 1)] = sk[i];
     named_bar_sync(1, nthr);
     if (cw != 0) return nullptr;
     const int m = cnt[3];
@@ -762,7 +762,7 @@ __device__ __forceinline__ void finish_survivors(const ScanParams& p, uint8_t* s
     named_bar_sync(1, nthr);
     trace_stamp(p, 9, cw, lane);
     int cnt = 0;
-    uint64_t* fin = block_select_topk(sk, ns, p.k, hdr, tid, nthr, cw, lane, &cnt);
+    uint64_t* fin = block_select_topk(sk, ns, p.k, hdr->cnts, tid, nthr, cw, lane, &cnt);
     if (!fin) return;
     trace_stamp(p, 10, cw, lane);
     if (p.xchg) {

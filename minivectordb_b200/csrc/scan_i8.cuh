@@ -174,6 +174,7 @@ struct I8Header {
     unsigned int thr;       // CTA-wide copy of the threshold (ordered image), only ever raised
     unsigned int refreshes; // how many times any warp of the CTA has recomputed it
     int last_flag;
+    int cnts4[4];           // scratch of block_select_topk (tail)
     uint32_t tile_of[16];   // counter-claimed tiles: tile held by ring stage s (kNoTile = stop) ...
     uint32_t adm_of[16];    // ... and its admissible word (mask & live)
 };
@@ -508,39 +509,20 @@ __global__ void __launch_bounds__(288, 1) scan_i8_kernel(const I8Params p) {
         return;
     }
     uint64_t* sk = reinterpret_cast<uint64_t*>(smem + p.stage_off);   // the ring is idle now
-    uint32_t npad = 64;
-    while (npad < ns) npad <<= 1;
-    for (uint32_t i = tid; i < npad; i += nthr) sk[i] = i < ns ? __ldcg(p.surv + i) : kEmptyKey;
+    for (uint32_t i = tid; i < ns; i += nthr) sk[i] = __ldcg(p.surv + i);
     named_bar_sync(1, nthr);
-    // from here on one warp is enough unless the list is long; the other warps leave (no barrier is executed
-    // on one side of a warp-level branch only)
-    if (npad <= 256) {
-        if (cw != 0) return;
-        if (npad == 64) warp_sort_buffer<2>(sk, int(ns), lane);
-        else if (npad == 128) warp_sort_buffer<4>(sk, int(ns), lane);
-        else warp_sort_buffer<8>(sk, int(ns), lane);
-    } else {
-        bitonic_sort_desc(sk, int(npad), tid, nthr, [&] { named_bar_sync(1, nthr); });
-        if (cw != 0) return;
-    }
-    __syncwarp();
+    // the k best of the survivors: register sort of a short list, block-wide k-th-element selection of a long one
+    int cnt = 0;
+    uint64_t* fin = block_select_topk(sk, ns, p.k, hdr->cnts4, tid, nthr, cw, lane, &cnt);
+    if (!fin) return;
     if (p.xchg) {
         // sharded search: same protocol as the fp32 scan's tail (scan.cuh finish_scan) -- send, publish, wait, merge
-        xchg_send(p.xchg, p.xchg_seq, 0, sk, int(min(ns, unsigned(p.k))), p.k, lane);
+        xchg_send(p.xchg, p.xchg_seq, 0, fin, cnt, p.k, lane);
         xchg_publish_and_wait(p.xchg, p.xchg_seq, lane);
-        xchg_merge(p.xchg, p.xchg_seq, 0, sk + 4096, select_cap(p.k), p.k, p.outD, p.outI, lane);
+        xchg_merge(p.xchg, p.xchg_seq, 0, fin == sk ? sk + kSelectMax : sk, select_cap(p.k), p.k, p.outD, p.outI, lane);
         return;
     }
-    for (int i = lane; i < p.k; i += kWarp) {
-        const uint64_t key = (unsigned(i) < ns) ? sk[i] : kEmptyKey;
-        if (key == kEmptyKey) {
-            p.outD[i] = -FLT_MAX;
-            p.outI[i] = -1;
-        } else {
-            p.outD[i] = key_score(key);
-            p.outI[i] = int64_t(key_row(key)) + p.label_offset;
-        }
-    }
+    write_results(fin, cnt, p.k, p.outD, p.outI, p.label_offset, lane);
 }
 
 }  // namespace mvdb
