@@ -81,6 +81,13 @@ int mvdb_index_reset(mvdb_index* ix);
  *   "scan_variant"  MVDB_SCAN_*          "fused_k_max"  largest k served by the fused select
  *   "grid_ctas"     CTAs of the scan kernel (0 = one per SM)
  *   "consumer_warps" consumer warps per CTA of the TMA scan (0 = auto)
+ *   "host_path"     (default 3) bit set for single-query searches with HOST buffers (mvdb_index_search,
+ *                   _search_with_mask; k <= fused_k_max): 1 = the kernels write the k results straight
+ *                   into pinned host memory (no device-to-host copy), 2 = the query and a per-call filter
+ *                   are pulled from pinned host memory by a small grid that the scan is launched behind as
+ *                   a programmatic dependent (the scan's start-up and ring fill overlap the PCIe round
+ *                   trip; no host-to-device copy).  0 = cudaMemcpyAsync both ways.  Results are identical
+ *                   for every value.
  *   "pdl"           (default 0) launch the scans of mvdb_index_search_device / _search_exchange
  *                   with programmatic stream serialization: searches enqueued back to back on
  *                   one stream overlap the serial tail of one (last-CTA merge, cross-GPU

@@ -7,6 +7,26 @@
 namespace mvdb {
 
 // ---------------------------------------------------------------------------
+// Host-buffer searches: the query (and a per-call filter) are staged in pinned host memory and PULLED into device
+// memory by this small grid instead of a copy-engine transfer.  The scan that follows is launched as a programmatic
+// dependent (this grid triggers it at entry), so its start-up and ring fill overlap the PCIe round trip and only its
+// first read of the query waits (ScanParams::dep_inputs); a copy-engine transfer costs ~8 us before the scan may even
+// start.  Reads are volatile (system scope): the host rewrites the buffer between launches.
+// (Measured and dropped: launching this grid BEFORE the host has copied the filter into the pinned buffer, with a
+// sequence word the grid waits for.  It was slower -- 266 vs 247 us at 1 M x 384 -- and any allocating CUDA call of
+// another host thread could stall behind the waiting grid while the waiting grid's own host thread queued behind
+// that call.)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pull_stage_kernel(const uint4* src, uint4* __restrict__ dst, uint32_t nvec) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) {
+        uint4 v;
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src + i) : "memory");
+        dst[i] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // K1 ingest: one warp per row; optional faiss.normalize_L2 semantics
 // (ref vector_database.py:45 -- nr = sum x^2 in fp32, scale by
 // (float)(1.0/sqrtf(nr)) when nr > 0); the row is written with zero padding

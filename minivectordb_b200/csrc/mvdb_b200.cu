@@ -45,6 +45,7 @@ static thread_local std::string g_err;
 static thread_local bool tl_allow_pdl = false;    // set by the device-buffer entry points (option "pdl")
 static thread_local bool tl_force_scan = false;   // overflow fallback of the batched path: stay on the fp32 scan
 static thread_local bool tl_host_checks_i8 = false;   // the caller synchronises and re-runs an overflowed int8 search itself
+static thread_local bool tl_stage_dep = false;    // host path: the next single-query scan launch depends programmatically on the staging pull
 static std::atomic<uint64_t> g_launches{0};
 
 static int fail(int code, const char* fmt, ...) {
@@ -426,6 +427,8 @@ struct mvdb_index {
     int gemm_debug = 0;            // GemmParams::debug experiments (results are garbage when non-zero)
     unsigned long long* gemm_prof_dev = nullptr;   // debug wait-cycle counters of the GEMM kernels (option "gemm_prof"), [256][8]
     int pdl = 0;                   // search_device: programmatic dependent launch of back-to-back scans (opt-in)
+    int host_path = 3;             // host-buffer single queries: 1 results written straight to pinned host memory, 2 inputs
+                                   // pulled by a grid the scan depends on programmatically
     int dyn_tiles = 15;            // % of the tiles the TMA scan claims from a global counter (rest: static round-robin)
     int l2_pin_mb = 0;             // head of the matrix kept L2-resident across scans (evict_last), MB
     int gemm_variant = 2;          // 0: one CTA per 128x256 tile; 1: CTA pairs (cta_group::2), 256x256 tiles;
@@ -1009,6 +1012,23 @@ static bool i8_eligible(const mvdb_index* ix, int64_t nq, int64_t k, uint32_t n)
 
 static constexpr uint32_t kSurvCap = 8192;   // = kSelectMax (scan.cuh)
 
+// Launch with the programmatic-stream-serialisation attribute: the grid may start while its predecessor on the stream
+// still runs; the kernel itself waits (griddepcontrol.wait) before it touches what the predecessor produces.
+template <class P>
+static cudaError_t launch_dependent(void (*fn)(P), int grid, int threads, size_t smem, cudaStream_t stream, const P& p) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(grid));
+    cfg.blockDim = dim3(unsigned(threads));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, fn, p);
+}
+
 // pinned + mapped word a kernel raises when its candidate / survivor list overflowed (host-buffer callers check it
 // after their synchronise and re-run the query on the classic scan)
 static int ws_overflow_flag(mvdb_workspace* ws) {
@@ -1123,7 +1143,13 @@ static int run_i8(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, int64_
     if (p.nbest > uint32_t(kI8BestM) * 32) return fail(MVDB_ERR_STATE, "int8 scan: too many consumer warps for the threshold table");
     // the idle ring doubles as the tail's scratch: 4096 survivor keys + the exchange merge's select buffer
     const size_t smem = std::max(size_t(p.stage_off) + size_t(stages) * p.stage_bytes, size_t(p.stage_off) + (size_t(kSelectMax) + 512) * 8);
-    scan_i8_kernel<<<grid, 32 * (1 + ncw), smem, stream>>>(p);
+    if (tl_stage_dep) {   // host path: start under the staging pull
+        tl_stage_dep = false;
+        p.dep_inputs = 1u;
+        CU_OK(launch_dependent(scan_i8_kernel, grid, 32 * (1 + ncw), smem, stream, p));
+    } else {
+        scan_i8_kernel<<<grid, 32 * (1 + ncw), smem, stream>>>(p);
+    }
     LAUNCHED();
     CU_OK(cudaGetLastError());
     *run_if = (tl_host_checks_i8 && !xch) ? nullptr : &ws->i8_ctl->overflow;
@@ -1292,7 +1318,13 @@ static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, in
                 sp.nbest = uint32_t(plan.grid);   // one slot per CTA
                 sp.ovf_host = (tl_host_checks_i8 && !xch) ? ws->i8_ovf_dev : nullptr;
                 if (sp.nbest <= uint32_t(kI8BestM) * 32) {
-                    q1_survivor_kernel(d4)<<<plan.grid, plan.threads, plan.smem, stream>>>(sp);
+                    if (tl_stage_dep) {
+                        tl_stage_dep = false;
+                        sp.dep_inputs = 1u;
+                        CU_OK(launch_dependent(q1_survivor_kernel(d4), plan.grid, plan.threads, plan.smem, stream, sp));
+                    } else {
+                        q1_survivor_kernel(d4)<<<plan.grid, plan.threads, plan.smem, stream>>>(sp);
+                    }
                     LAUNCHED();
                     CU_OK(cudaGetLastError());
                     if (tl_host_checks_i8 && !xch) {   // the caller checks the pinned flag after its synchronise
@@ -1323,7 +1355,14 @@ static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, in
                 cfg.attrs = attr;
                 cfg.numAttrs = 1;
                 CU_OK(cudaLaunchKernelEx(&cfg, plan.fn, p));
+            } else if (tl_stage_dep && plan.q1) {
+                tl_stage_dep = false;
+                ws->prev_scan_big = false;
+                p.dep_inputs = 1u;
+                CU_OK(launch_dependent(plan.fn, plan.grid, plan.threads, plan.smem, stream, p));
+                p.dep_inputs = 0u;
             } else {
+                tl_stage_dep = false;   // any other kernel runs in plain stream order behind the pull
                 ws->prev_scan_big = false;
                 plan.fn<<<plan.grid, plan.threads, plan.smem, stream>>>(p);
             }
@@ -1658,6 +1697,9 @@ int mvdb_index_set_option(mvdb_index* ix, const char* name, int64_t value) {
     } else if (s == "coalesce_leaders") {
         if (value < 0 || value > 2) return fail(MVDB_ERR_ARG, "coalesce_leaders must be 0 (auto), 1 or 2");
         ix->co_max_leaders = int(value);
+    } else if (s == "host_path") {
+        if (value < 0 || value > 3) return fail(MVDB_ERR_ARG, "host_path is a bit set 0..3");
+        ix->host_path = int(value);
     } else if (s == "pdl") {
         ix->pdl = value != 0;
     } else if (s == "survivor_tail") {
@@ -2006,6 +2048,10 @@ static int mask_wait(const mvdb_mask* m, cudaStream_t st) {
 }
 
 // One host-buffer search on its own workspace: stage query (+mask), run, copy results back.
+// Host buffers in, host buffers out.  Single queries on the scan kernels (the latency path) avoid both copy-engine
+// transfers: the inputs are pulled from pinned memory by a small grid that the scan depends on programmatically
+// (pull_stage_kernel), and the kernels write the k results straight into pinned host memory.  Everything else
+// (query batches, large k) stages by cudaMemcpyAsync as before.  Option "host_path" switches the pieces off (A/B).
 static int search_host_direct(mvdb_index* ix, const float* q, int64_t nq, int64_t k, const uint8_t* mask,
                               uint64_t mask_rows, int normalize_queries, float* D, int64_t* I,
                               const mvdb_mask* handle = nullptr) {
@@ -2019,58 +2065,84 @@ static int search_host_direct(mvdb_index* ix, const float* q, int64_t nq, int64_
     std::shared_lock<std::shared_mutex> mv(ix->move_mu);
     cudaStream_t st = ws->stream;
     const size_t qn = size_t(nq) * ix->d, on = size_t(nq) * k;
-    RC_OK(grow_dev(&ws->q_dev, &ws->q_cap, qn));
-    RC_OK(grow_pin(&ws->q_pin, &ws->q_pin_cap, qn));
+    const bool single = nq == 1 && k <= ix->fused_k_max;   // answered by one scan kernel that writes its k results once
+    const bool zc_out = single && (ix->host_path & 1);
+    const bool pull = single && (ix->host_path & 2);
     // labels and distances share one buffer ([I | D]) so that the results come back in ONE transfer
     const size_t out_elems = on + (on + 1) / 2;
-    RC_OK(grow_dev(&ws->I_dev, &ws->I_cap, out_elems));
     RC_OK(grow_pin(&ws->I_pin, &ws->I_pin_cap, out_elems));
-    float* const D_dev = reinterpret_cast<float*>(ws->I_dev + on);
+    if (!zc_out) RC_OK(grow_dev(&ws->I_dev, &ws->I_cap, out_elems));
+    int64_t* const I_out = zc_out ? ws->I_pin : ws->I_dev;   // pinned host memory is device-addressable under UVA
+    float* const D_out = reinterpret_cast<float*>(I_out + on);
     const float* const D_pin = reinterpret_cast<const float*>(ws->I_pin + on);
+
+    // staging layout: [filter words | pad to 128 B | q] in ONE buffer, or the query alone
+    const bool stage_mask = !handle && mask != nullptr;
+    uint64_t rows = 0;
+    size_t words = 0, bytes = 0, q_at = 0;
+    if (stage_mask) {
+        rows = std::min<uint64_t>(mask_rows, ix->ntotal.load(std::memory_order_acquire));
+        mask_rows = rows;
+        words = (rows + 31) / 32;
+        bytes = (rows + 7) / 8;
+        q_at = align_up(words * 4, 128) / 4;
+    }
+    const size_t total = align_up(q_at + qn, 4);   // whole 16-byte vectors
+    uint32_t *pin = nullptr, *dev = nullptr;
+    if (stage_mask) {
+        RC_OK(grow_dev(&ws->mask_dev, &ws->mask_cap, total));
+        RC_OK(grow_pin(&ws->mask_pin, &ws->mask_pin_cap, total));
+        pin = ws->mask_pin;
+        dev = ws->mask_dev;
+    } else {
+        RC_OK(grow_dev(&ws->q_dev, &ws->q_cap, total));
+        RC_OK(grow_pin(&ws->q_pin, &ws->q_pin_cap, total));
+        pin = reinterpret_cast<uint32_t*>(ws->q_pin);
+        dev = reinterpret_cast<uint32_t*>(ws->q_dev);
+    }
+    auto stage_filter = [&]() {
+        if (!words) return;
+        pin[words - 1] = 0;
+        memcpy(pin, mask, bytes);
+        if (rows & 7) reinterpret_cast<uint8_t*>(pin)[bytes - 1] &= uint8_t((1u << (rows & 7)) - 1u);
+    };
     const uint32_t* mask_dev = nullptr;
-    const float* q_dev = ws->q_dev;
-    bool q_sent = false;
     if (handle) {
         mask_dev = handle->dev;      // already resident: no per-query upload
         mask_rows = handle->rows;
         RC_OK(mask_wait(handle, st));
-    } else if (mask) {
-        const uint64_t rows = std::min<uint64_t>(mask_rows, ix->ntotal.load(std::memory_order_acquire));
-        mask_rows = rows;
-        const size_t words = (rows + 31) / 32, bytes = (rows + 7) / 8;
-        // the filter and the queries travel as ONE transfer: [mask words | pad to 128 B | q]
-        const size_t q_at = align_up(words * 4, 128) / 4;
-        RC_OK(grow_dev(&ws->mask_dev, &ws->mask_cap, q_at + qn));
-        RC_OK(grow_pin(&ws->mask_pin, &ws->mask_pin_cap, q_at + qn));
-        if (words) {
-            ws->mask_pin[words - 1] = 0;
-            memcpy(ws->mask_pin, mask, bytes);
-            if (rows & 7) reinterpret_cast<uint8_t*>(ws->mask_pin)[bytes - 1] &= uint8_t((1u << (rows & 7)) - 1u);
-        }
-        memcpy(ws->mask_pin + q_at, q, qn * 4);
-        CU_OK(cudaMemcpyAsync(ws->mask_dev, ws->mask_pin, (q_at + qn) * 4, cudaMemcpyHostToDevice, st));
-        mask_dev = ws->mask_dev;
-        q_dev = reinterpret_cast<const float*>(ws->mask_dev + q_at);
-        q_sent = true;
+    } else if (stage_mask) {
+        mask_dev = dev;
     }
-    if (!q_sent) {
-        memcpy(ws->q_pin, q, qn * 4);
-        CU_OK(cudaMemcpyAsync(ws->q_dev, ws->q_pin, qn * 4, cudaMemcpyHostToDevice, st));
+    const float* q_dev = reinterpret_cast<const float*>(dev + q_at);
+    memcpy(pin + q_at, q, qn * 4);
+
+    stage_filter();
+    if (pull) {
+        const uint32_t nvec = uint32_t(total / 4);
+        const unsigned grid = unsigned(std::min<uint32_t>((nvec + 255) / 256, uint32_t(ix->sm_count) * 2));
+        pull_stage_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint4*>(pin), reinterpret_cast<uint4*>(dev), nvec);
+        LAUNCHED();
+        tl_stage_dep = true;
+    } else {
+        CU_OK(cudaMemcpyAsync(dev, pin, total * 4, cudaMemcpyHostToDevice, st));
     }
     tl_host_checks_i8 = true;
-    int src = run_search(ix, ws, q_dev, nq, k, mask_dev, mask_rows, normalize_queries, 0, D_dev, ws->I_dev, st, nullptr);
+    int src = run_search(ix, ws, q_dev, nq, k, mask_dev, mask_rows, normalize_queries, 0, D_out, I_out, st, nullptr);
     tl_host_checks_i8 = false;
+    tl_stage_dep = false;
     RC_OK(src);
-    CU_OK(cudaMemcpyAsync(ws->I_pin, ws->I_dev, on * 12, cudaMemcpyDeviceToHost, st));
+    if (!zc_out) CU_OK(cudaMemcpyAsync(ws->I_pin, ws->I_dev, on * 12, cudaMemcpyDeviceToHost, st));
     CU_OK(cudaStreamSynchronize(st));
     if (ws->i8_ovf_pin && *reinterpret_cast<volatile unsigned int*>(ws->i8_ovf_pin)) {
-        // int8 shadow mode: the survivor list overflowed -- this query is answered by the fp32 scan
+        // int8 shadow / survivor mode: the list overflowed -- this query is answered by the classic fp32 scan
+        // (its inputs are already staged in device memory)
         *ws->i8_ovf_pin = 0u;
         tl_force_scan = true;
-        src = run_search(ix, ws, q_dev, nq, k, mask_dev, mask_rows, normalize_queries, 0, D_dev, ws->I_dev, st, nullptr);
+        src = run_search(ix, ws, q_dev, nq, k, mask_dev, mask_rows, normalize_queries, 0, D_out, I_out, st, nullptr);
         tl_force_scan = false;
         RC_OK(src);
-        CU_OK(cudaMemcpyAsync(ws->I_pin, ws->I_dev, on * 12, cudaMemcpyDeviceToHost, st));
+        if (!zc_out) CU_OK(cudaMemcpyAsync(ws->I_pin, ws->I_dev, on * 12, cudaMemcpyDeviceToHost, st));
         CU_OK(cudaStreamSynchronize(st));
     }
     memcpy(D, D_pin, on * 4);

@@ -38,6 +38,8 @@ struct ScanParams {
     unsigned int* ticket;  // zero before launch; reset by the last CTA
     unsigned int* tile_ctr;  // dynamic tile scheduler (NULL = static round-robin); zero before launch, reset by the last CTA
     uint32_t pdl_early;      // trigger the dependent launch at kernel entry (only when one CTA fills an SM)
+    uint32_t dep_inputs;     // q and mask are being written by the grid this launch programmatically depends on
+                             // (the host path's staging pull): wait for it before the first read of either
     uint32_t static_iters;   // ... iterations of every CTA served by the static round-robin first
     uint32_t dyn_tile0;      // ... first tile of the dynamically claimed remainder (= static_iters * grid, multiple of kDynChunk)
     float* outD;           // [nq][k]
@@ -223,6 +225,7 @@ struct SmemHeader {
     uint32_t tile_of[16];  // dynamic tile scheduler: tile held by ring stage s (kNoTile = stop)
     uint32_t adm_of[16];   // ... and its admissible byte (mask & live)
     unsigned int surv_thr, surv_refreshes;   // survivor mode: CTA-wide threshold (ordered image) and how often it was recomputed
+    unsigned int tail_ns;                    // survivor mode, last CTA: length of the survivor list (read once, by the thread that resets it)
 };
 static_assert(sizeof(SmemHeader) <= 1024, "header too large");
 
@@ -610,6 +613,7 @@ __device__ __forceinline__ void scan_producer(const ScanParams& p, SmemHeader* h
         issue(blockIdx.x + it * G);
     }
     if (!dyn) return;
+    if (p.dep_inputs) pdl_wait();   // the filter words may still be on their way (the static phase reads none)
     uint32_t a0 = (c0 < nchunks) ? admissible_word(p, word0 + c0) : 0u;
     while (c0 < nchunks) {
         // every claim's result is consumed before this loop ends, so none is in flight when
@@ -733,20 +737,29 @@ __device__ __forceinline__ void finish_survivors(const ScanParams& p, uint8_t* s
     const int tid = cw * kWarp + lane, nthr = ncw * kWarp;
     __threadfence();
     named_bar_sync(1, nthr);
-    if (tid == 0) hdr->last_flag = (atomicAdd(&p.sctl->ticket, 1u) == G - 1);
+    if (tid == 0) {
+        const bool last = atomicAdd(&p.sctl->ticket, 1u) == G - 1;
+        hdr->last_flag = last;
+        if (last) {
+            // ONE thread reads the list length and resets the shared state (every other CTA is done with it); the
+            // others take the length from shared memory after the barrier -- a thread that read the global counter
+            // itself could see the reset value and disagree with its CTA about the list
+            __threadfence();
+            const unsigned int cnt_now = *reinterpret_cast<volatile unsigned int*>(&p.sctl->count);
+            hdr->tail_ns = cnt_now;
+            p.sctl->last_count = cnt_now;
+            p.sctl->count = 0u;
+            p.sctl->ticket = 0u;
+            if (p.tile_ctr) *p.tile_ctr = 0u;
+        }
+    }
     named_bar_sync(1, nthr);
     if (blockIdx.x == 0) trace_stamp(p, 6, cw, lane);
     if (!hdr->last_flag) return;
     trace_stamp(p, 8, cw, lane);
     __threadfence();
-    const unsigned int ns = *reinterpret_cast<volatile unsigned int*>(&p.sctl->count);
+    const unsigned int ns = hdr->tail_ns;
     for (uint32_t i = tid; i < p.nbest; i += nthr) p.best[i] = 0u;
-    if (tid == 0) {
-        p.sctl->last_count = ns;
-        p.sctl->count = 0u;
-        p.sctl->ticket = 0u;
-        if (p.tile_ctr) *p.tile_ctr = 0u;
-    }
     if (ns > p.surv_cap) {   // the classic scan answers instead (conditional launch behind this one, or the host re-runs it)
         if (tid == 0) {
             p.sctl->overflow = 1u;
@@ -815,6 +828,7 @@ __global__ void __launch_bounds__(kTma ? 288 : 256, kTma ? 1 : 2) scan_q1_kernel
     }
 
     if (blockIdx.x == 0) trace_stamp(p, 0, cw, lane);
+    if (p.dep_inputs) pdl_wait();   // query and filter staged by the preceding pull grid; the ring is filling meanwhile
     float4 qr[D4];
     load_query_regs<D4>(p.q, p.d, p.ld4, p.normalize_q, lane, qr);
     if (blockIdx.x == 0) trace_stamp(p, 1, cw, lane);

@@ -63,6 +63,7 @@ struct I8Params {
     uint32_t dyn_tile0;       // ... the tiles from here on are claimed from ctl->tile_ctr, one at a time (= one mask word)
     int d, ld4, ld8, k, stages;
     float max_norm;           // largest ||x_r|| stored in the index
+    uint32_t dep_inputs;      // q and mask are written by the grid this launch programmatically depends on (see ScanParams)
     const XchgDev* xchg;      // fused cross-GPU exchange (nullptr = single GPU): the last CTA sends this shard's k best
     uint64_t xchg_seq;        // to every rank and merges, exactly as the fp32 scan's tail does
 };
@@ -174,6 +175,7 @@ struct I8Header {
     unsigned int thr;       // CTA-wide copy of the threshold (ordered image), only ever raised
     unsigned int refreshes; // how many times any warp of the CTA has recomputed it
     int last_flag;
+    unsigned int tail_ns, tail_nc;   // last CTA: survivor / candidate counts (read once, by the thread that resets them)
     int cnts4[4];           // scratch of block_select_topk (tail)
     uint32_t tile_of[16];   // counter-claimed tiles: tile held by ring stage s (kNoTile = stop) ...
     uint32_t adm_of[16];    // ... and its admissible word (mask & live)
@@ -242,6 +244,7 @@ __global__ void __launch_bounds__(288, 1) scan_i8_kernel(const I8Params p) {
                 issue(blockIdx.x + it * G);
             }
             uint32_t a0[kI8DynChunk], a1[kI8DynChunk];
+            if (p.dep_inputs) pdl_wait();
 #pragma unroll
             for (uint32_t t = 0; t < kI8DynChunk; t++) a0[t] = (c0 < n_dyn) ? admissible(p.dyn_tile0 + c0 * kI8DynChunk + t) : 0u;
             while (c0 < n_dyn) {
@@ -278,6 +281,7 @@ __global__ void __launch_bounds__(288, 1) scan_i8_kernel(const I8Params p) {
 
     // ---- the normalised fp32 query goes to shared memory once (the exact re-scoring reads it) ----
     float4* qs = reinterpret_cast<float4*>(smem + p.q_off);
+    if (p.dep_inputs) pdl_wait();
     {
         bool scaled;
         const float inv = i8_query_scale(p.q, p.d, p.ld4, p.normalize_q, lane, &scaled);   // same value in every warp
@@ -481,23 +485,32 @@ __global__ void __launch_bounds__(288, 1) scan_i8_kernel(const I8Params p) {
     if (lane == 0 && n_cand) atomicAdd(&p.ctl->cand_cnt, n_cand);
     __threadfence();
     named_bar_sync(1, ncw * 32);
-    if (cw == 0 && lane == 0) hdr->last_flag = (atomicAdd(&p.ctl->ticket, 1u) == G - 1);
+    if (cw == 0 && lane == 0) {
+        const bool last = atomicAdd(&p.ctl->ticket, 1u) == G - 1;
+        hdr->last_flag = last;
+        if (last) {
+            // ONE thread reads the counts and leaves the shared state clean for the next search on this workspace
+            // (every other CTA is done with it); the rest of the CTA takes the counts from shared memory after the
+            // barrier -- a thread reading the global counters itself could already see them reset
+            __threadfence();
+            const unsigned int ns_now = *reinterpret_cast<volatile unsigned int*>(&p.ctl->surv_cnt);
+            const unsigned int nc_now = *reinterpret_cast<volatile unsigned int*>(&p.ctl->cand_cnt);
+            hdr->tail_ns = ns_now;
+            hdr->tail_nc = nc_now;
+            p.ctl->last_cand = nc_now;
+            p.ctl->last_surv = ns_now;
+            p.ctl->cand_cnt = 0u;
+            p.ctl->surv_cnt = 0u;
+            p.ctl->ticket = 0u;
+            p.ctl->tile_ctr = 0u;
+        }
+    }
     named_bar_sync(1, ncw * 32);
     if (!hdr->last_flag) return;
     __threadfence();
     const int tid = cw * kWarp + lane, nthr = ncw * kWarp;
-    const unsigned int ns = *reinterpret_cast<volatile unsigned int*>(&p.ctl->surv_cnt);
-    const unsigned int nc = *reinterpret_cast<volatile unsigned int*>(&p.ctl->cand_cnt);
-    // leave the shared state clean for the next search on this workspace (every other CTA is done with it)
+    const unsigned int ns = hdr->tail_ns;
     for (uint32_t i = tid; i < p.nbest; i += nthr) p.best[i] = 0u;
-    if (tid == 0) {
-        p.ctl->last_cand = nc;
-        p.ctl->last_surv = ns;
-        p.ctl->cand_cnt = 0u;
-        p.ctl->surv_cnt = 0u;
-        p.ctl->ticket = 0u;
-        p.ctl->tile_ctr = 0u;
-    }
     if (ns > kI8SurvCap) {
         if (tid == 0) {   // the fp32 scan answers this query instead (conditional launch behind us, or the host re-runs it)
             p.ctl->overflow = 1u;

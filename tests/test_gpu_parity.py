@@ -629,3 +629,68 @@ def test_survivor_tail_is_result_neutral(mv, n, d):
             assert np.array_equal(I.cpu().numpy(), Ir) and np.array_equal(D.cpu().numpy(), Dr)
     ws.close()
     eng.close()
+
+
+@pytest.mark.parametrize("n,d", [(3_000, 32), (150_000, 384), (400_000, 100)])
+def test_host_path_pieces_are_result_neutral(mv, n, d):
+    """Option "host_path": results written straight to pinned host memory, inputs pulled by a grid the scan depends
+    on programmatically -- every combination returns what the copy-engine path
+    returns, for unfiltered / per-call filter / resident handle searches, on the classic scan, the survivor-list scan
+    (k = 100), the int8 shadow scan, query batches and large k (which stay on the copy path), with a different filter
+    on every call (the staging buffer and the sequence word are reused) and from several host threads."""
+    import threading
+    x, q = _data(n, d, 12, seed=91)
+    eng = mv.FlatIPEngine(d)
+    eng.add(x)
+    rng = np.random.default_rng(4)
+    masks = [rng.random(n) < f for f in (0.5, 0.05, 0.9, 0.5, 0.001, 0.3)]
+    handle = eng.mask_handle(masks[0])
+
+    def sweep(shadow):
+        eng.set_option("scan_shadow", shadow)
+        out = []
+        for k in (1, 10, 100):
+            for i in range(6):
+                out.append(eng.search(q[i:i + 1], k))
+                out.append(eng.search(q[i:i + 1], k, mask=masks[i]))
+                out.append(eng.search(q[i:i + 1], k, mask=masks[i][:n - 37 * i]))   # mask_rows < ntotal
+                out.append(eng.search(q[i:i + 1], k, mask=handle))
+        out.append(eng.search(q[:5], 10, mask=masks[1]))     # batch: copy path
+        out.append(eng.search(q[:1], 300, mask=masks[2]))    # large k: copy path
+        return out
+
+    eng.set_option("coalesce", 0)
+    for shadow in (0, 1):
+        eng.set_option("host_path", 0)
+        ref = sweep(shadow)
+        for hp in (1, 2, 3):
+            eng.set_option("host_path", hp)
+            for rep in range(2):
+                got = sweep(shadow)
+                for j, ((Dr, Ir), (Dg, Ig)) in enumerate(zip(ref, got)):
+                    assert np.array_equal(Ir, Ig) and np.array_equal(Dr, Dg), (shadow, hp, rep, j)
+    eng.set_option("scan_shadow", 0)
+    _check(x, q[:1], 10, *eng.search(q[:1], 10))
+    _check(x, q[1:2], 10, *eng.search(q[1:2], 10, mask=masks[0]), adm=masks[0])
+    # several host threads, each with its own filter, default host path, coalescer on and off
+    eng.set_option("host_path", 0)
+    want = [eng.search(q[i:i + 1], 10, mask=masks[i % 6]) for i in range(12)]
+    eng.set_option("host_path", 3)
+    for co in (0, 1):
+        eng.set_option("coalesce", co)
+        errs = []
+
+        def worker(t):
+            try:
+                for rep in range(40):
+                    i = (t + rep) % 12
+                    Dg, Ig = eng.search(q[i:i + 1], 10, mask=masks[i % 6])
+                    assert np.array_equal(Ig, want[i][1]) and np.array_equal(Dg, want[i][0]), (co, t, rep)
+            except Exception as e:   # noqa: BLE001
+                errs.append(e)
+        ts = [threading.Thread(target=worker, args=(t,)) for t in range(6)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        assert not errs, errs[:1]
+    handle.close()
+    eng.close()

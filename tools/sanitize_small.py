@@ -10,12 +10,14 @@ n, d = 40_000, 128
 x = O.synth_rows(1, 0, n, d); O.normalize_L2(x)
 q = O.synth_rows(2, 0, 3, d); O.normalize_L2(q)
 eng = mv.FlatIPEngine(d); eng.set_option("coalesce", 0); eng.add(x)
+if os.environ.get("MVDB_HOST_PATH"): eng.set_option("host_path", int(os.environ["MVDB_HOST_PATH"]))
 adm = np.random.default_rng(0).random(n) < 0.4
 for shadow in (0, 1):
     eng.set_option("scan_shadow", shadow)
     for k in (1, 10, 16, 100):
         for m in (None, adm):
             D, I = eng.search(q[:1], k, mask=m)
+            assert I.max() < n, (shadow, k, m is not None, I, D)
             Dr, Ir = (O.search_flat_ip(x, q[:1], k) if m is None else O.search_masked(x, m, q[:1], k))
             assert O.classify_parity(x, q[:1], I, D, Ir, Dr, admissible=m)["ok"], (shadow, k)
 eng.remove_rows(np.arange(0, n, 7))
