@@ -510,7 +510,7 @@ def run_b200(args):
             "e2e": {"value": K / res["e2e_total"] * world, "unit": "queries/s",
                     "h2d_bytes_per_step": res["h2d"], "d2h_bytes_per_step": res["d2h"],
                     "p50_latency_us": res["e2e_p50"] * 1e6, "qps_global": K / res["e2e_total"],
-                    "api": ("mvdb_index_search (C ABI, host buffers; H2D query" + ("+mask" if res["filt"] else "") + ", D2H results inside)"
+                    "api": ("mvdb_index_search (C ABI, host buffers; every step the query" + ("+mask" if res["filt"] else "") + " cross PCIe from pinned host memory -- pulled by a grid the scan is launched behind -- and the results are written by the scan into pinned host memory and copied to the caller's arrays)"
                             if world == 1 else
                             "RowShardedIndex.search_packed: one pinned H2D -> scan + fused NVLink exchange + merge -> one D2H")},
             "gpu_launches": res["launches"],
