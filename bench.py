@@ -337,12 +337,25 @@ def measure_single_query(args, wl_name, rank, world, local, with_parity=True, cl
     # every step copies the query (d*4 B) and, with a filter, the packed bitmask (n/8 B) H2D and the
     # (D, I) result D2H inside the timed region.
     e2e_lat, e2e_res = [], []
+    # the step's inputs lie in pinned host memory (what the contract asks for): the library then pulls the filter
+    # from where it lies instead of staging it through its own pinned buffer first
+    keep_pinned = []
+    if world == 1:
+        tq = torch.from_numpy(q_host).pin_memory()
+        keep_pinned.append(tq)
+        q_e2e = tq.numpy()
+        if filt:
+            tm = torch.from_numpy(packed).pin_memory()
+            keep_pinned.append(tm)
+            packed = tm.numpy()
+    else:
+        q_e2e = q_host
 
     def e2e_step(i):
         if world == 1:
             if filt:
-                return eng.search(q_host[i:i + 1], k, mask=packed, mask_rows=n)
-            return eng.search(q_host[i:i + 1], k)
+                return eng.search(q_e2e[i:i + 1], k, mask=packed, mask_rows=n)
+            return eng.search(q_e2e[i:i + 1], k)
         # one pinned H2D ([filter words | query]), scan + fused exchange + merge, one D2H ([labels | distances])
         if filt:
             return index.search_packed(q_host[i:i + 1], k, words, n)

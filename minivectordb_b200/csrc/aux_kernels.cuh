@@ -17,11 +17,15 @@ namespace mvdb {
 // another host thread could stall behind the waiting grid while the waiting grid's own host thread queued behind
 // that call.)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pull_stage_kernel(const uint4* src, uint4* __restrict__ dst, uint32_t nvec) {
+// Vectors [0, n_direct) come from `direct` (a filter the caller already holds in pinned memory: no staging copy on the
+// host at all), the rest from the staging buffer `src` (same indexing as dst).
+__global__ void __launch_bounds__(256) pull_stage_kernel(const uint4* src, const uint4* direct, uint32_t n_direct,
+                                                         uint4* __restrict__ dst, uint32_t nvec) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) {
+        const uint4* from = (i < n_direct) ? direct + i : src + i;
         uint4 v;
-        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src + i) : "memory");
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(from) : "memory");
         dst[i] = v;
     }
 }

@@ -2100,10 +2100,21 @@ static int search_host_direct(mvdb_index* ix, const float* q, int64_t nq, int64_
         pin = reinterpret_cast<uint32_t*>(ws->q_pin);
         dev = reinterpret_cast<uint32_t*>(ws->q_dev);
     }
+    // A filter the caller already keeps in pinned (page-locked, device-addressable) memory is pulled from where it
+    // lies: only its last partial 16-byte vector -- whose spare bits must read as zero -- goes through the staging buffer.
+    size_t direct_vecs = 0;
+    if (pull && stage_mask && bytes >= 4096 && (reinterpret_cast<uintptr_t>(mask) & 15) == 0) {
+        cudaPointerAttributes at = {};
+        if (cudaPointerGetAttributes(&at, mask) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer == mask)
+            direct_vecs = ((rows & 7) ? bytes - 1 : bytes) / 16;   // a last byte with spare bits is cleaned in the staging buffer
+        else
+            (void)cudaGetLastError();
+    }
     auto stage_filter = [&]() {
         if (!words) return;
         pin[words - 1] = 0;
-        memcpy(pin, mask, bytes);
+        const size_t skip = direct_vecs * 16;
+        memcpy(reinterpret_cast<uint8_t*>(pin) + skip, mask + skip, bytes - skip);
         if (rows & 7) reinterpret_cast<uint8_t*>(pin)[bytes - 1] &= uint8_t((1u << (rows & 7)) - 1u);
     };
     const uint32_t* mask_dev = nullptr;
@@ -2121,7 +2132,8 @@ static int search_host_direct(mvdb_index* ix, const float* q, int64_t nq, int64_
     if (pull) {
         const uint32_t nvec = uint32_t(total / 4);
         const unsigned grid = unsigned(std::min<uint32_t>((nvec + 255) / 256, uint32_t(ix->sm_count) * 2));
-        pull_stage_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint4*>(pin), reinterpret_cast<uint4*>(dev), nvec);
+        pull_stage_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint4*>(pin), reinterpret_cast<const uint4*>(mask),
+                                              uint32_t(direct_vecs), reinterpret_cast<uint4*>(dev), nvec);
         LAUNCHED();
         tl_stage_dep = true;
     } else {

@@ -672,6 +672,22 @@ def test_host_path_pieces_are_result_neutral(mv, n, d):
     eng.set_option("scan_shadow", 0)
     _check(x, q[:1], 10, *eng.search(q[:1], 10))
     _check(x, q[1:2], 10, *eng.search(q[1:2], 10, mask=masks[0]), adm=masks[0])
+    # a filter the caller keeps in pinned memory is pulled from where it lies (whole 16-byte vectors; the last partial
+    # one and a last byte with spare bits still go through the staging buffer)
+    import torch
+    eng.set_option("host_path", 3)
+    for rows in (n, n - 3, n - 64, n - 129):
+        pm = mv.pack_mask(masks[0][:rows])
+        tp = torch.from_numpy(pm).pin_memory()
+        for k in (10, 100):
+            Dr, Ir = eng.search(q[:1], k, mask=pm, mask_rows=rows)
+            Dg, Ig = eng.search(q[:1], k, mask=tp.numpy(), mask_rows=rows)
+            assert np.array_equal(Ir, Ig) and np.array_equal(Dr, Dg), (rows, k)
+            if len(pm) > 17:   # misaligned view of pinned memory: staged like any other buffer
+                off = np.concatenate([np.zeros(1, np.uint8), pm])
+                to = torch.from_numpy(off).pin_memory()
+                Dg, Ig = eng.search(q[:1], k, mask=to.numpy()[1:], mask_rows=rows)
+                assert np.array_equal(Ir, Ig) and np.array_equal(Dr, Dg), (rows, k, "misaligned")
     # several host threads, each with its own filter, default host path, coalescer on and off
     eng.set_option("host_path", 0)
     want = [eng.search(q[i:i + 1], 10, mask=masks[i % 6]) for i in range(12)]
