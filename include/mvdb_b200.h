@@ -87,7 +87,9 @@ int mvdb_index_reset(mvdb_index* ix);
  *                   are pulled from pinned host memory by a small grid that the scan is launched behind as
  *                   a programmatic dependent (the scan's start-up and ring fill overlap the PCIe round
  *                   trip; no host-to-device copy).  0 = cudaMemcpyAsync both ways.  Results are identical
- *                   for every value.
+ *                   for every value.  With bit 2, a filter that the caller holds in page-locked memory
+ *                   (cudaHostAlloc / cudaHostRegister, 16-byte aligned) is pulled from where it lies: no
+ *                   staging copy on the host.
  *   "pdl"           (default 0) launch the scans of mvdb_index_search_device / _search_exchange
  *                   with programmatic stream serialization: searches enqueued back to back on
  *                   one stream overlap the serial tail of one (last-CTA merge, cross-GPU
