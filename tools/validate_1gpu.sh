@@ -1,9 +1,11 @@
-# One-GPU validation of the tree (run under gpurun): the whole -m gpu suite, memcheck + synccheck on the small
-# end-to-end script, and the k = 10 / 100 fp32 vs int8-shadow timing at the C2 shape.
+# One-GPU validation of the tree (run under gpurun): the whole -m gpu suite, memcheck + synccheck + initcheck on the two
+# small end-to-end scripts, and the k = 10 / 100 fp32 vs int8-shadow timing at the C2 shape.
 timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-for tool in memcheck synccheck; do
-  timeout 420 compute-sanitizer --tool $tool --error-exitcode 7 python tools/sanitize_small.py > gpurun_out/sanitize_$tool.log 2>&1
-  echo "$tool rc=$? $(grep 'ERROR SUMMARY' gpurun_out/sanitize_$tool.log | head -1)"
+for tool in memcheck synccheck initcheck; do
+  for script in small tails; do
+    timeout 420 compute-sanitizer --tool $tool --error-exitcode 7 python tools/sanitize_$script.py > gpurun_out/sanitize_${script}_$tool.log 2>&1
+    echo "$tool $script rc=$? $(grep 'ERROR SUMMARY' gpurun_out/sanitize_${script}_$tool.log | head -1) $(grep -c 'sanitize_.* ok' gpurun_out/sanitize_${script}_$tool.log)"
+  done
 done
 python - <<PY
 import sys, json, numpy as np, torch
