@@ -45,6 +45,12 @@ except Exception:  # pragma: no cover - exercised in this image
 
     def partial_ratio(a: str, b: str) -> float:
         a, b = str(a), str(b)
+        if len(a) == len(b) and a != b:
+            # equal lengths: either string may be the one that is windowed; the scorer tries both and keeps the better
+            return max(_partial_ratio_windows(a, b), _partial_ratio_windows(b, a))
+        return _partial_ratio_windows(a, b)
+
+    def _partial_ratio_windows(a: str, b: str) -> float:
         short, long_ = (a, b) if len(a) <= len(b) else (b, a)
         m = len(short)
         if m == 0:

@@ -150,3 +150,51 @@ def test_persist_is_consistent_under_concurrent_stores(classes, tmp_path):
         stop.set()
         t.join()
     assert len(classes[0](storage_file=path).id_map) == n
+
+
+def test_partial_ratio_known_answers_and_definition():
+    """The reference reranks with thefuzz.fuzz.partial_ratio (VDB:5, 411); the package is not installable here, so
+    the restatement is pinned to (a) the answers thefuzz's README publishes and (b) the definition it restates: the
+    best Indel similarity 100 * 2*LCS / (len(a) + len(w)) of the shorter string against every window w of the longer
+    one (full-length windows plus the shorter ones at both ends; equal lengths: either string windowed), rounded to an
+    int -- recomputed here by brute force."""
+    import itertools
+    import random
+    from minivectordb_b200 import rerank
+
+    if rerank._fuzz is not None:
+        pytest.skip("thefuzz itself is installed: the restatement is not in use")
+    # published: thefuzz README ("Simple Ratio" / "Partial Ratio")
+    assert round(rerank._ratio("this is a test", "this is a test!")) == 97
+    assert rerank.partial_ratio("this is a test", "this is a test!") == 100
+    assert rerank.partial_ratio("YANKEES", "NEW YORK YANKEES") == 100
+    # conventions of the scorer underneath
+    assert rerank.partial_ratio("", "") == 100 and rerank.partial_ratio("abc", "") == 0 and rerank.partial_ratio("", "abc") == 0
+
+    def lcs(a, b):   # textbook DP
+        t = [[0] * (len(b) + 1) for _ in range(len(a) + 1)]
+        for i, j in itertools.product(range(len(a)), range(len(b))):
+            t[i + 1][j + 1] = t[i][j] + 1 if a[i] == b[j] else max(t[i][j + 1], t[i + 1][j])
+        return t[len(a)][len(b)]
+
+    def brute(a, b):
+        if len(a) == len(b):   # equal lengths: both strings are tried as the windowed one
+            return max(brute1(a, b), brute1(b, a))
+        return brute1(a, b)
+
+    def brute1(a, b):
+        s, l = (a, b) if len(a) <= len(b) else (b, a)
+        best = 0.0
+        for lo in range(len(l)):
+            for hi in range(lo + 1, min(len(l), lo + len(s)) + 1):
+                if hi - lo < len(s) and lo != 0 and hi != len(l):
+                    continue   # shorter windows only where they touch an end of the longer string
+                best = max(best, 100.0 * 2 * lcs(s, l[lo:hi]) / (len(s) + hi - lo))
+        return int(round(best))
+
+    rng = random.Random(5)
+    for _ in range(300):
+        a = "".join(rng.choice("abc d") for _ in range(rng.randint(1, 9)))
+        b = "".join(rng.choice("abc d") for _ in range(rng.randint(1, 14)))
+        assert rerank.partial_ratio(a, b) == brute(a, b) == rerank.partial_ratio(b, a), (a, b)
+    assert rerank.partial_ratio("hello world", "say hello world to them") == 100   # a substring scores 100
