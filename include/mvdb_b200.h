@@ -81,6 +81,10 @@ int mvdb_index_reset(mvdb_index* ix);
  *   "scan_variant"  MVDB_SCAN_*          "fused_k_max"  largest k served by the fused select
  *   "grid_ctas"     CTAs of the scan kernel (0 = one per SM)
  *   "consumer_warps" consumer warps per CTA of the TMA scan (0 = auto)
+ *   "large_k_fast"  (default 1) host-buffer searches with fused_k_max < k <= 8192: select the k best by two
+ *                   12-bit histogram passes over the score images, one collect and one single-CTA sort (5
+ *                   launches per query) instead of the 8-pass radix select (22 launches); a query whose k-th
+ *                   score is shared by more than 16384 rows falls back to the radix select.  Same results.
  *   "host_path"     (default 3) bit set for single-query searches with HOST buffers (mvdb_index_search,
  *                   _search_with_mask; k <= fused_k_max): 1 = the kernels write the k results straight
  *                   into pinned host memory (no device-to-host copy), 2 = the query and a per-call filter

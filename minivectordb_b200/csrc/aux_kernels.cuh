@@ -336,6 +336,145 @@ __global__ void keys_to_results_kernel(const uint64_t* keys, uint32_t navail, in
 }
 
 // ---------------------------------------------------------------------------
+// Fast select for 128 < k <= 8192 (host-buffer callers): two 12-bit digits of the score image fix a 24-bit
+// prefix T below which no row can be among the k best; every row at or above it (k plus the few that share the k-th
+// row's 24-bit prefix) is collected and ONE CTA sorts that list and writes the results.  5 launches per query (scan,
+// two histograms, collect, sort) instead of the radix select's 22 -- the latter stays as the fallback for the case
+// this one cannot bound: more than kFselCap rows at or above T (thousands of exact ties around the k-th score); the
+// sort kernel then raises a flag and the host re-runs the query.  Every CTA derives the digits itself from the global
+// histograms (a 4096-bin suffix scan), so no single-thread "pick" launches sit between the passes.
+// ---------------------------------------------------------------------------
+constexpr uint32_t kFselBins = 4096;
+constexpr uint32_t kFselCap = 16384;
+struct FselState {
+    unsigned int h0[kFselBins];   // rows per top-12-bit digit of the score image (empty rows, image 0, are not counted)
+    unsigned int h1[kFselBins];   // rows per next-12-bit digit among the rows whose top digit is the selected one
+    unsigned int out_count;
+    unsigned int overflow;
+};
+
+// The digit that holds the rem-th largest row (counting from the top bin down) and the rank left inside it.  All
+// threads of the block call this (blockDim.x == 512, 8 bins per thread); fewer than rem rows: digit 0, rank clamps.
+__device__ __forceinline__ uint32_t fsel_find_digit(const unsigned int* hist, uint32_t rem, uint32_t* rem_out, unsigned int* sh) {
+    const int t = threadIdx.x;   // thread t owns the bins 4095 - 8t ... 4088 - 8t
+    unsigned int c[8], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        c[j] = __ldcg(hist + (kFselBins - 1 - (8 * t + j)));
+        sum += c[j];
+    }
+    sh[t] = sum;
+    __syncthreads();
+    for (int o = 1; o < 512; o <<= 1) {   // inclusive scan over the threads
+        const unsigned int v = (t >= o) ? sh[t - o] : 0u;
+        __syncthreads();
+        sh[t] += v;
+        __syncthreads();
+    }
+    const unsigned int incl = sh[t], excl = incl - sum, total = sh[511];
+    __syncthreads();
+    if (t == 0) {
+        sh[0] = 0u;     // digit
+        sh[1] = rem > total ? 0xFFFFFFFFu : 0u;   // rank (beyond every count: the next level picks digit 0 too), overwritten below when it exists
+    }
+    __syncthreads();
+    if (excl < rem && rem <= incl) {
+        unsigned int r = rem - excl;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (r <= c[j]) {
+                sh[0] = kFselBins - 1 - (8 * t + j);
+                sh[1] = r;
+                break;
+            }
+            r -= c[j];
+        }
+    }
+    __syncthreads();
+    const uint32_t digit = sh[0];
+    *rem_out = sh[1];
+    __syncthreads();
+    return digit;
+}
+
+// level 0: histogram of the top digit; level 1: of the second digit among the rows of the selected top digit
+__global__ void __launch_bounds__(512) fsel_hist_kernel(const uint32_t* __restrict__ ord, uint32_t n, FselState* st, uint32_t k,
+                                                        int level) {
+    __shared__ unsigned int h[kFselBins];
+    __shared__ unsigned int sh[512];
+    for (uint32_t i = threadIdx.x; i < kFselBins; i += blockDim.x) h[i] = 0u;
+    uint32_t d0 = 0, rem = 0;
+    if (level == 1) d0 = fsel_find_digit(st->h0, k, &rem, sh);
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t o = ord[i];
+        if (o == 0u) continue;
+        if (level == 0) atomicAdd(&h[o >> 20], 1u);
+        else if ((o >> 20) == d0) atomicAdd(&h[(o >> 8) & 0xFFFu], 1u);
+    }
+    __syncthreads();
+    unsigned int* dst = level == 0 ? st->h0 : st->h1;
+    for (uint32_t i = threadIdx.x; i < kFselBins; i += blockDim.x)
+        if (h[i]) atomicAdd(&dst[i], h[i]);
+}
+
+// every row whose 24-bit prefix is at or above the selected one
+__global__ void __launch_bounds__(512) fsel_collect_kernel(const uint32_t* __restrict__ ord, uint32_t n, FselState* st, uint32_t k,
+                                                           uint64_t* out) {
+    __shared__ unsigned int sh[512];
+    uint32_t rem = 0, rem2 = 0;
+    const uint32_t d0 = fsel_find_digit(st->h0, k, &rem, sh);
+    const uint32_t d1 = fsel_find_digit(st->h1, rem, &rem2, sh);
+    const uint32_t thr = (d0 << 12) | d1;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t o = ord[i];
+        if (o != 0u && (o >> 8) >= thr) {
+            const unsigned int pos = atomicAdd(&st->out_count, 1u);
+            if (pos < kFselCap) out[pos] = ord_key(o, i);
+        }
+    }
+}
+
+// one CTA: sort the collected keys, write (D, I), leave the state clean for the next query
+__global__ void __launch_bounds__(1024) fsel_sort_results_kernel(const uint64_t* __restrict__ keys, FselState* st, int64_t k, float* D,
+                                                                  int64_t* I, int64_t label_offset, unsigned int* ovf_host) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint64_t* a = reinterpret_cast<uint64_t*>(smem);
+    const unsigned int cnt = st->out_count;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < kFselBins; i += blockDim.x) {
+        st->h0[i] = 0u;
+        st->h1[i] = 0u;
+    }
+    if (threadIdx.x == 0) st->out_count = 0u;
+    if (cnt > kFselCap) {   // too many rows share the k-th row's prefix: the radix select answers (the host re-runs the query)
+        if (threadIdx.x == 0) {
+            st->overflow = 1u;
+            if (ovf_host) {
+                *reinterpret_cast<volatile unsigned int*>(ovf_host) = 1u;
+                __threadfence_system();
+            }
+        }
+        return;
+    }
+    uint32_t npad = 64;
+    while (npad < cnt) npad <<= 1;
+    for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x) a[i] = (i < cnt) ? keys[i] : kEmptyKey;
+    __syncthreads();
+    bitonic_sort_desc(a, int(npad), int(threadIdx.x), int(blockDim.x), BlockSyncer());
+    for (int64_t i = threadIdx.x; i < k; i += blockDim.x) {
+        const uint64_t key = (i < int64_t(cnt)) ? a[i] : kEmptyKey;
+        if (key == kEmptyKey) {
+            D[i] = -FLT_MAX;
+            I[i] = -1;
+        } else {
+            D[i] = key_score(key);
+            I[i] = int64_t(key_row(key)) + label_offset;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // shard merge (sharded path): per query, merge nparts best-first lists.
 // Key = (score image, ~position) with position = part * k + i, so equal scores
 // keep shard order then in-shard order (= ascending global row when shards

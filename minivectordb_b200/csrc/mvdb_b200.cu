@@ -291,6 +291,7 @@ struct mvdb_workspace {
     uint32_t* all_ord = nullptr;
     size_t all_ord_cap = 0;
     RadixState* radix = nullptr;
+    FselState* fsel = nullptr;     // fast select for 128 < k <= 8192 on the host path (aux_kernels.cuh)
     uint64_t* keys = nullptr;
     size_t keys_cap = 0;
     // batched tensor-core path
@@ -427,6 +428,7 @@ struct mvdb_index {
     int gemm_debug = 0;            // GemmParams::debug experiments (results are garbage when non-zero)
     unsigned long long* gemm_prof_dev = nullptr;   // debug wait-cycle counters of the GEMM kernels (option "gemm_prof"), [256][8]
     int pdl = 0;                   // search_device: programmatic dependent launch of back-to-back scans (opt-in)
+    int large_k_fast = 1;          // host-buffer searches with 128 < k <= 8192: histogram select (5 launches) instead of the radix select (22)
     int host_path = 3;             // host-buffer single queries: 1 results written straight to pinned host memory, 2 inputs
                                    // pulled by a grid the scan depends on programmatically
     int dyn_tiles = 15;            // % of the tiles the TMA scan claims from a global counter (rest: static round-robin)
@@ -1383,6 +1385,18 @@ static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, in
     p.k = 1;
     const int hist_grid = int(std::min<uint64_t>(uint64_t(ix->sm_count) * 4, (uint64_t(n) + 511) / 512));
     ws->prev_scan_big = false;
+    // host-buffer callers (they synchronise and can re-run a query): two 12-bit histogram passes, collect, one sort
+    // -- 5 launches instead of 22; the radix select below is the fallback when too many rows tie around the k-th
+    const bool fsel = tl_host_checks_i8 && !tl_force_scan && !xch && ix->large_k_fast && kk <= 8192;
+    if (fsel) {
+        RC_OK(ws_overflow_flag(ws));
+        if (!ws->fsel) {
+            CU_OK(cudaMalloc(&ws->fsel, sizeof(FselState)));
+            CU_OK(cudaMemsetAsync(ws->fsel, 0, sizeof(FselState), stream));
+        }
+        RC_OK(grow_dev(&ws->keys, &ws->keys_cap, size_t(kFselCap)));
+        CU_OK(cudaFuncSetAttribute(fsel_sort_results_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kFselCap * 8)));
+    }
     for (int64_t qi = 0; qi < nq; qi++) {
         ScanPlan plan;
         RC_OK(plan_scan(ix, p, 1, &plan));
@@ -1393,6 +1407,19 @@ static int run_search(mvdb_index* ix, mvdb_workspace* ws, const float* q_dev, in
         p.outI = nullptr;
         plan.fn<<<plan.grid, plan.threads, plan.smem, stream>>>(p);
         LAUNCHED();
+        if (fsel) {
+            fsel_hist_kernel<<<hist_grid, 512, 0, stream>>>(ws->all_ord, n, ws->fsel, uint32_t(kk), 0);
+            LAUNCHED();
+            fsel_hist_kernel<<<hist_grid, 512, 0, stream>>>(ws->all_ord, n, ws->fsel, uint32_t(kk), 1);
+            LAUNCHED();
+            fsel_collect_kernel<<<hist_grid, 512, 0, stream>>>(ws->all_ord, n, ws->fsel, uint32_t(kk), ws->keys);
+            LAUNCHED();
+            fsel_sort_results_kernel<<<1, 1024, size_t(kFselCap) * 8, stream>>>(ws->keys, ws->fsel, k, D_dev + qi * k, I_dev + qi * k,
+                                                                              label_offset, ws->i8_ovf_dev);
+            LAUNCHED();
+            CU_OK(cudaGetLastError());
+            continue;
+        }
         radix_init_kernel<<<1, 256, 0, stream>>>(ws->radix, kk);
         LAUNCHED();
         for (int shift = 56; shift >= 0; shift -= 8) {
@@ -1432,6 +1459,7 @@ static void ws_release(mvdb_workspace* ws) {   // device / pinned memory and the
     cudaFree(ws->ticket);
     cudaFree(ws->all_ord);
     cudaFree(ws->radix);
+    cudaFree(ws->fsel);
     cudaFree(ws->keys);
     cudaFree(ws->b_qn);
     cudaFree(ws->b_qnorm);
@@ -1697,6 +1725,8 @@ int mvdb_index_set_option(mvdb_index* ix, const char* name, int64_t value) {
     } else if (s == "coalesce_leaders") {
         if (value < 0 || value > 2) return fail(MVDB_ERR_ARG, "coalesce_leaders must be 0 (auto), 1 or 2");
         ix->co_max_leaders = int(value);
+    } else if (s == "large_k_fast") {
+        ix->large_k_fast = value != 0;
     } else if (s == "host_path") {
         if (value < 0 || value > 3) return fail(MVDB_ERR_ARG, "host_path is a bit set 0..3");
         ix->host_path = int(value);

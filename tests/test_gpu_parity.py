@@ -710,3 +710,51 @@ def test_host_path_pieces_are_result_neutral(mv, n, d):
         assert not errs, errs[:1]
     handle.close()
     eng.close()
+
+
+@pytest.mark.parametrize("n,d", [(6_000, 64), (250_000, 128)])
+def test_large_k_fast_select_equals_the_radix_select(mv, n, d):
+    """Host-buffer searches with 128 < k <= 8192 take the histogram select (two 12-bit digit passes, collect, one
+    sort); it must return exactly what the radix select returns -- with filters (incl. fewer admissible rows than k),
+    tombstones, several queries per call, k beyond its range, and a crowd of exact ties around the k-th score that
+    overflows its list (the host then re-runs the query on the radix select)."""
+    x, q = _data(n, d, 3, seed=17)
+    eng = mv.FlatIPEngine(d)
+    eng.set_option("coalesce", 0)
+    eng.add(x)
+    rng = np.random.default_rng(3)
+    masks = [None, rng.random(n) < 0.5, rng.random(n) < 0.01]
+    eng.remove_rows(np.arange(5, n, 11))
+
+    def sweep():
+        out = []
+        for k in (129, 500, 1000, 4097, 8192, 9000):
+            if k > n:
+                continue
+            for m in masks:
+                out.append(eng.search(q[:1], k, mask=m))
+            out.append(eng.search(q, k, mask=masks[1]))
+        return out
+
+    eng.set_option("large_k_fast", 0)
+    ref = sweep()
+    eng.set_option("large_k_fast", 1)
+    for rep in range(2):
+        for j, ((Dr, Ir), (Dg, Ig)) in enumerate(zip(ref, sweep())):
+            assert np.array_equal(Ir, Ig) and np.array_equal(Dr, Dg), (rep, j)
+    live = np.ones(n, bool); live[5::11] = False
+    _check(x, q[:1], 500, *eng.search(q[:1], 500), adm=live)
+    # 20 000 copies of one row: every one of them shares the k-th row's prefix -> list overflow -> radix select
+    eng.add(np.repeat(x[3:4], 20_000, axis=0))
+    for k in (200, 3000):
+        eng.set_option("large_k_fast", 0)
+        Dr, Ir = eng.search(x[3:4], k)
+        eng.set_option("large_k_fast", 1)
+        for _ in range(2):
+            Dg, Ig = eng.search(x[3:4], k)
+            assert np.array_equal(Ir, Ig) and np.array_equal(Dr, Dg), k
+        Dg, Ig = eng.search(q[:1], k)        # and the next ordinary query finds the state clean
+        eng.set_option("large_k_fast", 0)
+        Dr, Ir = eng.search(q[:1], k)
+        assert np.array_equal(Ir, Ig) and np.array_equal(Dr, Dg), k
+    eng.close()

@@ -30,6 +30,20 @@ for n, d in ((1_000_000, 384), (100_000, 512)):
         assert np.all(np.diff(Dh) <= 0) and len(set(Ih.tolist())) == k
         rec = dict(n=n, d=d, k=k, us_per_search=round(t, 1), launches_per_search=round(launches, 1),
                    stream_roofline_frac=round(alg / (t * 1e-6) / 6452.8e9, 3))
+        # host-buffer API (mvdb_index_search), host to host: for k > 128 the histogram select against the radix select
+        import time
+        qh = q.cpu().numpy()
+        for fast in ((0, 1) if k > 128 else (1,)):
+            eng.set_option("large_k_fast", fast)
+            for i in range(4): eng.search(qh[i:i + 1], k)
+            lat = []
+            l0 = N.lib().mvdb_launch_count()
+            for i in range(32):
+                a = time.perf_counter(); r = eng.search(qh[i % 16:i % 16 + 1], k); lat.append(time.perf_counter() - a)
+            rec["host_us_fast%d" % fast] = round(float(np.median(lat)) * 1e6, 1)
+            rec["host_launches_fast%d" % fast] = round((N.lib().mvdb_launch_count() - l0) / 32, 1)
+            if fast == 0: ref = r
+            elif k > 128: assert np.array_equal(ref[1], r[1]) and np.array_equal(ref[0], r[0])
         out.append(rec); print(json.dumps(rec), flush=True)
     ws.close(); eng.close()
 os.makedirs("gpurun_out", exist_ok=True)
