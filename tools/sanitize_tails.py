@@ -1,6 +1,6 @@
 """Second compute-sanitizer exercise (memcheck / synccheck / initcheck): the block-wide selection tails of the
 survivor-list scan (32 < k <= 128) and of the int8 shadow scan, incl. list overflow (thousands of exact ties ->
-classic-scan fallback), the fused exchange behind those tails (3-shard group on one device), and the host path
+classic-scan fallback), the fused exchange behind those tails (3-shard group on one device), the histogram select for k > 128, and the host path
 (inputs pulled by a grid the scan depends on programmatically, pinned caller filter, results in pinned memory)."""
 import os, sys
 import numpy as np
@@ -30,6 +30,15 @@ for shadow in (0, 1):
     for k in (10, 100):
         D, I = eng.search(x[7:8], k)
         assert I.max() < n + 9000 and np.all(D > 0.999), (shadow, k)
+# k > 128 on the host path: histogram select against the radix select, incl. its overflow (9000 ties is below its cap,
+# 20000 more are not)
+for extra in (0, 20000):
+    if extra: eng.add(np.repeat(x[7:8], extra, axis=0))
+    for qq in (q[:1], x[7:8]):
+        for k in (200, 1000):
+            eng.set_option("large_k_fast", 0); Dr, Ir = eng.search(qq, k)
+            eng.set_option("large_k_fast", 1); Dg, Ig = eng.search(qq, k)
+            assert np.array_equal(Ir, Ig) and np.array_equal(Dr, Dg), (extra, k)
 eng.close()
 # fused exchange behind the selection tails
 for shadow in (0, 1):
